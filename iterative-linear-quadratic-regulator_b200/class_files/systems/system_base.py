@@ -1,0 +1,176 @@
+"""System base class -- drop-in for the reference's class_files/systems/system_base.py.
+
+The reference builds a discrete step from `_f_cont_fcn` with one of four integrators and gets
+every derivative from JAX autodiff (system_base.py:25-251).  Here the shipped systems are
+device models inside libilqr_b200.so: the same twelve public callables
+(`f_fcn, f_x_fcn, f_u_fcn, l_fcn, l_x_fcn, l_u_fcn, l_xx_fcn, l_uu_fcn, l_ux_fcn, l_f_fcn,
+l_f_x_fcn, l_f_xx_fcn`, system_base.py:223-251) evaluate on the GPU with analytic Jacobians,
+for one point (x (n,), u (m,)) exactly as in the reference, or for a batch of points
+(x (P,n), u (P,m)).
+
+A subclass describes itself to the kernels through `_device_model()`; arbitrary Python
+`_f_cont_fcn` bodies cannot run inside a CUDA kernel (NVRTC codegen, is
+future work), so a subclass without a device model raises NotImplementedError when used.
+"""
+import ctypes as C
+from abc import ABC
+
+import numpy as np
+import torch
+
+from .. import _cabi
+from .. import _device as D
+
+_SUPPORTED = ("rk4", "midpoint", "euler", "backward_euler")
+
+
+def _square(M, k, name):
+    M = np.asarray(M.detach().cpu().numpy() if isinstance(M, torch.Tensor) else M, dtype=np.float64)
+    if M.ndim == 0:
+        M = M.reshape(1, 1)
+    if M.shape != (k, k):
+        raise ValueError(f"{name} must have shape {(k, k)}, but got {M.shape}")
+    return M
+
+
+class System(ABC):
+    def __init__(self, n_x: int, n_u: int, dt: float, use_jit: bool = True, integrator: str = "rk4",
+                 dtype: str = "float64"):
+        self.n_x = n_x
+        self.n_u = n_u
+        self.dt = dt
+        self.use_jit = use_jit          # kept for signature parity; kernels are always compiled
+        if integrator not in _SUPPORTED:
+            # same message as the reference, system_base.py:197-198
+            raise ValueError(f"Unknown integrator: '{integrator}'. Supported: 'rk4', 'midpoint', 'euler', "
+                             f"'backward_euler'.")
+        if dtype not in _cabi.DTYPES:
+            raise ValueError(f"dtype must be 'float64' or 'float32', got {dtype!r}")
+        self.integrator = integrator
+        self.dtype = dtype
+        self._point_handles = {}
+        # public callables, same names as system_base.py:223-251
+        self.f_fcn = self._f
+        self.f_x_fcn = lambda x, u: self._jac(x, u)[0]
+        self.f_u_fcn = lambda x, u: self._jac(x, u)[1]
+        self.l_fcn = lambda x, u: self._cost(x, u, "l")
+        self.l_x_fcn = lambda x, u: self._cost(x, u, "lx")
+        self.l_u_fcn = lambda x, u: self._cost(x, u, "lu")
+        self.l_xx_fcn = lambda x, u: self._cost(x, u, "lxx")
+        self.l_uu_fcn = lambda x, u: self._cost(x, u, "luu")
+        self.l_ux_fcn = lambda x, u: self._cost(x, u, "lux")
+        self.l_f_fcn = lambda x: self._cost(x, None, "lf")
+        self.l_f_x_fcn = lambda x: self._cost(x, None, "lfx")
+        self.l_f_xx_fcn = lambda x: self._cost(x, None, "lfxx")
+
+    # ---- what a subclass provides -----------------------------------------------------
+    def _device_model(self):
+        """-> (model name in _cabi.MODELS, list of physical parameters in ilqr_problem_t.phys order)"""
+        raise NotImplementedError(
+            f"{type(self).__name__} has no device model: only the shipped systems (MyPendulum, "
+            "MyDoublePendulum, MyUADoublePendulum) run on the GPU; user-defined _f_cont_fcn bodies "
+            "are not supported by this build.")
+
+    def _cost_weights(self):
+        return self.Q, self.R, self.Q_f, self.x_target
+
+    # ---- problem struct ---------------------------------------------------------------
+    def make_problem(self, N, B, tol=1e-5, maxiter=100, alpha_factor=0.5, min_alpha=1e-8, n_alpha=10):
+        model, phys = self._device_model()
+        n, m = self.n_x, self.n_u
+        Q, R, Q_f, x_t = self._cost_weights()
+        p = _cabi.Problem()
+        p.model, p.integrator, p.dtype = _cabi.MODELS[model], _cabi.INTEGRATORS[self.integrator], _cabi.DTYPES[self.dtype]
+        p.n, p.m, p.N, p.B = n, m, int(N), int(B)
+        p.n_alpha, p.maxiter = int(n_alpha), int(maxiter)
+        p.dt, p.tol, p.alpha_factor, p.min_alpha = float(self.dt), float(tol), float(alpha_factor), float(min_alpha)
+        _cabi.fill(p.phys, phys)
+        _cabi.fill(p.Q, _square(Q, n, "Q").ravel())
+        _cabi.fill(p.R, _square(R, m, "R").ravel())     # integer R (run_iLQR_UA_MPC.py:53) is promoted here
+        _cabi.fill(p.Qf, _square(Q_f, n, "Q_f").ravel())
+        xt = np.asarray(x_t.detach().cpu().numpy() if isinstance(x_t, torch.Tensor) else x_t, dtype=np.float64).ravel()
+        if xt.shape != (n,):
+            raise ValueError(f"x_target must have shape {(n,)}, but got {xt.shape}")
+        _cabi.fill(p.x_target, xt)
+        return p
+
+    # ---- point evaluations ------------------------------------------------------------
+    def _points(self, x, u):
+        """-> (xd [n][P], ud [m][P] or None, P, single, torch_out)"""
+        tdt = D.torch_dtype(self.dtype)
+        torch_out = D.is_torch(x) and x.is_cuda
+        xd = D.to_device(x, tdt)
+        single = xd.ndim == 1
+        xd = xd.reshape(-1, self.n_x)
+        P = xd.shape[0]
+        ud = None
+        if u is not None:
+            ud = D.to_device(u, tdt).reshape(-1, self.n_u)
+            if ud.shape[0] != P:
+                raise ValueError(f"x and u disagree on the number of points: {P} vs {ud.shape[0]}")
+            ud = ud.t().contiguous()
+        return xd.t().contiguous(), ud, P, single, torch_out
+
+    def _handle(self, P):
+        h = self._point_handles.get(P)
+        if h is None:
+            h = D.Handle(self.make_problem(N=1, B=P))
+            self._point_handles[P] = h
+        return h
+
+    def _out(self, t, single, torch_out):
+        """t is batch-LAST; move the batch axis first and drop it for a single point."""
+        t = t.movedim(-1, 0)
+        if single:
+            t = t[0]
+        if torch_out:
+            return t
+        return D.host(t.cpu().numpy())
+
+    def _f(self, x, u):
+        xd, ud, P, single, tout = self._points(x, u)
+        h = self._handle(P)
+        xn = torch.empty_like(xd)
+        h.check(h.lib.ilqr_step(h.h, 0, None, D.ptr(xd), D.ptr(ud), D.ptr(xn), D.stream_ptr()))
+        return self._out(xn, single, tout)
+
+    def _jac(self, x, u):
+        xd, ud, P, single, tout = self._points(x, u)
+        h = self._handle(P)
+        n, m = self.n_x, self.n_u
+        X = torch.stack([xd, xd])            # [N+1=2][n][P]; only t=0 is linearized
+        U = ud.reshape(1, m, P)
+        A = torch.empty((1, n, n, P), dtype=xd.dtype, device="cuda")
+        Bd = torch.empty((1, n, m, P), dtype=xd.dtype, device="cuda")
+        h.check(h.lib.ilqr_linearize(h.h, None, D.ptr(X), D.ptr(U), D.ptr(A), D.ptr(Bd), D.stream_ptr()))
+        return self._out(A[0], single, tout), self._out(Bd[0], single, tout)
+
+    def _cost(self, x, u, which):
+        n, m = self.n_x, self.n_u
+        if u is None:
+            u = torch.zeros((x.shape[0], m)) if getattr(x, "ndim", 1) == 2 else torch.zeros(m)
+        xd, ud, P, single, tout = self._points(x, u)
+        h = self._handle(P)
+        X = torch.stack([xd, xd])
+        U = ud.reshape(1, m, P)
+        shapes = dict(l=(1, P), lx=(1, n, P), lu=(1, m, P), lxx=(1, n, n, P), luu=(1, m, m, P), lux=(1, m, n, P),
+                      lf=(P,), lfx=(n, P), lfxx=(n, n, P))
+        out = torch.empty(shapes[which], dtype=xd.dtype, device="cuda")
+        order = ["l", "lx", "lu", "lxx", "luu", "lux", "lf", "lfx", "lfxx"]
+        args = [D.ptr(out) if k == which else C.c_void_p(0) for k in order]
+        h.check(h.lib.ilqr_cost_expansion(h.h, D.ptr(X), D.ptr(U), *args, D.stream_ptr()))
+        if which in ("lf", "lfx", "lfxx"):
+            return self._out(out, single, tout)
+        return self._out(out[0], single, tout)
+
+    # ---- the reference's abstract methods ----------------------------------------------
+    # (system_base.py:255-275).  The shipped subclasses implement them on the device; they are not
+    # abstract here so that the device-backed subclasses need not carry Python bodies.
+    def _f_cont_fcn(self, x, u):
+        raise NotImplementedError("continuous dynamics live in the CUDA device model of this system")
+
+    def _l_fcn(self, x, u):
+        return self.l_fcn(x, u)
+
+    def _l_f_fcn(self, x):
+        return self.l_f_fcn(x)

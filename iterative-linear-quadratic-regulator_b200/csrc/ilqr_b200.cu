@@ -1,0 +1,938 @@
+// ilqr_b200.cu -- batched iLQR kernels for B200 (sm_100a) and the C ABI of include/ilqr_b200.h.
+//
+// Four kernels per iLQR iteration (BASELINE.json north_star):
+//   K1 commit_linearize_kernel  commit the accepted line-search candidate, then analytic A_t,B_t for
+//                               every (t,b) at once                 (iLQR_class.py:318-331)
+//   K2 backward_kernel          reverse Riccati scan, one trajectory per thread, value function
+//                               in registers, coalesced K/k stores  (iLQR_class.py:79-161)
+//   K3 rollout_kernel           forward rollout of every (alpha,b) pair concurrently
+//                                                                    (iLQR_class.py:164-247,278-302)
+//   K4 select_kernel            first-acceptable-alpha selection, convergence test, per-trajectory
+//                               status/iteration bookkeeping on device (iLQR_class.py:265-271,289-307)
+// All arrays are batch-innermost so that a warp's 32 trajectories touch 32 consecutive elements.
+// Paths in comments are relative to /root/reference/python/class_files/.
+#include "ilqr_b200.h"
+#include "ilqr_systems.cuh"
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <type_traits>
+
+namespace ilqr {
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+
+struct AlphaList { double a[ILQR_MAX_ALPHAS]; };
+
+// iteration-control block living at the head of the workspace
+struct Control {
+    unsigned long long total_iters;          // sum over trajectories of backward passes executed
+    unsigned int n_active[1];                 // [maxiter + 2], n_active[it] = trajectories entering iteration it
+};
+
+template <class Sys, int INTEG, typename T>
+__global__ void step_kernel(Sys sys, T dt, int B, const T *__restrict__ x, const T *__restrict__ u,
+                            T *__restrict__ xn)
+{
+    constexpr int n = Sys::N, m = Sys::M;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    T xv[n], uv[m], out[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) xv[i] = x[(size_t)i * B + b];
+#pragma unroll
+    for (int j = 0; j < m; ++j) uv[j] = u[(size_t)j * B + b];
+    step<INTEG>(sys, dt, xv, uv, out);
+#pragma unroll
+    for (int i = 0; i < n; ++i) xn[(size_t)i * B + b] = out[i];
+}
+
+// K1.  One thread per (t,b), t in [0,N].  If winner != nullptr and winner[b] >= 0 the thread first
+// copies the accepted candidate (Xc/Uc slab winner[b]) into the nominal X/U; if the trajectory is
+// active it then writes the discrete Jacobians about that nominal point.
+template <class Sys, int INTEG, typename T>
+__global__ void commit_linearize_kernel(Sys sys, T dt, int N, int B, T *__restrict__ X, T *__restrict__ U,
+                                        T *__restrict__ A, T *__restrict__ Bd, const T *__restrict__ Xc,
+                                        const T *__restrict__ Uc, const int *__restrict__ winner,
+                                        const int *__restrict__ active, int do_linearize,
+                                        const unsigned int *__restrict__ gate0, const unsigned int *__restrict__ gate1)
+{
+    constexpr int n = Sys::N, m = Sys::M;
+    if (gate0 && *gate0 == 0u && *gate1 == 0u) return;   // nobody active now or in the previous iteration
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)(N + 1) * B) return;
+    const int t = (int)(gid / B), b = (int)(gid % B);
+    const int w = winner ? winner[b] : -1;
+    const bool act = do_linearize && (active ? active[b] != 0 : true) && t < N;
+    if (w < 0 && !act) return;
+    T x[n], u[m];
+    if (w >= 0) {
+        const T *xs = Xc + (size_t)w * (N + 1) * n * B, *us = Uc + (size_t)w * N * m * B;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            x[i] = xs[((size_t)t * n + i) * B + b];
+            X[((size_t)t * n + i) * B + b] = x[i];
+        }
+        if (t < N) {
+#pragma unroll
+            for (int j = 0; j < m; ++j) {
+                u[j] = us[((size_t)t * m + j) * B + b];
+                U[((size_t)t * m + j) * B + b] = u[j];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < n; ++i) x[i] = X[((size_t)t * n + i) * B + b];
+#pragma unroll
+        for (int j = 0; j < m; ++j) u[j] = U[((size_t)t * m + j) * B + b];
+    }
+    if (!act) return;
+    T Aj[n][n], Bj[n][m];
+    step_jac<INTEG>(sys, dt, x, u, Aj, Bj);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int j = 0; j < n; ++j) A[(((size_t)t * n + i) * n + j) * B + b] = Aj[i][j];
+#pragma unroll
+        for (int j = 0; j < m; ++j) Bd[(((size_t)t * n + i) * m + j) * B + b] = Bj[i][j];
+    }
+}
+
+// K2.  One thread per trajectory; V_x, V_xx live in registers for the whole scan.
+template <typename T, int n, int m>
+struct BwdIn { T A[n][n], Bd[n][m], x[n], u[m]; };
+
+template <typename T, int n, int m>
+ILQR_DEV void bwd_load(BwdIn<T, n, m> &d, int t, int b, int B, const T *__restrict__ X, const T *__restrict__ U,
+                       const T *__restrict__ A, const T *__restrict__ Bd)
+{
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int j = 0; j < n; ++j) d.A[i][j] = A[(((size_t)t * n + i) * n + j) * B + b];
+#pragma unroll
+        for (int j = 0; j < m; ++j) d.Bd[i][j] = Bd[(((size_t)t * n + i) * m + j) * B + b];
+        d.x[i] = X[((size_t)t * n + i) * B + b];
+    }
+#pragma unroll
+    for (int j = 0; j < m; ++j) d.u[j] = U[((size_t)t * m + j) * B + b];
+}
+
+template <typename T, int n, int m>
+__global__ void backward_kernel(QuadCost<T, n, m> qc, int N, int B, const T *__restrict__ X,
+                                const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
+                                T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
+                                const unsigned int *__restrict__ gate)
+{
+    if (gate && *gate == 0u) return;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (active && !active[b]) return;
+    T Vx[n], Vxx[n][n];
+    {
+        T xN[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) xN[i] = X[((size_t)N * n + i) * B + b];
+        qc.terminal_grad(xN, Vx);                                        // iLQR_class.py:136-138
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) Vxx[i][j] = qc.Qfs[i][j];
+    }
+    BwdIn<T, n, m> cur, nxt;
+    bwd_load(cur, N - 1, b, B, X, U, A, Bd);
+    for (int t = N - 1; t >= 0; --t) {
+        if (t > 0) bwd_load(nxt, t - 1, b, B, X, U, A, Bd);              // prefetch the next step's inputs
+        T lx[n], lu[m];
+        qc.grad(cur.x, cur.u, lx, lu);
+        // Q_x = l_x + f_x' V_x ; Q_u = l_u + f_u' V_x                    (:100-101)
+        T Qx[n], Qu[m];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T s = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) s += cur.A[l][i] * Vx[l];
+            Qx[i] = lx[i] + s;
+        }
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+            T s = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) s += cur.Bd[l][j] * Vx[l];
+            Qu[j] = lu[j] + s;
+        }
+        // T1 = f_x' V_xx, T2 = f_u' V_xx ; Q_xx = l_xx + T1 f_x ; Q_ux = T2 f_x ; Q_uu = l_uu + T2 f_u   (:102-104)
+        T T1[n][n], T2[m][n], Qxx[n][n], Qux[m][n], Quu[m][m];
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int l = 0; l < n; ++l) s += cur.A[l][i] * Vxx[l][j];
+                T1[i][j] = s;
+            }
+#pragma unroll
+        for (int i = 0; i < m; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int l = 0; l < n; ++l) s += cur.Bd[l][i] * Vxx[l][j];
+                T2[i][j] = s;
+            }
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int l = 0; l < n; ++l) s += T1[i][l] * cur.A[l][j];
+                Qxx[i][j] = qc.Qs[i][j] * qc.dt + s;
+            }
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int l = 0; l < n; ++l) s += T2[i][l] * cur.A[l][j];
+                Qux[i][j] = s;                                           // l_ux = 0 for the quadratic cost
+            }
+#pragma unroll
+            for (int j = 0; j < m; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int l = 0; l < n; ++l) s += T2[i][l] * cur.Bd[l][j];
+                Quu[i][j] = qc.Rs[i][j] * qc.dt + s;
+            }
+        }
+        // K = -Q_uu^-1 Q_ux, k = -Q_uu^-1 Q_u                            (:109-110; no regularisation)
+        T Kt[m][n], kt[m];
+        if (m == 1) {
+            const T r = T(-1) / Quu[0][0];
+#pragma unroll
+            for (int j = 0; j < n; ++j) Kt[0][j] = Qux[0][j] * r;
+            kt[0] = Qu[0] * r;
+        } else {
+            T rhs[m][n + 1];
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+#pragma unroll
+                for (int j = 0; j < n; ++j) rhs[i][j] = Qux[i][j];
+                rhs[i][n] = Qu[i];
+            }
+            T Lm[m][m];
+#pragma unroll
+            for (int i = 0; i < m; ++i)
+#pragma unroll
+                for (int j = 0; j < m; ++j) Lm[i][j] = Quu[i][j];
+            lu_solve_inplace<m, n + 1>(Lm, rhs);
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+#pragma unroll
+                for (int j = 0; j < n; ++j) Kt[i][j] = -rhs[i][j];
+                kt[i] = -rhs[i][n];
+            }
+        }
+        // V_x = Q_x + K' Q_u ; V_xx = Q_xx + Q_ux' K                      (:113-114; not symmetrised)
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T s = T(0);
+#pragma unroll
+            for (int j = 0; j < m; ++j) s += Kt[j][i] * Qu[j];
+            Vx[i] = Qx[i] + s;
+#pragma unroll
+            for (int c = 0; c < n; ++c) {
+                T s2 = T(0);
+#pragma unroll
+                for (int j = 0; j < m; ++j) s2 += Qux[j][i] * Kt[j][c];
+                Vxx[i][c] = Qxx[i][c] + s2;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) K[(((size_t)t * m + j) * n + i) * B + b] = Kt[j][i];
+            k[((size_t)t * m + j) * B + b] = kt[j];
+        }
+        cur = nxt;
+    }
+}
+
+// K3.  One thread per (alpha, b); b fastest so loads of the shared nominal/gains coalesce and are
+// served once from L2 for all alphas.
+template <typename T, int n, int m>
+struct FwdIn { T xo[n], uo[m], kk[m], K[m][n]; };
+
+template <typename T, int n, int m>
+ILQR_DEV void fwd_load(FwdIn<T, n, m> &d, int t, int b, int B, const T *__restrict__ X, const T *__restrict__ U,
+                       const T *__restrict__ k, const T *__restrict__ K)
+{
+#pragma unroll
+    for (int i = 0; i < n; ++i) d.xo[i] = X[((size_t)t * n + i) * B + b];
+#pragma unroll
+    for (int j = 0; j < m; ++j) {
+        d.uo[j] = U[((size_t)t * m + j) * B + b];
+        d.kk[j] = k[((size_t)t * m + j) * B + b];
+#pragma unroll
+        for (int i = 0; i < n; ++i) d.K[j][i] = K[(((size_t)t * m + j) * n + i) * B + b];
+    }
+}
+
+template <class Sys, int INTEG, typename T>
+__global__ void rollout_kernel(Sys sys, QuadCost<T, Sys::N, Sys::M> qc, int N, int B, int n_alpha,
+                               const __grid_constant__ AlphaList alphas,
+                               const T *__restrict__ x0, const T *__restrict__ X_old, const T *__restrict__ U_old,
+                               const T *__restrict__ k, const T *__restrict__ K, T *__restrict__ Xc,
+                               T *__restrict__ Uc, T *__restrict__ cost_alpha, const int *__restrict__ active,
+                               const unsigned int *__restrict__ gate)
+{
+    constexpr int n = Sys::N, m = Sys::M;
+    if (gate && *gate == 0u) return;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)n_alpha * B) return;
+    const int ai = (int)(gid / B), b = (int)(gid % B);
+    if (active && !active[b]) return;
+    const T alpha = (T)alphas.a[ai];
+    T *Xw = Xc + (size_t)ai * (N + 1) * n * B, *Uw = Uc + (size_t)ai * N * m * B;
+    T x[n], cost = T(0);
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = x0[(size_t)i * B + b];
+    FwdIn<T, n, m> cur, nxt;
+    fwd_load(cur, 0, b, B, X_old, U_old, k, K);
+    for (int t = 0; t < N; ++t) {
+        if (t + 1 < N) fwd_load(nxt, t + 1, b, B, X_old, U_old, k, K);
+        T u[m], xn[n];
+#pragma unroll
+        for (int j = 0; j < m; ++j) {                                    // iLQR_class.py:181-182
+            T s = T(0);
+#pragma unroll
+            for (int i = 0; i < n; ++i) s += cur.K[j][i] * (x[i] - cur.xo[i]);
+            u[j] = cur.uo[j] + alpha * cur.kk[j] + s;
+        }
+#pragma unroll
+        for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + b] = x[i];
+#pragma unroll
+        for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + b] = u[j];
+        cost += qc.stage(x, u);                                          // :187
+        step<INTEG>(sys, qc.dt, x, u, xn);                               // :185
+#pragma unroll
+        for (int i = 0; i < n; ++i) x[i] = xn[i];
+        cur = nxt;
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) Xw[((size_t)N * n + i) * B + b] = x[i];
+    cost_alpha[(size_t)ai * B + b] = cost + qc.terminal(x);              // :245
+}
+
+// after the alpha = 0 rollout (iLQR_class.py:257-263): everything active, candidate 0 is the nominal
+template <typename T>
+__global__ void init_kernel(int B, const T *__restrict__ cost_alpha, T *__restrict__ cost, int *__restrict__ winner,
+                            int *__restrict__ active, int *__restrict__ iters, int *__restrict__ status, int maxiter,
+                            Control *ctl, T *__restrict__ tr_cost)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) ctl->n_active[0] = maxiter > 0 ? (unsigned)B : 0u;
+    if (b >= B) return;
+    cost[b] = cost_alpha[b];
+    if (tr_cost) tr_cost[b] = cost_alpha[b];
+    winner[b] = 0;
+    active[b] = maxiter > 0;
+    iters[b] = 0;
+    status[b] = maxiter > 0 ? ILQR_ST_RUNNING : ILQR_ST_MAXITER;
+}
+
+// K4.  iLQR_class.py:265-271 (convergence), :281-307 (first acceptable alpha, failure => stop)
+template <typename T>
+__global__ void select_kernel(int B, int n_alpha, const T *__restrict__ cost_alpha, T *__restrict__ cost,
+                              int *__restrict__ winner, int *__restrict__ active, int *__restrict__ iters,
+                              int *__restrict__ status, T tol, int it, int maxiter, Control *ctl,
+                              int *__restrict__ tr_alpha, T *__restrict__ tr_cost)
+{
+    if (ctl->n_active[it] == 0u) return;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    bool still = false, ran = false;
+    if (b < B) {
+        if (!active[b]) {
+            winner[b] = -1;
+        } else {
+            ran = true;
+            const T c0 = cost[b];
+            int w = -1;
+            T cw = c0;
+            for (int a = 0; a < n_alpha; ++a) {
+                const T c = cost_alpha[(size_t)a * B + b];
+                if (c <= c0) { w = a; cw = c; break; }                   // NaN compares false, as in Python
+            }
+            winner[b] = w;
+            iters[b] = it + 1;
+            if (tr_alpha) tr_alpha[(size_t)it * B + b] = w;
+            if (tr_cost) tr_cost[(size_t)(it + 1) * B + b] = cw;
+            if (w < 0) {
+                status[b] = ILQR_ST_LS_FAILED;
+                active[b] = 0;
+            } else {
+                cost[b] = cw;
+                if (it + 1 >= maxiter) { status[b] = ILQR_ST_MAXITER; active[b] = 0; }
+                else if (abs_t(cw - c0) <= tol) { status[b] = ILQR_ST_CONVERGED; active[b] = 0; }
+                else still = true;
+            }
+        }
+    }
+    const unsigned full = 0xffffffffu;
+    const unsigned ns = __popc(__ballot_sync(full, still)), nr = __popc(__ballot_sync(full, ran));
+    if ((threadIdx.x & 31) == 0) {
+        if (ns) atomicAdd(&ctl->n_active[it + 1], ns);
+        if (nr) atomicAdd(&ctl->total_iters, (unsigned long long)nr);
+    }
+}
+
+// winner only (ilqr_forward_linesearch)
+template <typename T>
+__global__ void winner_kernel(int B, int n_alpha, const T *__restrict__ cost_alpha, const T *__restrict__ cost,
+                              int *__restrict__ winner)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const T c0 = cost[b];
+    int w = -1;
+    for (int a = 0; a < n_alpha; ++a)
+        if (cost_alpha[(size_t)a * B + b] <= c0) { w = a; break; }
+    winner[b] = w;
+}
+
+// materialised cost expansion (system_base.py:212-219); one thread per (t,b), t in [0,N]
+template <typename T, int n, int m>
+__global__ void cost_expansion_kernel(QuadCost<T, n, m> qc, int N, int B, const T *__restrict__ X,
+                                      const T *__restrict__ U, T *__restrict__ l, T *__restrict__ lx,
+                                      T *__restrict__ lu, T *__restrict__ lxx, T *__restrict__ luu,
+                                      T *__restrict__ lux, T *__restrict__ lf, T *__restrict__ lfx,
+                                      T *__restrict__ lfxx)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)(N + 1) * B) return;
+    const int t = (int)(gid / B), b = (int)(gid % B);
+    T x[n], u[m];
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = X[((size_t)t * n + i) * B + b];
+    if (t == N) {
+        if (lf) lf[b] = qc.terminal(x);
+        T g[n];
+        qc.terminal_grad(x, g);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            if (lfx) lfx[(size_t)i * B + b] = g[i];
+#pragma unroll
+            for (int j = 0; j < n; ++j)
+                if (lfxx) lfxx[((size_t)i * n + j) * B + b] = qc.Qfs[i][j];
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < m; ++j) u[j] = U[((size_t)t * m + j) * B + b];
+    T gx[n], gu[m];
+    qc.grad(x, u, gx, gu);
+    if (l) l[(size_t)t * B + b] = qc.stage(x, u);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        if (lx) lx[((size_t)t * n + i) * B + b] = gx[i];
+#pragma unroll
+        for (int j = 0; j < n; ++j)
+            if (lxx) lxx[(((size_t)t * n + i) * n + j) * B + b] = qc.Qs[i][j] * qc.dt;
+    }
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+        if (lu) lu[((size_t)t * m + i) * B + b] = gu[i];
+#pragma unroll
+        for (int j = 0; j < m; ++j)
+            if (luu) luu[(((size_t)t * m + i) * m + j) * B + b] = qc.Rs[i][j] * qc.dt;
+#pragma unroll
+        for (int j = 0; j < n; ++j)
+            if (lux) lux[(((size_t)t * m + i) * n + j) * B + b] = T(0);
+    }
+}
+
+// run_iLQR_UA_MPC.py:157,168
+template <typename T>
+__global__ void mpc_shift_kernel(int N, int m, int B, T *__restrict__ U, T *__restrict__ u0)
+{
+    // one thread per (j,b): walks the horizon so the in-place shift needs no second buffer
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= m * B) return;
+    const int j = gid / B, b = gid % B;
+    T prev = U[((size_t)0 * m + j) * B + b];
+    if (u0) u0[(size_t)j * B + b] = prev;
+    for (int t = 0; t + 1 < N; ++t) {
+        const T v = U[((size_t)(t + 1) * m + j) * B + b];
+        U[((size_t)t * m + j) * B + b] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+
+template <typename T> PendulumSys<T> make_pendulum(const ilqr_problem_t &p)
+{
+    PendulumSys<T> s;
+    s.gl = (T)(p.phys[0] / p.phys[1]);
+    s.d = (T)p.phys[2];
+    return s;
+}
+
+template <typename T, int M> DoublePendulumSys<T, M> make_double(const ilqr_problem_t &p)
+{
+    const double g = p.phys[0], m1 = p.phys[1], m2 = p.phys[2], l1 = p.phys[3], l2 = p.phys[4];
+    const double d1 = p.phys[5], d2 = p.phys[6], th1 = p.phys[7], th2 = p.phys[8];
+    DoublePendulumSys<T, M> s;
+    s.c = (T)(m2 * l1 * l2);
+    s.m11_0 = (T)((m1 * l1 * l1) / 4 + m2 * l1 * l1 + (m2 * l2 * l2) / 4 + th1 + th2);
+    s.m12_0 = (T)((m2 * l2 * l2) / 4 + th2);
+    s.g1 = (T)(m2 * g * l2 / 2);
+    s.g2 = (T)(m2 * g * l1 + (m1 * g * l1) / 2);
+    s.d1 = (T)d1;
+    s.d2 = (T)d2;
+    return s;
+}
+
+template <typename T, int n, int m> QuadCost<T, n, m> make_cost(const ilqr_problem_t &p)
+{
+    QuadCost<T, n, m> c;
+    c.dt = (T)p.dt;
+    bool diag = true;
+    for (int i = 0; i < n; ++i) {
+        c.xt[i] = (T)p.x_target[i];
+        for (int j = 0; j < n; ++j) {
+            const double q = 0.5 * (p.Q[i * n + j] + p.Q[j * n + i]), qf = 0.5 * (p.Qf[i * n + j] + p.Qf[j * n + i]);
+            c.Qs[i][j] = (T)q;
+            c.Qfs[i][j] = (T)qf;
+            if (i != j && (q != 0.0 || qf != 0.0)) diag = false;
+        }
+    }
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) {
+            const double r = 0.5 * (p.R[i * m + j] + p.R[j * m + i]);
+            c.Rs[i][j] = (T)r;
+            if (i != j && r != 0.0) diag = false;
+        }
+    c.diag = diag ? 1 : 0;
+    return c;
+}
+
+struct Handle {
+    ilqr_problem_t p;
+    int n_alpha_eff;          // tries actually made: stops once alpha < min_alpha (iLQR_class.py:300-302)
+    AlphaList alphas;
+    long long launches;
+    int last_cuda;
+    unsigned int *h_flag;     // pinned, for the pipelined early-exit poll
+    int *tr_alpha;            // optional per-iteration trace (ilqr_set_trace)
+    void *tr_cost;
+    cudaEvent_t ev[2];
+};
+
+static inline int grid_for(size_t threads, int bs) { return (int)((threads + bs - 1) / bs); }
+
+// pick a block size that still spreads small batches over all 148 SMs
+static inline int block_for(size_t threads)
+{
+    int bs = 256;
+    while (bs > 32 && (threads + bs - 1) / bs < 2 * 148) bs >>= 1;
+    return bs;
+}
+
+struct WsLayout {
+    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, active, total;
+};
+
+static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
+{
+    const size_t w = p.dtype == ILQR_F64 ? 8 : 4;
+    const size_t B = p.B, N = p.N, n = p.n, m = p.m;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    WsLayout L;
+    size_t off = 0;
+    L.ctl = off; off = al(off + sizeof(Control) + sizeof(unsigned int) * (size_t)(p.maxiter + 2));
+    L.A = off; off = al(off + w * N * n * n * B);
+    L.Bd = off; off = al(off + w * N * n * m * B);
+    L.Xc = off; off = al(off + w * (size_t)n_alpha * (N + 1) * n * B);
+    L.Uc = off; off = al(off + w * (size_t)n_alpha * N * m * B);
+    L.cost_alpha = off; off = al(off + w * (size_t)n_alpha * B);
+    L.winner = off; off = al(off + 4 * B);
+    L.active = off; off = al(off + 4 * B);
+    L.total = off;
+    return L;
+}
+
+#define ILQR_CHECK_LAUNCH(h)                                         \
+    do {                                                             \
+        (h)->launches++;                                             \
+        cudaError_t e_ = cudaGetLastError();                         \
+        if (e_ != cudaSuccess) { (h)->last_cuda = (int)e_; return ILQR_E_CUDA; } \
+    } while (0)
+
+// dispatch on (dtype, model, integrator): calls f(T{}, sys, qc, integral_constant<int,INTEG>{})
+template <typename T, class Sys, class F> static int dispatch_integ(const Handle *h, const Sys &sys, F &&f)
+{
+    auto qc = make_cost<T, Sys::N, Sys::M>(h->p);
+    switch (h->p.integrator) {
+    case ILQR_EULER: return f(T(0), sys, qc, std::integral_constant<int, EULER>{});
+    case ILQR_MIDPOINT: return f(T(0), sys, qc, std::integral_constant<int, MIDPOINT>{});
+    case ILQR_RK4: return f(T(0), sys, qc, std::integral_constant<int, RK4>{});
+    case ILQR_BACKWARD_EULER: return f(T(0), sys, qc, std::integral_constant<int, BACKWARD_EULER>{});
+    }
+    return ILQR_E_INVALID;
+}
+
+template <typename T, class F> static int dispatch_model(const Handle *h, F &&f)
+{
+    switch (h->p.model) {
+    case ILQR_PENDULUM: return dispatch_integ<T>(h, make_pendulum<T>(h->p), f);
+    case ILQR_DOUBLE_PENDULUM: return dispatch_integ<T>(h, make_double<T, 2>(h->p), f);
+    case ILQR_UA_DOUBLE_PENDULUM: return dispatch_integ<T>(h, make_double<T, 1>(h->p), f);
+    }
+    return ILQR_E_INVALID;
+}
+
+template <class F> static int dispatch(const Handle *h, F &&f)
+{
+    if (h->p.dtype == ILQR_F64) return dispatch_model<double>(h, f);
+    return dispatch_model<float>(h, f);
+}
+
+// ---- launch helpers -----------------------------------------------------------------------
+
+static int launch_commit_linearize(Handle *h, void *X, void *U, void *A, void *Bd, const void *Xc, const void *Uc,
+                                   const int *winner, const int *active, int do_lin, const unsigned int *g0,
+                                   const unsigned int *g1, cudaStream_t st)
+{
+    return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
+        using T = decltype(tz);
+        using Sys = decltype(sys);
+        constexpr int I = decltype(integ)::value;
+        const size_t threads = (size_t)(h->p.N + 1) * h->p.B;
+        const int bs = 128;
+        commit_linearize_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
+            sys, qc.dt, h->p.N, h->p.B, (T *)X, (T *)U, (T *)A, (T *)Bd, (const T *)Xc, (const T *)Uc, winner, active,
+            do_lin, g0, g1);
+        ILQR_CHECK_LAUNCH(h);
+        return ILQR_OK;
+    });
+}
+
+static int launch_backward(Handle *h, const void *X, const void *U, const void *A, const void *Bd, void *K, void *k,
+                           const int *active, const unsigned int *gate, cudaStream_t st)
+{
+    return dispatch(h, [&](auto tz, auto sys, auto qc, auto) -> int {
+        using T = decltype(tz);
+        using Sys = decltype(sys);
+        const int bs = block_for(h->p.B);
+        backward_kernel<T, Sys::N, Sys::M><<<grid_for(h->p.B, bs), bs, 0, st>>>(
+            qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active, gate);
+        ILQR_CHECK_LAUNCH(h);
+        return ILQR_OK;
+    });
+}
+
+static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const void *x0, const void *X, const void *U,
+                          const void *k, const void *K, void *Xc, void *Uc, void *cost_alpha, const int *active,
+                          const unsigned int *gate, cudaStream_t st)
+{
+    return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
+        using T = decltype(tz);
+        using Sys = decltype(sys);
+        constexpr int I = decltype(integ)::value;
+        const size_t threads = (size_t)n_alpha * h->p.B;
+        const int bs = block_for(threads);
+        rollout_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
+            sys, qc, h->p.N, h->p.B, n_alpha, al, (const T *)x0, (const T *)X, (const T *)U, (const T *)k,
+            (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate);
+        ILQR_CHECK_LAUNCH(h);
+        return ILQR_OK;
+    });
+}
+
+}  // namespace ilqr
+
+using namespace ilqr;
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *ilqr_version(void) { return "ilqr_b200 0.1 (sm_100a)"; }
+
+const char *ilqr_strerror(int code)
+{
+    switch (code) {
+    case ILQR_OK: return "ok";
+    case ILQR_E_INVALID: return "invalid argument or unsupported model/integrator/dimension combination";
+    case ILQR_E_CUDA: return "CUDA runtime error (see ilqr_last_cuda_error)";
+    case ILQR_E_WORKSPACE: return "workspace too small (see ilqr_workspace_bytes)";
+    }
+    return "unknown error";
+}
+
+int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
+{
+    if (!p || !out) return ILQR_E_INVALID;
+    *out = nullptr;
+    if (p->integrator < ILQR_EULER || p->integrator > ILQR_BACKWARD_EULER) return ILQR_E_INVALID;
+    if (p->dtype != ILQR_F64 && p->dtype != ILQR_F32) return ILQR_E_INVALID;
+    int n = 0, m = 0;
+    switch (p->model) {
+    case ILQR_PENDULUM: n = 2; m = 1; break;
+    case ILQR_DOUBLE_PENDULUM: n = 4; m = 2; break;
+    case ILQR_UA_DOUBLE_PENDULUM: n = 4; m = 1; break;
+    default: return ILQR_E_INVALID;
+    }
+    if (p->n != n || p->m != m) return ILQR_E_INVALID;
+    if (p->N < 1 || p->B < 1 || p->n_alpha < 1 || p->n_alpha > ILQR_MAX_ALPHAS || p->maxiter < 0) return ILQR_E_INVALID;
+    if (!(p->dt > 0.0)) return ILQR_E_INVALID;
+    Handle *h = new (std::nothrow) Handle;
+    if (!h) return ILQR_E_INVALID;
+    std::memset(h, 0, sizeof(Handle));
+    h->p = *p;
+    // alpha = 1, then *= alpha_factor per failed try; tries stop once alpha < min_alpha (:279-302)
+    double a = 1.0;
+    int cnt = 0;
+    for (int j = 0; j < p->n_alpha; ++j) {
+        h->alphas.a[cnt++] = a;
+        a *= p->alpha_factor;
+        if (a < p->min_alpha) break;
+    }
+    h->n_alpha_eff = cnt;
+    if (cudaMallocHost((void **)&h->h_flag, 2 * sizeof(unsigned int)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming) != cudaSuccess) {
+        h->last_cuda = (int)cudaGetLastError();
+        delete h;
+        return ILQR_E_CUDA;
+    }
+    *out = (ilqr_handle_t)h;
+    return ILQR_OK;
+}
+
+int ilqr_destroy(ilqr_handle_t hh)
+{
+    Handle *h = (Handle *)hh;
+    if (!h) return ILQR_E_INVALID;
+    cudaEventDestroy(h->ev[0]);
+    cudaEventDestroy(h->ev[1]);
+    cudaFreeHost(h->h_flag);
+    delete h;
+    return ILQR_OK;
+}
+
+size_t ilqr_workspace_bytes(ilqr_handle_t hh)
+{
+    Handle *h = (Handle *)hh;
+    if (!h) return 0;
+    return ws_layout(h->p, h->n_alpha_eff).total;
+}
+
+int64_t ilqr_launch_count(ilqr_handle_t hh) { return hh ? ((Handle *)hh)->launches : 0; }
+int ilqr_last_cuda_error(ilqr_handle_t hh) { return hh ? ((Handle *)hh)->last_cuda : 0; }
+
+int ilqr_step(ilqr_handle_t hh, int /*t*/, const void * /*phi*/, const void *x, const void *u, void *xn, void *stream)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !x || !u || !xn) return ILQR_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
+        using T = decltype(tz);
+        using Sys = decltype(sys);
+        constexpr int I = decltype(integ)::value;
+        const int bs = block_for(h->p.B);
+        step_kernel<Sys, I, T><<<grid_for(h->p.B, bs), bs, 0, st>>>(sys, qc.dt, h->p.B, (const T *)x, (const T *)u, (T *)xn);
+        ILQR_CHECK_LAUNCH(h);
+        return ILQR_OK;
+    });
+}
+
+int ilqr_linearize(ilqr_handle_t hh, const void * /*phi*/, const void *X, const void *U, void *A, void *Bd, void *stream)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !X || !U || !A || !Bd) return ILQR_E_INVALID;
+    return launch_commit_linearize(h, (void *)X, (void *)U, A, Bd, nullptr, nullptr, nullptr, nullptr, 1, nullptr,
+                                   nullptr, (cudaStream_t)stream);
+}
+
+int ilqr_cost_expansion(ilqr_handle_t hh, const void *X, const void *U, void *l, void *lx, void *lu, void *lxx,
+                        void *luu, void *lux, void *lf, void *lfx, void *lfxx, void *stream)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !X || !U) return ILQR_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch(h, [&](auto tz, auto sys, auto qc, auto) -> int {
+        using T = decltype(tz);
+        using Sys = decltype(sys);
+        const size_t threads = (size_t)(h->p.N + 1) * h->p.B;
+        const int bs = 128;
+        cost_expansion_kernel<T, Sys::N, Sys::M><<<grid_for(threads, bs), bs, 0, st>>>(
+            qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (T *)l, (T *)lx, (T *)lu, (T *)lxx, (T *)luu, (T *)lux,
+            (T *)lf, (T *)lfx, (T *)lfxx);
+        ILQR_CHECK_LAUNCH(h);
+        return ILQR_OK;
+    });
+}
+
+int ilqr_set_trace(ilqr_handle_t hh, int32_t *alpha_idx, void *cost_trace)
+{
+    Handle *h = (Handle *)hh;
+    if (!h) return ILQR_E_INVALID;
+    h->tr_alpha = alpha_idx;
+    h->tr_cost = cost_trace;
+    return ILQR_OK;
+}
+
+int ilqr_backward(ilqr_handle_t hh, const void *X, const void *U, const void *A, const void *Bd, void *K, void *k,
+                  void *stream)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !X || !U || !A || !Bd || !K || !k) return ILQR_E_INVALID;
+    return launch_backward(h, X, U, A, Bd, K, k, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int ilqr_backward_pass(ilqr_handle_t hh, const void *phi, const void *X, const void *U, void *K, void *k, void *ws,
+                       size_t ws_bytes, void *stream)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !ws) return ILQR_E_INVALID;
+    const WsLayout L = ws_layout(h->p, h->n_alpha_eff);
+    if (ws_bytes < L.total) return ILQR_E_WORKSPACE;
+    char *w = (char *)ws;
+    int rc = ilqr_linearize(hh, phi, X, U, w + L.A, w + L.Bd, stream);
+    if (rc) return rc;
+    return ilqr_backward(hh, X, U, w + L.A, w + L.Bd, K, k, stream);
+}
+
+int ilqr_rollout(ilqr_handle_t hh, const void * /*phi*/, const void *x0, double alpha, const void *X_old,
+                 const void *U_old, const void *k, const void *K, void *X_new, void *U_new, void *cost, void *stream)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !x0 || !X_old || !U_old || !k || !K || !X_new || !U_new || !cost) return ILQR_E_INVALID;
+    AlphaList al;
+    std::memset(&al, 0, sizeof al);
+    al.a[0] = alpha;
+    return launch_rollout(h, 1, al, x0, X_old, U_old, k, K, X_new, U_new, cost, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int ilqr_forward_linesearch(ilqr_handle_t hh, const void * /*phi*/, const void *x0, const void *X, const void *U,
+                            const void *k, const void *K, const void *cost, void *Xc, void *Uc, void *cost_alpha,
+                            int32_t *winner, void *stream)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !x0 || !X || !U || !k || !K || !cost || !Xc || !Uc || !cost_alpha || !winner) return ILQR_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_rollout(h, h->n_alpha_eff, h->alphas, x0, X, U, k, K, Xc, Uc, cost_alpha, nullptr, nullptr, st);
+    if (rc) return rc;
+    const int bs = 128;
+    if (h->p.dtype == ILQR_F64)
+        winner_kernel<double><<<grid_for(h->p.B, bs), bs, 0, st>>>(h->p.B, h->n_alpha_eff, (const double *)cost_alpha,
+                                                                     (const double *)cost, winner);
+    else
+        winner_kernel<float><<<grid_for(h->p.B, bs), bs, 0, st>>>(h->p.B, h->n_alpha_eff, (const float *)cost_alpha,
+                                                                    (const float *)cost, winner);
+    ILQR_CHECK_LAUNCH(h);
+    return ILQR_OK;
+}
+
+int ilqr_solve(ilqr_handle_t hh, const void * /*phi*/, const void *x0, void *X, void *U, void *K, void *k, void *cost,
+               int32_t *iters, int32_t *status, void *ws, size_t ws_bytes, void *stream, int64_t *total_iters)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !x0 || !X || !U || !K || !k || !cost || !iters || !status || !ws) return ILQR_E_INVALID;
+    const ilqr_problem_t &p = h->p;
+    const WsLayout L = ws_layout(p, h->n_alpha_eff);
+    if (ws_bytes < L.total) return ILQR_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *w = (char *)ws;
+    Control *ctl = (Control *)(w + L.ctl);
+    void *A = w + L.A, *Bd = w + L.Bd, *Xc = w + L.Xc, *Uc = w + L.Uc, *ca = w + L.cost_alpha;
+    int *winner = (int *)(w + L.winner), *active = (int *)(w + L.active);
+    const int B = p.B, bsB = 128;
+    int rc;
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { h->last_cuda = (int)e_; return ILQR_E_CUDA; } } while (0)
+    CU(cudaMemsetAsync(ctl, 0, sizeof(Control) + sizeof(unsigned int) * (size_t)(p.maxiter + 2), st));
+    // initial rollout, alpha = 0, with the incoming X,K,k (iLQR_class.py:257-259) into candidate slab 0
+    AlphaList a0;
+    std::memset(&a0, 0, sizeof a0);
+    if ((rc = launch_rollout(h, 1, a0, x0, X, U, k, K, Xc, Uc, ca, nullptr, nullptr, st))) return rc;
+    if (p.dtype == ILQR_F64)
+        init_kernel<double><<<grid_for(B, bsB), bsB, 0, st>>>(B, (const double *)ca, (double *)cost, winner, active,
+                                                                iters, status, p.maxiter, ctl, (double *)h->tr_cost);
+    else
+        init_kernel<float><<<grid_for(B, bsB), bsB, 0, st>>>(B, (const float *)ca, (float *)cost, winner, active, iters,
+                                                               status, p.maxiter, ctl, (float *)h->tr_cost);
+    ILQR_CHECK_LAUNCH(h);
+    // iterations are enqueued in blocks of CHK; the active count after each block is copied to pinned
+    // memory and inspected one block later, so the device never idles waiting for the host.
+    const int CHK = 8;
+    int pending = -1;   // event slot holding the count after the previous block
+    int it = 0;
+    bool stop = false;
+    while (it < p.maxiter && !stop) {
+        const int end = (it + CHK < p.maxiter) ? it + CHK : p.maxiter;
+        for (; it < end; ++it) {
+            const unsigned int *g = &ctl->n_active[it];
+            const unsigned int *gprev = it > 0 ? &ctl->n_active[it - 1] : g;
+            if ((rc = launch_commit_linearize(h, X, U, A, Bd, Xc, Uc, winner, active, 1, g, gprev, st))) return rc;
+            if ((rc = launch_backward(h, X, U, A, Bd, K, k, active, g, st))) return rc;
+            if ((rc = launch_rollout(h, h->n_alpha_eff, h->alphas, x0, X, U, k, K, Xc, Uc, ca, active, g, st))) return rc;
+            if (p.dtype == ILQR_F64)
+                select_kernel<double><<<grid_for(B, bsB), bsB, 0, st>>>(B, h->n_alpha_eff, (const double *)ca,
+                                                                          (double *)cost, winner, active, iters, status,
+                                                                          p.tol, it, p.maxiter, ctl, h->tr_alpha,
+                                                                          (double *)h->tr_cost);
+            else
+                select_kernel<float><<<grid_for(B, bsB), bsB, 0, st>>>(B, h->n_alpha_eff, (const float *)ca,
+                                                                         (float *)cost, winner, active, iters, status,
+                                                                         (float)p.tol, it, p.maxiter, ctl, h->tr_alpha,
+                                                                         (float *)h->tr_cost);
+            ILQR_CHECK_LAUNCH(h);
+        }
+        if (pending >= 0) {
+            CU(cudaEventSynchronize(h->ev[pending]));
+            if (h->h_flag[pending] == 0u) stop = true;
+        }
+        if (!stop && it < p.maxiter) {
+            const int slot = pending < 0 ? 0 : 1 - pending;
+            CU(cudaMemcpyAsync(&h->h_flag[slot], &ctl->n_active[it], sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(h->ev[slot], st));
+            pending = slot;
+        }
+    }
+    // commit the candidates accepted in the last executed iteration (no linearization)
+    if ((rc = launch_commit_linearize(h, X, U, A, Bd, Xc, Uc, winner, nullptr, 0, nullptr, nullptr, st))) return rc;
+    if (total_iters) {
+        unsigned long long tot = 0;
+        CU(cudaMemcpyAsync(&tot, &ctl->total_iters, sizeof tot, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        *total_iters = (int64_t)tot;
+    }
+#undef CU
+    return ILQR_OK;
+}
+
+int ilqr_mpc_shift(ilqr_handle_t hh, void *U, void *u0, void *stream)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !U) return ILQR_E_INVALID;
+    const int threads = h->p.m * h->p.B, bs = 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->p.dtype == ILQR_F64)
+        mpc_shift_kernel<double><<<grid_for(threads, bs), bs, 0, st>>>(h->p.N, h->p.m, h->p.B, (double *)U, (double *)u0);
+    else
+        mpc_shift_kernel<float><<<grid_for(threads, bs), bs, 0, st>>>(h->p.N, h->p.m, h->p.B, (float *)U, (float *)u0);
+    ILQR_CHECK_LAUNCH(h);
+    return ILQR_OK;
+}
+
+}  // extern "C"

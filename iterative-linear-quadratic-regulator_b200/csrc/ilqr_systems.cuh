@@ -1,0 +1,495 @@
+// ilqr_systems.cuh -- device-side system definitions (continuous dynamics, analytic Jacobians,
+// integrators, quadratic cost) for the batched iLQR kernels.  sm_100a, CUDA cores only: the
+// per-step matrices are n<=12, m<=4, far below a tensor-core tile (BASELINE.json north_star).
+//
+// What each piece replaces in the reference (paths relative to /root/reference/python/):
+//   PendulumSys            class_files/systems/pendulum_sys.py:60-75
+//   DoublePendulumSys<M>   class_files/systems/double_pendulum_sys.py:84-111,138-206 (M=2)
+//                          class_files/systems/UA_double_pendulum_sys.py:84-111,140-208 (M=1)
+//   step<INTEG>            class_files/systems/system_base.py:50-74 (euler/midpoint/rk4), :88-140 (backward Euler)
+//   step_jac<INTEG>        system_base.py:203-205 (jacfwd of the step) and :146-188 (IFT for backward Euler),
+//                          evaluated in closed form instead of by autodiff
+//   QuadCost               pendulum_sys.py:77-98 and the same block in the two double-pendulum files;
+//                          derivatives system_base.py:212-219
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ilqr {
+
+enum Model { PENDULUM = 0, DOUBLE_PENDULUM = 1, UA_DOUBLE_PENDULUM = 2, LTV = 3 };
+enum Integ { EULER = 0, MIDPOINT = 1, RK4 = 2, BACKWARD_EULER = 3 };
+
+#define ILQR_DEV __device__ __forceinline__
+
+ILQR_DEV void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
+ILQR_DEV void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
+ILQR_DEV double sin_t(double x) { return sin(x); }
+ILQR_DEV float sin_t(float x) { return sinf(x); }
+ILQR_DEV double sqrt_t(double x) { return sqrt(x); }
+ILQR_DEV float sqrt_t(float x) { return sqrtf(x); }
+ILQR_DEV double abs_t(double x) { return fabs(x); }
+ILQR_DEV float abs_t(float x) { return fabsf(x); }
+
+// ------------------------------------------------------------------------------------------
+// Second-order mechanical systems: x = [q, qd], xdot = [qd, qdd(x,u)].  A system provides
+//   acc(x,u,a)                 a = qdd
+//   acc_jac(x,u,a,J,Bq)        J = d qdd / d x  (NQ x N),  Bq = d qdd / d u  (NQ x M)
+// The continuous Jacobian is then A_c = [[0, I],[J]], B_c = [[0],[Bq]], and products with A_c
+// only need the NQ dense rows (the zero/identity rows are never multiplied).
+// ------------------------------------------------------------------------------------------
+
+template <typename T>
+struct PendulumSys {
+    static constexpr int NQ = 1, N = 2, M = 1;
+    T gl, d;   // g/l, damping
+    ILQR_DEV void acc(const T *x, const T *u, T *a) const
+    {
+        a[0] = u[0] - d * x[1] - gl * sin_t(x[0]);
+    }
+    ILQR_DEV void acc_jac(const T *x, const T *u, T *a, T (*J)[N], T (*Bq)[M]) const
+    {
+        T s, c;
+        sincos_t(x[0], &s, &c);
+        a[0] = u[0] - d * x[1] - gl * s;
+        J[0][0] = -gl * c;
+        J[0][1] = -d;
+        Bq[0][0] = T(1);
+    }
+};
+
+template <typename T, int M_>
+struct DoublePendulumSys {
+    static constexpr int NQ = 2, N = 4, M = M_;
+    // derived constants (host, double precision):
+    //   c = m2 l1 l2, m11_0 = m1 l1^2/4 + m2 l1^2 + m2 l2^2/4 + th1 + th2, m12_0 = m22 = m2 l2^2/4 + th2,
+    //   g1 = m2 g l2/2, g2 = m2 g l1 + m1 g l1/2
+    T c, m11_0, m12_0, g1, g2, d1, d2;
+
+    ILQR_DEV void acc(const T *x, const T *u, T *a) const
+    {
+        const T q1d = x[2], q2d = x[3];
+        T s1, c1, s2, c2;
+        sincos_t(x[0], &s1, &c1);
+        sincos_t(x[1], &s2, &c2);
+        const T s12 = s1 * c2 + c1 * s2;
+        const T m11 = m11_0 + c * c2, m12 = m12_0 + T(0.5) * c * c2, m22 = m12_0;
+        const T inv = T(1) / (m11 * m22 - m12 * m12);
+        const T cs2 = c * s2;
+        T h1 = u[0] + T(0.5) * cs2 * (T(2) * q1d * q2d + q2d * q2d) - g1 * s12 - g2 * s1 - d1 * q1d;
+        T h2 = -T(0.5) * cs2 * (q1d * q1d) - g1 * s12 - d2 * q2d;
+        if (M == 2) h2 += u[M - 1];
+        a[0] = inv * (m22 * h1 - m12 * h2);
+        a[1] = inv * (m11 * h2 - m12 * h1);
+    }
+
+    ILQR_DEV void acc_jac(const T *x, const T *u, T *a, T (*J)[N], T (*Bq)[M]) const
+    {
+        const T q1d = x[2], q2d = x[3];
+        T s1, c1, s2, c2;
+        sincos_t(x[0], &s1, &c1);
+        sincos_t(x[1], &s2, &c2);
+        const T s12 = s1 * c2 + c1 * s2, c12 = c1 * c2 - s1 * s2;
+        const T m11 = m11_0 + c * c2, m12 = m12_0 + T(0.5) * c * c2, m22 = m12_0;
+        const T inv = T(1) / (m11 * m22 - m12 * m12);
+        const T i00 = inv * m22, i01 = -inv * m12, i11 = inv * m11;   // M^-1 (symmetric)
+        const T cs2 = c * s2, cc2 = c * c2;
+        const T w = T(2) * q1d * q2d + q2d * q2d;
+        T h1 = u[0] + T(0.5) * cs2 * w - g1 * s12 - g2 * s1 - d1 * q1d;
+        T h2 = -T(0.5) * cs2 * (q1d * q1d) - g1 * s12 - d2 * q2d;
+        if (M == 2) h2 += u[M - 1];
+        const T a1 = i00 * h1 + i01 * h2, a2 = i01 * h1 + i11 * h2;
+        a[0] = a1; a[1] = a2;
+        // r_z = dh/dz - (dM/dz) qdd ;  dM/dq2 = -c s2 [[1, 1/2],[1/2, 0]]
+        T r0[4], r1[4];
+        r0[0] = -g1 * c12 - g2 * c1;
+        r1[0] = -g1 * c12;
+        r0[1] = T(0.5) * cc2 * w - g1 * c12 + cs2 * (a1 + T(0.5) * a2);
+        r1[1] = -T(0.5) * cc2 * (q1d * q1d) - g1 * c12 + T(0.5) * cs2 * a1;
+        r0[2] = cs2 * q2d - d1;
+        r1[2] = -cs2 * q1d;
+        r0[3] = cs2 * (q1d + q2d);
+        r1[3] = -d2;
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {
+            J[0][z] = i00 * r0[z] + i01 * r1[z];
+            J[1][z] = i01 * r0[z] + i11 * r1[z];
+        }
+        Bq[0][0] = i00; Bq[1][0] = i01;
+        if (M == 2) { Bq[0][M - 1] = i01; Bq[1][M - 1] = i11; }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// small dense LU with partial pivoting, fully unrolled (used by backward Euler and by the
+// Q_uu solve for m >= 2).  Rows are swapped by value so all indices stay compile-time.
+// ------------------------------------------------------------------------------------------
+template <int n, int nrhs, typename T>
+ILQR_DEV void lu_solve_inplace(T (*a)[n], T (*b)[nrhs])
+{
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+#pragma unroll
+        for (int i = j + 1; i < n; ++i) {
+            // bubble the largest |a[.][j]| of rows j..n-1 into row j (first maximum wins, as getrf)
+            const bool sw = abs_t(a[i][j]) > abs_t(a[j][j]);
+#pragma unroll
+            for (int c = 0; c < n; ++c) { const T u = a[j][c], v = a[i][c]; a[j][c] = sw ? v : u; a[i][c] = sw ? u : v; }
+#pragma unroll
+            for (int c = 0; c < nrhs; ++c) { const T u = b[j][c], v = b[i][c]; b[j][c] = sw ? v : u; b[i][c] = sw ? u : v; }
+        }
+        const T r = T(1) / a[j][j];
+#pragma unroll
+        for (int i = j + 1; i < n; ++i) {
+            const T l = a[i][j] * r;
+#pragma unroll
+            for (int c = j + 1; c < n; ++c) a[i][c] -= l * a[j][c];
+#pragma unroll
+            for (int c = 0; c < nrhs; ++c) b[i][c] -= l * b[j][c];
+        }
+    }
+#pragma unroll
+    for (int i = n - 1; i >= 0; --i) {
+        const T r = T(1) / a[i][i];
+#pragma unroll
+        for (int c = 0; c < nrhs; ++c) {
+            T s = b[i][c];
+#pragma unroll
+            for (int k = i + 1; k < n; ++k) s -= a[i][k] * b[k][c];
+            b[i][c] = s * r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// integrators
+// ------------------------------------------------------------------------------------------
+template <class Sys, typename T>
+ILQR_DEV void f_cont(const Sys &s, const T *x, const T *u, T *xd)
+{
+    constexpr int NQ = Sys::NQ;
+    T a[NQ];
+    s.acc(x, u, a);
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) { xd[i] = x[NQ + i]; xd[NQ + i] = a[i]; }
+}
+
+// backward Euler quasi-Newton (system_base.py:101-140): explicit-Euler guess, Jacobian of the
+// residual frozen at the guess, iterate while ||F||_2 > 1e-5 and k < 20.
+template <class Sys, typename T>
+ILQR_DEV void backward_euler_step(const Sys &s, T dt, const T *x, const T *u, T *xn)
+{
+    constexpr int n = Sys::N, NQ = Sys::NQ, M = Sys::M;
+    T f[n], F[n][1], a[NQ], J[NQ][n], Bq[NQ][M], Jr[n][n];
+    f_cont(s, x, u, f);
+#pragma unroll
+    for (int i = 0; i < n; ++i) xn[i] = x[i] + dt * f[i];
+    s.acc_jac(xn, u, a, J, Bq);
+    T fn = T(0);
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        F[i][0] = xn[i] - x[i] - dt * xn[NQ + i];
+        F[NQ + i][0] = xn[NQ + i] - x[NQ + i] - dt * a[i];
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) fn += F[i][0] * F[i][0];
+    fn = sqrt_t(fn);
+    // residual Jacobian I - dt*A_c at the guess; inverted once (n<=4) instead of an LU object
+    T Inv[n][n];
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            const T ac = (i < NQ) ? ((j == i + NQ) ? T(1) : T(0)) : J[i - NQ][j];
+            Jr[i][j] = ((i == j) ? T(1) : T(0)) - dt * ac;
+            Inv[i][j] = (i == j) ? T(1) : T(0);
+        }
+    lu_solve_inplace<n, n>(Jr, Inv);
+    int k = 0;
+    while (fn > T(1e-5) && k < 20) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T d = T(0);
+#pragma unroll
+            for (int j = 0; j < n; ++j) d -= Inv[i][j] * F[j][0];
+            xn[i] += d;
+        }
+        s.acc(xn, u, a);
+        fn = T(0);
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            F[i][0] = xn[i] - x[i] - dt * xn[NQ + i];
+            F[NQ + i][0] = xn[NQ + i] - x[NQ + i] - dt * a[i];
+        }
+#pragma unroll
+        for (int i = 0; i < n; ++i) fn += F[i][0] * F[i][0];
+        fn = sqrt_t(fn);
+        ++k;
+    }
+}
+
+template <int INTEG, class Sys, typename T>
+ILQR_DEV void step(const Sys &s, T dt, const T *x, const T *u, T *xn)
+{
+    constexpr int n = Sys::N;
+    if (INTEG == EULER) {
+        T k1[n];
+        f_cont(s, x, u, k1);
+#pragma unroll
+        for (int i = 0; i < n; ++i) xn[i] = x[i] + k1[i] * dt;
+    } else if (INTEG == MIDPOINT) {
+        T k1[n], k2[n], xs[n];
+        f_cont(s, x, u, k1);
+#pragma unroll
+        for (int i = 0; i < n; ++i) xs[i] = x[i] + (dt * T(0.5)) * k1[i];
+        f_cont(s, xs, u, k2);
+#pragma unroll
+        for (int i = 0; i < n; ++i) xn[i] = x[i] + dt * k2[i];
+    } else if (INTEG == RK4) {
+        T k1[n], k2[n], k3[n], k4[n], xs[n];
+        f_cont(s, x, u, k1);
+#pragma unroll
+        for (int i = 0; i < n; ++i) xs[i] = x[i] + (dt * T(0.5)) * k1[i];
+        f_cont(s, xs, u, k2);
+#pragma unroll
+        for (int i = 0; i < n; ++i) xs[i] = x[i] + (dt * T(0.5)) * k2[i];
+        f_cont(s, xs, u, k3);
+#pragma unroll
+        for (int i = 0; i < n; ++i) xs[i] = x[i] + dt * k3[i];
+        f_cont(s, xs, u, k4);
+#pragma unroll
+        for (int i = 0; i < n; ++i) xn[i] = x[i] + (dt / T(6)) * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
+    } else {
+        backward_euler_step(s, dt, x, u, xn);
+    }
+}
+
+// out = A_c * S for a second-order system: rows 0..NQ-1 are rows NQ..N-1 of S, the rest J*S
+template <int NQ, int n, int cols, typename T>
+ILQR_DEV void mul_Ac(const T (*J)[n], const T (*S)[cols], T (*out)[cols])
+{
+#pragma unroll
+    for (int c = 0; c < cols; ++c) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) out[i][c] = S[NQ + i][c];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            T acc = T(0);
+#pragma unroll
+            for (int k = 0; k < n; ++k) acc += J[i][k] * S[k][c];
+            out[NQ + i][c] = acc;
+        }
+    }
+}
+
+// discrete Jacobians A = d step/dx (n x n), Bd = d step/du (n x m)
+template <int INTEG, class Sys, typename T>
+ILQR_DEV void step_jac(const Sys &s, T dt, const T *x, const T *u, T (*A)[Sys::N], T (*Bd)[Sys::M])
+{
+    constexpr int n = Sys::N, NQ = Sys::NQ, M = Sys::M;
+    T a[NQ], J[NQ][n], Bq[NQ][M];
+    if (INTEG == EULER) {
+        s.acc_jac(x, u, a, J, Bq);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                const T ac = (i < NQ) ? ((j == i + NQ) ? T(1) : T(0)) : J[i - NQ][j];
+                A[i][j] = ((i == j) ? T(1) : T(0)) + dt * ac;
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) Bd[i][j] = (i < NQ) ? T(0) : dt * Bq[i - NQ][j];
+        }
+    } else if (INTEG == BACKWARD_EULER) {
+        // IFT at the converged step: A = (I - dt A_c(x+))^-1, B = A dt B_c(x+)
+        T xn[n], Jr[n][n], R[n][n + M];
+        backward_euler_step(s, dt, x, u, xn);
+        s.acc_jac(xn, u, a, J, Bq);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                const T ac = (i < NQ) ? ((j == i + NQ) ? T(1) : T(0)) : J[i - NQ][j];
+                Jr[i][j] = ((i == j) ? T(1) : T(0)) - dt * ac;
+                R[i][j] = (i == j) ? T(1) : T(0);
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) R[i][n + j] = (i < NQ) ? T(0) : dt * Bq[i - NQ][j];
+        }
+        lu_solve_inplace<n, n + M>(Jr, R);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) A[i][j] = R[i][j];
+#pragma unroll
+            for (int j = 0; j < M; ++j) Bd[i][j] = R[i][n + j];
+        }
+    } else {
+        // explicit Runge-Kutta stages with ZOH on u:
+        //   Kx_s = A_c(x_s) (I + c_s dt Kx_{s-1}),  Ku_s = A_c(x_s) c_s dt Ku_{s-1} + B_c(x_s)
+        constexpr int S = (INTEG == MIDPOINT) ? 2 : 4;
+        const T cs[4] = { T(0), T(0.5), (INTEG == RK4) ? T(0.5) : T(0), T(1) };
+        const T ws[4] = { (INTEG == RK4) ? T(1) : T(0), (INTEG == RK4) ? T(2) : T(1), T(2), T(1) };
+        T kprev[n], Kx[n][n], Ku[n][M], Ax[n][n], Au[n][M], xs[n];
+#pragma unroll
+        for (int st = 0; st < S; ++st) {
+            if (st == 0) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) xs[i] = x[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < n; ++i) xs[i] = x[i] + (cs[st] * dt) * kprev[i];
+            }
+            s.acc_jac(xs, u, a, J, Bq);
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) { kprev[i] = xs[NQ + i]; kprev[NQ + i] = a[i]; }
+            if (st == 0) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+#pragma unroll
+                    for (int j = 0; j < n; ++j) Kx[i][j] = (i < NQ) ? ((j == i + NQ) ? T(1) : T(0)) : J[i - NQ][j];
+#pragma unroll
+                    for (int j = 0; j < M; ++j) Ku[i][j] = (i < NQ) ? T(0) : Bq[i - NQ][j];
+                }
+            } else {
+                T Sx[n][n], Su[n][M], Nx[n][n], Nu[n][M];
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+#pragma unroll
+                    for (int j = 0; j < n; ++j) Sx[i][j] = ((i == j) ? T(1) : T(0)) + (cs[st] * dt) * Kx[i][j];
+#pragma unroll
+                    for (int j = 0; j < M; ++j) Su[i][j] = (cs[st] * dt) * Ku[i][j];
+                }
+                mul_Ac<NQ, n, n>(J, Sx, Nx);
+                mul_Ac<NQ, n, M>(J, Su, Nu);
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+#pragma unroll
+                    for (int j = 0; j < n; ++j) Kx[i][j] = Nx[i][j];
+#pragma unroll
+                    for (int j = 0; j < M; ++j) Ku[i][j] = Nu[i][j] + ((i < NQ) ? T(0) : Bq[i - NQ][j]);
+                }
+            }
+            if (st == 0) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+#pragma unroll
+                    for (int j = 0; j < n; ++j) Ax[i][j] = ws[0] * Kx[i][j];
+#pragma unroll
+                    for (int j = 0; j < M; ++j) Au[i][j] = ws[0] * Ku[i][j];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+#pragma unroll
+                    for (int j = 0; j < n; ++j) Ax[i][j] += ws[st] * Kx[i][j];
+#pragma unroll
+                    for (int j = 0; j < M; ++j) Au[i][j] += ws[st] * Ku[i][j];
+                }
+            }
+        }
+        const T h = (INTEG == RK4) ? dt / T(6) : dt;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) A[i][j] = ((i == j) ? T(1) : T(0)) + h * Ax[i][j];
+#pragma unroll
+            for (int j = 0; j < M; ++j) Bd[i][j] = h * Au[i][j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// quadratic cost  l = (1/2 dx'Q dx + 1/2 u'R u) dt,  l_f = 1/2 dx'Q_f dx,  dx = x - x_target.
+// Qs/Rs/Qfs are the symmetrised weights (the derivatives the reference gets from autodiff are
+// those of the symmetric part).
+// ------------------------------------------------------------------------------------------
+template <typename T, int n, int m>
+struct QuadCost {
+    T dt;
+    T xt[n];
+    T Qs[n][n], Rs[m][m], Qfs[n][n];
+    int diag;   // all three weights diagonal (true for every reference script)
+
+    ILQR_DEV T stage(const T *x, const T *u) const
+    {
+        T cx = T(0), cu = T(0);
+        if (diag) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) { const T d = x[i] - xt[i]; cx += (T(0.5) * d) * Qs[i][i] * d; }
+#pragma unroll
+            for (int j = 0; j < m; ++j) cu += (T(0.5) * u[j]) * Rs[j][j] * u[j];
+        } else {
+            T dx[n];
+#pragma unroll
+            for (int i = 0; i < n; ++i) dx[i] = x[i] - xt[i];
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int i = 0; i < n; ++i) s += (T(0.5) * dx[i]) * Qs[i][j];
+                cx += s * dx[j];
+            }
+#pragma unroll
+            for (int j = 0; j < m; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int i = 0; i < m; ++i) s += (T(0.5) * u[i]) * Rs[i][j];
+                cu += s * u[j];
+            }
+        }
+        return (cx + cu) * dt;
+    }
+    ILQR_DEV T terminal(const T *x) const
+    {
+        T dx[n], c = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) dx[i] = x[i] - xt[i];
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            T s = T(0);
+#pragma unroll
+            for (int i = 0; i < n; ++i) s += (T(0.5) * dx[i]) * Qfs[i][j];
+            c += s * dx[j];
+        }
+        return c;
+    }
+    // l_x = dt Qs dx, l_u = dt Rs u
+    ILQR_DEV void grad(const T *x, const T *u, T *lx, T *lu) const
+    {
+        T dx[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) dx[i] = x[i] - xt[i];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T s = T(0);
+            if (diag) s = Qs[i][i] * dx[i];
+            else {
+#pragma unroll
+                for (int j = 0; j < n; ++j) s += Qs[i][j] * dx[j];
+            }
+            lx[i] = s * dt;
+        }
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+            T s = T(0);
+            if (diag) s = Rs[i][i] * u[i];
+            else {
+#pragma unroll
+                for (int j = 0; j < m; ++j) s += Rs[i][j] * u[j];
+            }
+            lu[i] = s * dt;
+        }
+    }
+    ILQR_DEV void terminal_grad(const T *x, T *vx) const
+    {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T s = T(0);
+#pragma unroll
+            for (int j = 0; j < n; ++j) s += Qfs[i][j] * (x[j] - xt[j]);
+            vx[i] = s;
+        }
+    }
+};
+
+}  // namespace ilqr

@@ -164,6 +164,7 @@ class _Trace:
     def __init__(self, sol):
         self.fw = []       # (alpha, cost) per forward_pass call
         self.n_bw = 0
+        self.snap = []     # (X, U, U_ff, K) per backward_pass call
         f0, b0 = sol.forward_pass, sol.backward_pass
 
         def fwd(x0, alpha, X, U, U_ff, K):
@@ -173,7 +174,10 @@ class _Trace:
 
         def bwd(X, U):
             self.n_bw += 1
-            return b0(X, U)
+            r = b0(X, U)
+            # per-iteration snapshot: the nominal the iteration starts from and the gains it produces
+            self.snap.append((npy(X), npy(U), npy(r[0]), npy(r[1])))
+            return r
         sol.forward_pass, sol.backward_pass = fwd, bwd
 
 
@@ -193,6 +197,9 @@ def case_solve(p, integrator, T, x0, maxiter, tol):
                X=npy(X), U=npy(U), cost=npy(cost), K=npy(sol.K), U_ff=npy(sol.U_ff),
                trace_alpha=np.array([a for a, _ in tr.fw]), trace_cost=np.array([c for _, c in tr.fw]),
                n_backward=tr.n_bw)
+    if tr.snap:
+        out.update(it_X=np.stack([s[0] for s in tr.snap]), it_U=np.stack([s[1] for s in tr.snap]),
+                   it_U_ff=np.stack([s[2] for s in tr.snap]), it_K=np.stack([s[3] for s in tr.snap]))
     return out
 
 

@@ -1,0 +1,70 @@
+"""Shared by the CPU and GPU tests: build reference-API systems / oracle problems from golden files."""
+import numpy as np
+
+PHYS_DP = ("g", "m1", "m2", "l1", "l2", "d1", "d2", "theta1", "theta2")
+
+
+def system_from_golden(g, integrator=None, dtype="float64"):
+    """Instantiate the drop-in System subclass for a golden file's parameter block."""
+    from class_files.systems.pendulum_sys import MyPendulum
+    from class_files.systems.double_pendulum_sys import MyDoublePendulum
+    from class_files.systems.UA_double_pendulum_sys import MyUADoublePendulum
+    kind = str(g["p_kind"])
+    integ = integrator or str(g["p_integrator"])
+    common = dict(dt=float(g["p_dt"]), x_target=np.array(g["p_x_target"]), Q=np.diag(g["p_Q"]), R=np.diag(g["p_R"]),
+                  Q_f=np.diag(g["p_Q_f"]), integrator=integ, dtype=dtype)
+    if kind == "pendulum":
+        return MyPendulum(g=float(g["p_g"]), l=float(g["p_l"]), d=float(g["p_d"]), **common)
+    phys = {k: float(g["p_" + k]) for k in PHYS_DP}
+    cls = MyDoublePendulum if kind == "double" else MyUADoublePendulum
+    return cls(**phys, **common)
+
+
+def cfg2_x0(count, seed=0):
+    """BASELINE config 2 initial states (same generator as tests/golden/make_golden.py)."""
+    rng = np.random.default_rng(seed)
+    x0 = np.empty((count, 4))
+    x0[:, :2] = rng.uniform(-np.pi, np.pi, size=(count, 2))
+    x0[:, 2:] = rng.uniform(-2.0, 2.0, size=(count, 2))
+    return x0
+
+
+UA_OL = dict(dt=0.01, Q=[1.0, 1.0, 0.1, 0.1], R=[1.0], Q_f=[1000.0, 1000.0, 100.0, 100.0],
+             x_target=[np.pi, 0.0, 0.0, 0.0],
+             phys=dict(g=9.81, m1=1.0, m2=1.0, l1=1.0, l2=1.0, d1=0.1, d2=0.1, theta1=1.0 / 12, theta2=1.0 / 12))
+
+
+def ua_system(integrator="rk4", dtype="float64", **over):
+    from class_files.systems.UA_double_pendulum_sys import MyUADoublePendulum
+    p = dict(UA_OL)
+    p.update(over)
+    return MyUADoublePendulum(dt=p["dt"], x_target=np.array(p["x_target"]), Q=np.diag(p["Q"]), R=np.diag(p["R"]),
+                              Q_f=np.diag(p["Q_f"]), integrator=integrator, dtype=dtype, **p["phys"])
+
+
+def ua_oracle_problem(O, N, integrator="rk4", **kw):
+    p = UA_OL
+    return O.make_problem("ua", integrator, N, p["dt"], p["Q"], p["R"], p["Q_f"], p["x_target"], p["phys"], **kw)
+
+
+def golden_flow(g):
+    """Per-iteration (accepted try index or -1, cost after the iteration) from the call trace that
+    make_golden.py recorded around the reference's forward_pass (first call = alpha-0 rollout)."""
+    ta, tc = np.asarray(g["trace_alpha"]), np.asarray(g["trace_cost"])
+    cost = tc[0]
+    idx, costs = [], [cost]
+    i = 1
+    while i < len(ta):
+        j, acc = 0, -1
+        while i < len(ta):
+            if j > 0 and ta[i] == 1.0:
+                break                       # next iteration's first try
+            if tc[i] <= cost:
+                acc, cost = j, tc[i]
+                i += 1
+                break
+            i += 1
+            j += 1
+        idx.append(acc)
+        costs.append(cost)
+    return np.array(idx), np.array(costs)
