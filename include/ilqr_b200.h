@@ -139,6 +139,15 @@ int ilqr_set_trace(ilqr_handle_t h, int32_t *alpha_idx, void *cost_trace);
  * returns u0[m][B] = U[0] before the shift (run_iLQR_UA_MPC.py:157). */
 int ilqr_mpc_shift(ilqr_handle_t h, void *U, void *u0, void *stream);
 
+/* Optional per-kernel timing of ilqr_solve: CUDA events are chained between its launches on the
+ * caller's stream and folded into per-class totals when the solve synchronizes (total_iters != NULL).
+ * Classes index the arrays of ilqr_get_kernel_times (ms[ILQR_N_KERNEL_CLASSES], launches[...]).
+ * ILQR_KC_OTHER collects the select/convergence kernel and the gaps between launches. */
+enum { ILQR_KC_LINEARIZE = 0, ILQR_KC_BACKWARD = 1, ILQR_KC_ROLLOUT = 2, ILQR_KC_INIT_ROLLOUT = 3,
+       ILQR_KC_OTHER = 4, ILQR_N_KERNEL_CLASSES = 5 };
+int ilqr_set_profiling(ilqr_handle_t h, int enable);
+int ilqr_get_kernel_times(ilqr_handle_t h, double *ms, int64_t *launches);
+
 /* number of kernel launches issued through this handle since creation */
 int64_t ilqr_launch_count(ilqr_handle_t h);
 /* last cudaError_t seen by this handle (0 = none) and its string */

@@ -11,6 +11,7 @@ NMAX, MMAX, MAX_ALPHAS = 12, 4, 16
 MODELS = {"pendulum": 0, "double_pendulum": 1, "ua_double_pendulum": 2, "ltv": 3}
 INTEGRATORS = {"euler": 0, "midpoint": 1, "rk4": 2, "backward_euler": 3}
 DTYPES = {"float64": 0, "float32": 1}
+KERNEL_CLASSES = ("linearize", "backward", "rollout", "init_rollout", "other")
 STATUS_NAMES = {0: "converged", 1: "ls_failed", 2: "maxiter", 3: "running"}
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -47,6 +48,8 @@ SIGNATURES = {
     "ilqr_forward_linesearch": (C.c_int, [_VP] * 12 + [_VP]),
     "ilqr_solve": (C.c_int, [_VP] * 8 + [_VP, _VP, _VP, C.c_size_t, _VP, _I64P]),
     "ilqr_set_trace": (C.c_int, [_VP, _VP, _VP]),
+    "ilqr_set_profiling": (C.c_int, [_VP, C.c_int]),
+    "ilqr_get_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_double), _I64P]),
     "ilqr_mpc_shift": (C.c_int, [_VP, _VP, _VP, _VP]),
     "ilqr_launch_count": (C.c_int64, [_VP]),
     "ilqr_last_cuda_error": (C.c_int, [_VP]),

@@ -2,6 +2,7 @@
 transposes between the reference's (dim,time) arrays and the kernels' batch-innermost arrays,
 and a thin handle wrapper over the C ABI.  No numerics happen here."""
 import ctypes as C
+import sys
 
 import numpy as np
 import torch
@@ -19,6 +20,42 @@ class HostArray(np.ndarray):
 
 def host(a):
     return np.asarray(a).view(HostArray)
+
+
+class _PinnedPool:
+    """Page-locked staging buffers for device->host results.  A buffer is handed out again only
+    when the caller has dropped every array that views it (refcount check), so results a caller
+    keeps (e.g. X_bar of an earlier MPC tick) are never overwritten."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def take(self, shape, dtype):
+        key = (tuple(shape), dtype)
+        lst = self._bufs.setdefault(key, [])
+        for buf, arr in lst:
+            if sys.getrefcount(arr) == 3:      # lst tuple + loop variable + getrefcount argument
+                return buf, arr
+        buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+        arr = buf.numpy()
+        lst.append((buf, arr))
+        if len(lst) > 8:                       # bound the pool; dropped buffers are freed once unreferenced
+            lst.pop(0)
+        return buf, arr
+
+
+_pool = _PinnedPool()
+
+
+def to_host(t):
+    """CUDA tensor (any strides) -> C-contiguous HostArray through pinned memory."""
+    t = t.contiguous()
+    if t.numel() * t.element_size() < (1 << 16):
+        return host(t.cpu().numpy())
+    buf, arr = _pool.take(t.shape, t.dtype)
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return arr.view(HostArray)
 
 
 def require_cuda():

@@ -105,7 +105,7 @@ class iLQR:
             v = v[0]
         if self._torch_out:
             return v
-        return D.host(v.cpu().numpy())
+        return D.to_host(v)
 
     # ------------------------------------------------------------------ attributes
     @property
@@ -286,3 +286,23 @@ class iLQR:
 
     def launches(self):
         return self._handle.launches()
+
+    def set_profiling(self, enable=True):
+        """chain CUDA events between the solve's kernels (see ilqr_set_profiling)"""
+        h = self._handle
+        h.check(h.lib.ilqr_set_profiling(h.h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """{kernel class: (total ms, launches)} accumulated since set_profiling(True)"""
+        h = self._handle
+        n = len(_cabi.KERNEL_CLASSES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        h.check(h.lib.ilqr_get_kernel_times(h.h, ms, cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_cabi.KERNEL_CLASSES)}
+
+    def reset_state(self):
+        """fresh-solver state: X = K = U_ff = 0 (iLQR_class.py:55-61); U and x_0 are left as they are"""
+        self._X.zero_()
+        self._K.zero_()
+        self._k.zero_()

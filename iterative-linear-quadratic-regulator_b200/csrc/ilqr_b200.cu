@@ -19,6 +19,7 @@
 #include <cstring>
 #include <new>
 #include <type_traits>
+#include <vector>
 
 namespace ilqr {
 
@@ -533,6 +534,12 @@ struct Handle {
     unsigned int *h_flag;     // pinned, for the pipelined early-exit poll
     int *tr_alpha;            // optional per-iteration trace (ilqr_set_trace)
     void *tr_cost;
+    // optional per-kernel timing (ilqr_set_profiling): events chained between the launches of ilqr_solve
+    int profiling;
+    std::vector<cudaEvent_t> *prof_ev;
+    std::vector<int> *prof_kind;          // kernel class that ran between event i and i+1
+    double prof_ms[ILQR_N_KERNEL_CLASSES];
+    long long prof_cnt[ILQR_N_KERNEL_CLASSES];
     cudaEvent_t ev[2];
 };
 
@@ -657,6 +664,35 @@ static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const voi
     });
 }
 
+// record a chained event after a launch of kernel class `kind` (no-op unless profiling)
+static void prof_mark(Handle *h, int kind, cudaStream_t st)
+{
+    if (!h->profiling) return;
+    const size_t i = h->prof_kind->size();
+    if (h->prof_ev->size() <= i) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        h->prof_ev->push_back(e);
+    }
+    cudaEventRecord((*h->prof_ev)[i], st);
+    h->prof_kind->push_back(kind);
+}
+
+// fold the chained events of the last solve into per-class totals (stream must be idle)
+static void prof_collect(Handle *h)
+{
+    if (!h->profiling) return;
+    for (size_t i = 1; i < h->prof_kind->size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, (*h->prof_ev)[i - 1], (*h->prof_ev)[i]) == cudaSuccess) {
+            const int kd = (*h->prof_kind)[i];
+            h->prof_ms[kd] += ms;
+            h->prof_cnt[kd] += 1;
+        }
+    }
+    h->prof_kind->clear();
+}
+
 }  // namespace ilqr
 
 using namespace ilqr;
@@ -699,6 +735,8 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
     if (!h) return ILQR_E_INVALID;
     std::memset(h, 0, sizeof(Handle));
     h->p = *p;
+    h->prof_ev = new std::vector<cudaEvent_t>();
+    h->prof_kind = new std::vector<int>();
     // alpha = 1, then *= alpha_factor per failed try; tries stop once alpha < min_alpha (:279-302)
     double a = 1.0;
     int cnt = 0;
@@ -726,6 +764,9 @@ int ilqr_destroy(ilqr_handle_t hh)
     cudaEventDestroy(h->ev[0]);
     cudaEventDestroy(h->ev[1]);
     cudaFreeHost(h->h_flag);
+    for (cudaEvent_t e : *h->prof_ev) cudaEventDestroy(e);
+    delete h->prof_ev;
+    delete h->prof_kind;
     delete h;
     return ILQR_OK;
 }
@@ -864,7 +905,10 @@ int ilqr_solve(ilqr_handle_t hh, const void * /*phi*/, const void *x0, void *X, 
     // initial rollout, alpha = 0, with the incoming X,K,k (iLQR_class.py:257-259) into candidate slab 0
     AlphaList a0;
     std::memset(&a0, 0, sizeof a0);
+    if (h->profiling) { cudaStreamSynchronize(st); prof_collect(h); }
+    prof_mark(h, ILQR_KC_OTHER, st);
     if ((rc = launch_rollout(h, 1, a0, x0, X, U, k, K, Xc, Uc, ca, nullptr, nullptr, st))) return rc;
+    prof_mark(h, ILQR_KC_INIT_ROLLOUT, st);
     if (p.dtype == ILQR_F64)
         init_kernel<double><<<grid_for(B, bsB), bsB, 0, st>>>(B, (const double *)ca, (double *)cost, winner, active,
                                                                 iters, status, p.maxiter, ctl, (double *)h->tr_cost);
@@ -883,9 +927,13 @@ int ilqr_solve(ilqr_handle_t hh, const void * /*phi*/, const void *x0, void *X, 
         for (; it < end; ++it) {
             const unsigned int *g = &ctl->n_active[it];
             const unsigned int *gprev = it > 0 ? &ctl->n_active[it - 1] : g;
+            prof_mark(h, ILQR_KC_OTHER, st);
             if ((rc = launch_commit_linearize(h, X, U, A, Bd, Xc, Uc, winner, active, 1, g, gprev, st))) return rc;
+            prof_mark(h, ILQR_KC_LINEARIZE, st);
             if ((rc = launch_backward(h, X, U, A, Bd, K, k, active, g, st))) return rc;
+            prof_mark(h, ILQR_KC_BACKWARD, st);
             if ((rc = launch_rollout(h, h->n_alpha_eff, h->alphas, x0, X, U, k, K, Xc, Uc, ca, active, g, st))) return rc;
+            prof_mark(h, ILQR_KC_ROLLOUT, st);
             if (p.dtype == ILQR_F64)
                 select_kernel<double><<<grid_for(B, bsB), bsB, 0, st>>>(B, h->n_alpha_eff, (const double *)ca,
                                                                           (double *)cost, winner, active, iters, status,
@@ -916,8 +964,27 @@ int ilqr_solve(ilqr_handle_t hh, const void * /*phi*/, const void *x0, void *X, 
         CU(cudaMemcpyAsync(&tot, &ctl->total_iters, sizeof tot, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         *total_iters = (int64_t)tot;
+        prof_collect(h);
     }
 #undef CU
+    return ILQR_OK;
+}
+
+int ilqr_set_profiling(ilqr_handle_t hh, int enable)
+{
+    Handle *h = (Handle *)hh;
+    if (!h) return ILQR_E_INVALID;
+    h->profiling = enable ? 1 : 0;
+    h->prof_kind->clear();
+    for (int i = 0; i < ILQR_N_KERNEL_CLASSES; ++i) { h->prof_ms[i] = 0.0; h->prof_cnt[i] = 0; }
+    return ILQR_OK;
+}
+
+int ilqr_get_kernel_times(ilqr_handle_t hh, double *ms, int64_t *launches)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !ms || !launches) return ILQR_E_INVALID;
+    for (int i = 0; i < ILQR_N_KERNEL_CLASSES; ++i) { ms[i] = h->prof_ms[i]; launches[i] = h->prof_cnt[i]; }
     return ILQR_OK;
 }
 

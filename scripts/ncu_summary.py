@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (ncu --set full) into a small text table for profiles/.
+
+    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<round>_<what>.txt
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+]
+
+
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    print(f"# ncu --set full --clock-control none summary of {rep}")
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        print(f"\n## {name[:150]}")
+        for k in KEYS:
+            if k in idx and r[idx[k]] not in ("", "n/a"):
+                print(f"{k:82s} {r[idx[k]]:>18s} {units[idx[k]]}")
+        try:
+            rd = float(r[idx["dram__bytes_read.sum"]].replace(",", ""))
+            wr = float(r[idx["dram__bytes_write.sum"]].replace(",", ""))
+            u = units[idx["dram__bytes_read.sum"]]
+            print(f"{'traffic = dram read + write':82s} {rd + wr:18.3f} {u}")
+        except Exception:
+            pass
+
+
+if __name__ == "__main__":
+    main()

@@ -68,3 +68,38 @@ def golden_flow(g):
         idx.append(acc)
         costs.append(cost)
     return np.array(idx), np.array(costs)
+
+
+def rounding_sensitivity(O, p, x0, n_draws=3, eps=1e-14, seed=7):
+    """How far rounding-level input noise moves a full iLQR solve of this problem.
+
+    iLQR on the pendulum swing-ups amplifies tiny differences from iteration to iteration (the accept
+    tests are discontinuous and the rollouts are chaotic), so two correct float64 implementations drift
+    apart.  This runs the CPU oracle on x0 and on `n_draws` copies of x0 perturbed by `eps` (relative,
+    absolute for zero entries) and returns the largest drift seen: per-iteration relative cost drift,
+    final X/U/K/U_ff drift, and whether the control flow (accepted step sizes) stayed the same.
+    End-to-end parity tests accept max(1e-9, 10 x this); per-kernel and per-iteration tests on identical
+    inputs stay at 1e-9 without any such allowance."""
+    rng = np.random.default_rng(seed)
+    x0 = np.asarray(x0, dtype=np.float64)
+    U0 = np.zeros((p.m, p.N))
+    base = O.optimize(p, x0, U0)
+    nb = base["iters"]
+    out = dict(cost=np.zeros(nb), X=0.0, U=0.0, K=0.0, U_ff=0.0, flow_stable=True, stable_prefix=nb)
+    for _ in range(n_draws):
+        d = rng.choice([-1.0, 1.0], size=x0.shape) * eps
+        xp = np.where(x0 != 0.0, x0 * (1.0 + d), d)
+        r = O.optimize(p, xp, U0)
+        n = min(nb, r["iters"])
+        same = r["alpha_idx"][:n] == base["alpha_idx"][:n]
+        k = n if same.all() else int(np.argmin(same))
+        if k < nb or r["iters"] != nb:
+            out["flow_stable"] = False
+        out["stable_prefix"] = min(out["stable_prefix"], k)
+        dc = np.abs(r["cost_trace"][:n] - base["cost_trace"][:n]) / np.abs(base["cost_trace"][:n])
+        out["cost"][:n] = np.maximum(out["cost"][:n], dc)
+        for key, floor in (("X", 0.0), ("U", 1e-3), ("K", 0.0), ("U_ff", 1e-3)):
+            e = float(np.max(np.abs(r[key] - base[key])) / max(float(np.max(np.abs(base[key]))), floor))
+            out[key] = max(out[key], e)
+    out["cost"] = np.maximum.accumulate(out["cost"])
+    return out
