@@ -215,7 +215,7 @@ __global__ void backward_kernel(QuadCost<T, n, m> qc, int N, int B, const T *__r
         // K = -Q_uu^-1 Q_ux, k = -Q_uu^-1 Q_u                            (:109-110; no regularisation)
         T Kt[m][n], kt[m];
         if (m == 1) {
-            const T r = T(-1) / Quu[0][0];
+            const T r = -rcp_t(Quu[0][0]);
 #pragma unroll
             for (int j = 0; j < n; ++j) Kt[0][j] = Qux[0][j] * r;
             kt[0] = Qu[0] * r;
@@ -549,7 +549,7 @@ static inline int grid_for(size_t threads, int bs) { return (int)((threads + bs 
 static inline int block_for(size_t threads)
 {
     int bs = 256;
-    while (bs > 32 && (threads + bs - 1) / bs < 2 * 148) bs >>= 1;
+    while (bs > 32 && (threads + bs - 1) / bs < 16 * 148) bs >>= 1;   // small batches: one warp per block balances best
     return bs;
 }
 

@@ -21,10 +21,51 @@ enum Integ { EULER = 0, MIDPOINT = 1, RK4 = 2, BACKWARD_EULER = 3 };
 
 #define ILQR_DEV __device__ __forceinline__
 
-ILQR_DEV void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
+// sin and cos of one FP64 argument sharing a single two-constant Cody-Waite reduction (exact under
+// FMA: the first product-difference is rounded once, the second constant carries the next 53 bits of
+// pi/2) and the fdlibm minimax kernels on [-pi/4, pi/4].  ~22 FP64 instructions, no slow-path call;
+// absolute error ~1e-16 for |x| up to ~1e9 (the generic CUDA sincos() costs about twice the
+// instructions because of its Payne-Hanek guard).  NaN/Inf propagate as NaN.
+ILQR_DEV void sincos_t(double x, double *s, double *c)
+{
+    const double magic = 6755399441055744.0;                 // 1.5 * 2^52: rounds to nearest integer
+    const double t = fma(x, 0.63661977236758138243, magic);  // x * 2/pi
+    const int k = __double2loint(t);
+    const double kd = t - magic;
+    double r = fma(-kd, 1.57079632679489655800e+00, x);
+    r = fma(-kd, 6.12323399573676603587e-17, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double sn = fma(z * r, ps, r);
+    const double cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const double a = (k & 1) ? cs : sn, b = (k & 1) ? sn : cs;
+    *s = (k & 2) ? -a : a;
+    *c = ((k + 1) & 2) ? -b : b;
+}
 ILQR_DEV void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
-ILQR_DEV double sin_t(double x) { return sin(x); }
+ILQR_DEV double sin_t(double x) { double s, c; sincos_t(x, &s, &c); return s; }
 ILQR_DEV float sin_t(float x) { return sinf(x); }
+// reciprocal to ~1 ulp: MUFU seed + two Newton steps, no special-case path (the callers' arguments
+// are a positive-definite 2x2 determinant or Q_uu, never 0/Inf/denormal in a healthy solve)
+ILQR_DEV double rcp_t(double d)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+ILQR_DEV float rcp_t(float d) { return 1.0f / d; }
 ILQR_DEV double sqrt_t(double x) { return sqrt(x); }
 ILQR_DEV float sqrt_t(float x) { return sqrtf(x); }
 ILQR_DEV double abs_t(double x) { return fabs(x); }
@@ -73,7 +114,7 @@ struct DoublePendulumSys {
         sincos_t(x[1], &s2, &c2);
         const T s12 = s1 * c2 + c1 * s2;
         const T m11 = m11_0 + c * c2, m12 = m12_0 + T(0.5) * c * c2, m22 = m12_0;
-        const T inv = T(1) / (m11 * m22 - m12 * m12);
+        const T inv = rcp_t(m11 * m22 - m12 * m12);
         const T cs2 = c * s2;
         T h1 = u[0] + T(0.5) * cs2 * (T(2) * q1d * q2d + q2d * q2d) - g1 * s12 - g2 * s1 - d1 * q1d;
         T h2 = -T(0.5) * cs2 * (q1d * q1d) - g1 * s12 - d2 * q2d;
@@ -90,7 +131,7 @@ struct DoublePendulumSys {
         sincos_t(x[1], &s2, &c2);
         const T s12 = s1 * c2 + c1 * s2, c12 = c1 * c2 - s1 * s2;
         const T m11 = m11_0 + c * c2, m12 = m12_0 + T(0.5) * c * c2, m22 = m12_0;
-        const T inv = T(1) / (m11 * m22 - m12 * m12);
+        const T inv = rcp_t(m11 * m22 - m12 * m12);
         const T i00 = inv * m22, i01 = -inv * m12, i11 = inv * m11;   // M^-1 (symmetric)
         const T cs2 = c * s2, cc2 = c * c2;
         const T w = T(2) * q1d * q2d + q2d * q2d;

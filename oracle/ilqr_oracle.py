@@ -37,19 +37,37 @@ class Problem(C.Structure):
 def build(force=False):
     """Compile the oracle with gcc (also done by __graft_entry__.build())."""
     src = os.path.join(_HERE, "ilqr_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libilqr_oracle.so"])
+    fma = _LIB_PATH.replace(".so", "_fma.so")
+    if force or not all(os.path.exists(f) and os.path.getmtime(f) >= os.path.getmtime(src) for f in (_LIB_PATH, fma)):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "all"])
     return _LIB_PATH
 
 
-_lib = None
+_libs = {}
+_variant = [""]
+
+
+class rounding_variant:
+    """Context manager: run the oracle from libilqr_oracle_fma.so, the same source compiled with
+    -ffp-contract=fast -mfma, i.e. with a different rounding in nearly every operation.  The distance
+    between the two builds measures how strongly a computation amplifies rounding-level noise
+    (tests/helpers.py uses it to calibrate parity bounds)."""
+
+    def __init__(self, name="fma"):
+        self.name = name
+
+    def __enter__(self):
+        _variant.append(self.name)
+
+    def __exit__(self, *a):
+        _variant.pop()
 
 
 def lib():
-    global _lib
-    if _lib is None:
+    v = _variant[-1]
+    if v not in _libs:
         build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(_LIB_PATH if not v else _LIB_PATH.replace(".so", f"_{v}.so"))
         P, D, I = C.POINTER(Problem), C.POINTER(C.c_double), C.POINTER(C.c_int)
         L.orc_f_cont.argtypes = [P, C.c_int, C.c_double, D, D, D]
         L.orc_f_cont_jac.argtypes = [P, C.c_int, C.c_double, D, D, D, D]
@@ -70,8 +88,8 @@ def lib():
         L.orc_optimize_batch.argtypes = [P, C.c_int, D, D, D, D, D, D, D, D, I, I, C.c_int]
         L.orc_mpc.argtypes = [P, P, C.c_double, D, C.c_int, D, D, D, I, D, D, D, D, D, D]
         L.orc_max_threads.restype = C.c_int
-        _lib = L
-    return _lib
+        _libs[v] = L
+    return _libs[v]
 
 
 def _d(a):
