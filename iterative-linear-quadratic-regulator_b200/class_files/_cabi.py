@@ -15,7 +15,7 @@ KERNEL_CLASSES = ("linearize", "backward", "rollout", "init_rollout", "other")
 STATUS_NAMES = {0: "converged", 1: "ls_failed", 2: "maxiter", 3: "running"}
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "libilqr_b200.so")
+LIB_PATH = os.environ.get("ILQR_B200_LIB") or os.path.join(_PKG_ROOT, "libilqr_b200.so")
 
 
 class Problem(C.Structure):

@@ -97,6 +97,7 @@ class System(ABC):
     # ---- point evaluations ------------------------------------------------------------
     def _points(self, x, u):
         """-> (xd [n][P], ud [m][P] or None, P, single, torch_out)"""
+        D.require_cuda()
         tdt = D.torch_dtype(self.dtype)
         torch_out = D.is_torch(x) and x.is_cuda
         xd = D.to_device(x, tdt)

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <type_traits>
 #include <vector>
@@ -103,36 +104,78 @@ __global__ void commit_linearize_kernel(Sys sys, T dt, int N, int B, T *__restri
     }
 }
 
-// K2.  One thread per trajectory; V_x, V_xx live in registers for the whole scan.
+// K2.  One thread per trajectory; V_x, V_xx live in registers for the whole scan.  The scan is
+// sequential in t, so at small batches a warp cannot hide HBM latency by occupancy: each thread
+// streams its own A_t, B_t, x_t, u_t through a DEPTH-deep shared-memory ring with cp.async
+// (LDGSTS), DEPTH-1 timesteps ahead of the arithmetic.  A thread only ever reads the ring slots it
+// filled itself, so cp.async.wait_group is the only synchronisation needed (no block barrier).
 template <typename T, int n, int m>
 struct BwdIn { T A[n][n], Bd[n][m], x[n], u[m]; };
 
-template <typename T, int n, int m>
-ILQR_DEV void bwd_load(BwdIn<T, n, m> &d, int t, int b, int B, const T *__restrict__ X, const T *__restrict__ U,
-                       const T *__restrict__ A, const T *__restrict__ Bd)
+template <int BYTES>
+ILQR_DEV void cp_async(void *smem_dst, const void *gsrc)
 {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+ILQR_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING> ILQR_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+// rows of one ring stage: A (n*n), Bd (n*m), x (n), u (m); element [row][tid]
+template <typename T, int n, int m>
+ILQR_DEV void bwd_issue(T *stage, int t, int b, int B, const T *__restrict__ X, const T *__restrict__ U,
+                        const T *__restrict__ A, const T *__restrict__ Bd)
+{
+    const int bd = blockDim.x, tid = threadIdx.x;
+    int row = 0;
 #pragma unroll
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n * n; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, A + ((size_t)t * n * n + i) * B + b);
 #pragma unroll
-        for (int j = 0; j < n; ++j) d.A[i][j] = A[(((size_t)t * n + i) * n + j) * B + b];
+    for (int i = 0; i < n * m; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, Bd + ((size_t)t * n * m + i) * B + b);
 #pragma unroll
-        for (int j = 0; j < m; ++j) d.Bd[i][j] = Bd[(((size_t)t * n + i) * m + j) * B + b];
-        d.x[i] = X[((size_t)t * n + i) * B + b];
-    }
+    for (int i = 0; i < n; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, X + ((size_t)t * n + i) * B + b);
 #pragma unroll
-    for (int j = 0; j < m; ++j) d.u[j] = U[((size_t)t * m + j) * B + b];
+    for (int i = 0; i < m; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, U + ((size_t)t * m + i) * B + b);
 }
 
 template <typename T, int n, int m>
+ILQR_DEV void bwd_read(BwdIn<T, n, m> &d, const T *stage)
+{
+    const int bd = blockDim.x, tid = threadIdx.x;
+    int row = 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < n; ++j, ++row) d.A[i][j] = stage[row * bd + tid];
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < m; ++j, ++row) d.Bd[i][j] = stage[row * bd + tid];
+#pragma unroll
+    for (int i = 0; i < n; ++i, ++row) d.x[i] = stage[row * bd + tid];
+#pragma unroll
+    for (int j = 0; j < m; ++j, ++row) d.u[j] = stage[row * bd + tid];
+}
+
+template <typename T, int n, int m, int DEPTH>
 __global__ void backward_kernel(QuadCost<T, n, m> qc, int N, int B, const T *__restrict__ X,
                                 const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
                                 T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
                                 const unsigned int *__restrict__ gate)
 {
+    constexpr int L = n * n + n * m + n + m;
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    T *ring = reinterpret_cast<T *>(ring_raw);
     if (gate && *gate == 0u) return;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     if (active && !active[b]) return;
+    const int stage_elems = L * blockDim.x;
+#pragma unroll
+    for (int s = 0; s < DEPTH; ++s) {
+        if (N - 1 - s >= 0) bwd_issue<T, n, m>(ring + s * stage_elems, N - 1 - s, b, B, X, U, A, Bd);
+        cp_async_commit();
+    }
     T Vx[n], Vxx[n][n];
     {
         T xN[n];
@@ -144,10 +187,11 @@ __global__ void backward_kernel(QuadCost<T, n, m> qc, int N, int B, const T *__r
 #pragma unroll
             for (int j = 0; j < n; ++j) Vxx[i][j] = qc.Qfs[i][j];
     }
-    BwdIn<T, n, m> cur, nxt;
-    bwd_load(cur, N - 1, b, B, X, U, A, Bd);
+    BwdIn<T, n, m> cur;
+    int stage = 0;
     for (int t = N - 1; t >= 0; --t) {
-        if (t > 0) bwd_load(nxt, t - 1, b, B, X, U, A, Bd);              // prefetch the next step's inputs
+        cp_async_wait<DEPTH - 1>();                                       // the group holding step t has landed
+        bwd_read(cur, ring + stage * stage_elems);
         T lx[n], lu[m];
         qc.grad(cur.x, cur.u, lx, lu);
         // Q_x = l_x + f_x' V_x ; Q_u = l_u + f_u' V_x                    (:100-101)
@@ -261,7 +305,9 @@ __global__ void backward_kernel(QuadCost<T, n, m> qc, int N, int B, const T *__r
             for (int i = 0; i < n; ++i) K[(((size_t)t * m + j) * n + i) * B + b] = Kt[j][i];
             k[((size_t)t * m + j) * B + b] = kt[j];
         }
-        cur = nxt;
+        if (t - DEPTH >= 0) bwd_issue<T, n, m>(ring + stage * stage_elems, t - DEPTH, b, B, X, U, A, Bd);
+        cp_async_commit();
+        stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
     }
 }
 
@@ -285,13 +331,37 @@ ILQR_DEV void fwd_load(FwdIn<T, n, m> &d, int t, int b, int B, const T *__restri
     }
 }
 
+// one step of the forward pass: control law (iLQR_class.py:181-182), store, stage cost (:187), dynamics (:185)
+template <int INTEG, class Sys, typename T>
+ILQR_DEV void rollout_step(const Sys &sys, const QuadCost<T, Sys::N, Sys::M> &qc, const FwdIn<T, Sys::N, Sys::M> &in,
+                           T alpha, int t, int b, int B, T *x, T &cost, T *__restrict__ Xw, T *__restrict__ Uw)
+{
+    constexpr int n = Sys::N, m = Sys::M;
+    T u[m], xn[n];
+#pragma unroll
+    for (int j = 0; j < m; ++j) {
+        T s = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) s += in.K[j][i] * (x[i] - in.xo[i]);
+        u[j] = in.uo[j] + alpha * in.kk[j] + s;
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + b] = x[i];
+#pragma unroll
+    for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + b] = u[j];
+    cost += qc.stage(x, u);
+    step<INTEG>(sys, qc.dt, x, u, xn);
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = xn[i];
+}
+
 template <class Sys, int INTEG, typename T>
 __global__ void rollout_kernel(Sys sys, QuadCost<T, Sys::N, Sys::M> qc, int N, int B, int n_alpha,
                                const __grid_constant__ AlphaList alphas,
                                const T *__restrict__ x0, const T *__restrict__ X_old, const T *__restrict__ U_old,
                                const T *__restrict__ k, const T *__restrict__ K, T *__restrict__ Xc,
                                T *__restrict__ Uc, T *__restrict__ cost_alpha, const int *__restrict__ active,
-                               const unsigned int *__restrict__ gate)
+                               const unsigned int *__restrict__ gate, const T *__restrict__ cost_ref)
 {
     constexpr int n = Sys::N, m = Sys::M;
     if (gate && *gate == 0u) return;
@@ -304,28 +374,51 @@ __global__ void rollout_kernel(Sys sys, QuadCost<T, Sys::N, Sys::M> qc, int N, i
     T x[n], cost = T(0);
 #pragma unroll
     for (int i = 0; i < n; ++i) x[i] = x0[(size_t)i * B + b];
-    FwdIn<T, n, m> cur, nxt;
-    fwd_load(cur, 0, b, B, X_old, U_old, k, K);
-    for (int t = 0; t < N; ++t) {
-        if (t + 1 < N) fwd_load(nxt, t + 1, b, B, X_old, U_old, k, K);
-        T u[m], xn[n];
-#pragma unroll
-        for (int j = 0; j < m; ++j) {                                    // iLQR_class.py:181-182
-            T s = T(0);
-#pragma unroll
-            for (int i = 0; i < n; ++i) s += cur.K[j][i] * (x[i] - cur.xo[i]);
-            u[j] = cur.uo[j] + alpha * cur.kk[j] + s;
+    // Early rejection: with non-negative diagonal weights every stage cost is >= 0 and the running sum
+    // is monotone in floating point, so once it exceeds the cost to beat the acceptance test
+    // `cost_new <= cost` (iLQR_class.py:289) is already decided.  Exactly the reference's decision,
+    // without rolling a diverged candidate to the end of the horizon.
+    const bool can_reject = cost_ref != nullptr && qc.monotone;
+    const T c_ref = can_reject ? cost_ref[b] : T(0);
+    // the time loop is unrolled by two over a ping-pong pair of input buffers so that the next step's
+    // nominal/gains are in flight during the current step without register-to-register copies
+#ifndef ILQR_UNROLL2
+#define ILQR_UNROLL2 1
+#endif
+#ifndef ILQR_REJECT
+#define ILQR_REJECT 0
+#endif
+#if ILQR_UNROLL2
+    FwdIn<T, n, m> in0, in1;
+    fwd_load(in0, 0, b, B, X_old, U_old, k, K);
+    for (int t = 0; t < N; t += 2) {
+        if (t + 1 < N) fwd_load(in1, t + 1, b, B, X_old, U_old, k, K);
+        rollout_step<INTEG>(sys, qc, in0, alpha, t, b, B, x, cost, Xw, Uw);
+        if (t + 1 >= N) break;
+        if (t + 2 < N) fwd_load(in0, t + 2, b, B, X_old, U_old, k, K);
+        rollout_step<INTEG>(sys, qc, in1, alpha, t + 1, b, B, x, cost, Xw, Uw);
+#if ILQR_REJECT
+        if (can_reject && !(cost <= c_ref)) {
+            cost_alpha[(size_t)ai * B + b] = cost;                       // already > cost to beat (or NaN): rejected
+            return;
         }
-#pragma unroll
-        for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + b] = x[i];
-#pragma unroll
-        for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + b] = u[j];
-        cost += qc.stage(x, u);                                          // :187
-        step<INTEG>(sys, qc.dt, x, u, xn);                               // :185
-#pragma unroll
-        for (int i = 0; i < n; ++i) x[i] = xn[i];
-        cur = nxt;
+#endif
     }
+#else
+    FwdIn<T, n, m> in0, in1;
+    fwd_load(in0, 0, b, B, X_old, U_old, k, K);
+    for (int t = 0; t < N; ++t) {
+        if (t + 1 < N) fwd_load(in1, t + 1, b, B, X_old, U_old, k, K);
+        rollout_step<INTEG>(sys, qc, in0, alpha, t, b, B, x, cost, Xw, Uw);
+        in0 = in1;
+#if ILQR_REJECT
+        if (can_reject && !(cost <= c_ref)) {
+            cost_alpha[(size_t)ai * B + b] = cost;
+            return;
+        }
+#endif
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < n; ++i) Xw[((size_t)N * n + i) * B + b] = x[i];
     cost_alpha[(size_t)ai * B + b] = cost + qc.terminal(x);              // :245
@@ -522,6 +615,11 @@ template <typename T, int n, int m> QuadCost<T, n, m> make_cost(const ilqr_probl
             if (i != j && r != 0.0) diag = false;
         }
     c.diag = diag ? 1 : 0;
+    // early rejection in the line search needs every stage cost >= 0 in floating point
+    bool mono = diag;
+    for (int i = 0; i < n && mono; ++i) mono = p.Q[i * n + i] >= 0.0 && p.Qf[i * n + i] >= 0.0;
+    for (int i = 0; i < m && mono; ++i) mono = p.R[i * m + i] >= 0.0;
+    c.monotone = mono ? 1 : 0;
     return c;
 }
 
@@ -632,33 +730,54 @@ static int launch_commit_linearize(Handle *h, void *X, void *U, void *A, void *B
     });
 }
 
+template <typename T, int n, int m, int DEPTH>
+static int launch_backward_depth(Handle *h, int bs, const QuadCost<T, n, m> &qc, const void *X, const void *U,
+                                 const void *A, const void *Bd, void *K, void *k, const int *active,
+                                 const unsigned int *gate, cudaStream_t st)
+{
+    constexpr int L = n * n + n * m + n + m;
+    const size_t smem = (size_t)DEPTH * L * bs * sizeof(T);
+    static size_t configured = 0;           // per instantiation: opt in to > 48 KB dynamic shared memory once
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(backward_kernel<T, n, m, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) { h->last_cuda = (int)e; return ILQR_E_CUDA; }
+        configured = smem;
+    }
+    backward_kernel<T, n, m, DEPTH><<<grid_for(h->p.B, bs), bs, smem, st>>>(
+        qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active, gate);
+    ILQR_CHECK_LAUNCH(h);
+    return ILQR_OK;
+}
+
 static int launch_backward(Handle *h, const void *X, const void *U, const void *A, const void *Bd, void *K, void *k,
                            const int *active, const unsigned int *gate, cudaStream_t st)
 {
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto) -> int {
         using T = decltype(tz);
         using Sys = decltype(sys);
-        const int bs = block_for(h->p.B);
-        backward_kernel<T, Sys::N, Sys::M><<<grid_for(h->p.B, bs), bs, 0, st>>>(
-            qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active, gate);
-        ILQR_CHECK_LAUNCH(h);
-        return ILQR_OK;
+        // small batches: one warp per block and a deep ring (latency bound); large batches: shallower
+        // ring so that more warps fit per SM (HBM bound)
+        if (h->p.B <= 32768)
+            return launch_backward_depth<T, Sys::N, Sys::M, 8>(h, 32, qc, X, U, A, Bd, K, k, active, gate, st);
+        return launch_backward_depth<T, Sys::N, Sys::M, 4>(h, 64, qc, X, U, A, Bd, K, k, active, gate, st);
     });
 }
 
 static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const void *x0, const void *X, const void *U,
                           const void *k, const void *K, void *Xc, void *Uc, void *cost_alpha, const int *active,
-                          const unsigned int *gate, cudaStream_t st)
+                          const unsigned int *gate, const void *cost_ref, cudaStream_t st)
 {
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
         using T = decltype(tz);
         using Sys = decltype(sys);
         constexpr int I = decltype(integ)::value;
         const size_t threads = (size_t)n_alpha * h->p.B;
-        const int bs = block_for(threads);
+        const char *bs_env = getenv("ILQR_ROLLOUT_BS");
+        const int bs = bs_env ? atoi(bs_env) : block_for(threads);
         rollout_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
             sys, qc, h->p.N, h->p.B, n_alpha, al, (const T *)x0, (const T *)X, (const T *)U, (const T *)k,
-            (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate);
+            (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });
@@ -862,7 +981,7 @@ int ilqr_rollout(ilqr_handle_t hh, const void * /*phi*/, const void *x0, double 
     AlphaList al;
     std::memset(&al, 0, sizeof al);
     al.a[0] = alpha;
-    return launch_rollout(h, 1, al, x0, X_old, U_old, k, K, X_new, U_new, cost, nullptr, nullptr, (cudaStream_t)stream);
+    return launch_rollout(h, 1, al, x0, X_old, U_old, k, K, X_new, U_new, cost, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int ilqr_forward_linesearch(ilqr_handle_t hh, const void * /*phi*/, const void *x0, const void *X, const void *U,
@@ -872,7 +991,7 @@ int ilqr_forward_linesearch(ilqr_handle_t hh, const void * /*phi*/, const void *
     Handle *h = (Handle *)hh;
     if (!h || !x0 || !X || !U || !k || !K || !cost || !Xc || !Uc || !cost_alpha || !winner) return ILQR_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_rollout(h, h->n_alpha_eff, h->alphas, x0, X, U, k, K, Xc, Uc, cost_alpha, nullptr, nullptr, st);
+    int rc = launch_rollout(h, h->n_alpha_eff, h->alphas, x0, X, U, k, K, Xc, Uc, cost_alpha, nullptr, nullptr, cost, st);
     if (rc) return rc;
     const int bs = 128;
     if (h->p.dtype == ILQR_F64)
@@ -907,7 +1026,7 @@ int ilqr_solve(ilqr_handle_t hh, const void * /*phi*/, const void *x0, void *X, 
     std::memset(&a0, 0, sizeof a0);
     if (h->profiling) { cudaStreamSynchronize(st); prof_collect(h); }
     prof_mark(h, ILQR_KC_OTHER, st);
-    if ((rc = launch_rollout(h, 1, a0, x0, X, U, k, K, Xc, Uc, ca, nullptr, nullptr, st))) return rc;
+    if ((rc = launch_rollout(h, 1, a0, x0, X, U, k, K, Xc, Uc, ca, nullptr, nullptr, nullptr, st))) return rc;
     prof_mark(h, ILQR_KC_INIT_ROLLOUT, st);
     if (p.dtype == ILQR_F64)
         init_kernel<double><<<grid_for(B, bsB), bsB, 0, st>>>(B, (const double *)ca, (double *)cost, winner, active,
@@ -918,7 +1037,8 @@ int ilqr_solve(ilqr_handle_t hh, const void * /*phi*/, const void *x0, void *X, 
     ILQR_CHECK_LAUNCH(h);
     // iterations are enqueued in blocks of CHK; the active count after each block is copied to pinned
     // memory and inspected one block later, so the device never idles waiting for the host.
-    const int CHK = 8;
+    const char *chk_env = getenv("ILQR_CHECK_EVERY");
+    const int CHK = chk_env ? (atoi(chk_env) > 0 ? atoi(chk_env) : 8) : 8;
     int pending = -1;   // event slot holding the count after the previous block
     int it = 0;
     bool stop = false;
@@ -932,7 +1052,7 @@ int ilqr_solve(ilqr_handle_t hh, const void * /*phi*/, const void *x0, void *X, 
             prof_mark(h, ILQR_KC_LINEARIZE, st);
             if ((rc = launch_backward(h, X, U, A, Bd, K, k, active, g, st))) return rc;
             prof_mark(h, ILQR_KC_BACKWARD, st);
-            if ((rc = launch_rollout(h, h->n_alpha_eff, h->alphas, x0, X, U, k, K, Xc, Uc, ca, active, g, st))) return rc;
+            if ((rc = launch_rollout(h, h->n_alpha_eff, h->alphas, x0, X, U, k, K, Xc, Uc, ca, active, g, cost, st))) return rc;
             prof_mark(h, ILQR_KC_ROLLOUT, st);
             if (p.dtype == ILQR_F64)
                 select_kernel<double><<<grid_for(B, bsB), bsB, 0, st>>>(B, h->n_alpha_eff, (const double *)ca,

@@ -21,6 +21,14 @@ enum Integ { EULER = 0, MIDPOINT = 1, RK4 = 2, BACKWARD_EULER = 3 };
 
 #define ILQR_DEV __device__ __forceinline__
 
+// minimax coefficients of the fdlibm sin/cos kernels on [-pi/4, pi/4]; in constant memory so the
+// DFMAs take them as c[bank][offset] operands instead of materialising 64-bit immediates
+__constant__ double kTrig[12] = {
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+
 // sin and cos of one FP64 argument sharing a single two-constant Cody-Waite reduction (exact under
 // FMA: the first product-difference is rounded once, the second constant carries the next 53 bits of
 // pi/2) and the fdlibm minimax kernels on [-pi/4, pi/4].  ~22 FP64 instructions, no slow-path call;
@@ -35,16 +43,16 @@ ILQR_DEV void sincos_t(double x, double *s, double *c)
     double r = fma(-kd, 1.57079632679489655800e+00, x);
     r = fma(-kd, 6.12323399573676603587e-17, r);
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double ps = fma(z, kTrig[0], kTrig[1]);
+    ps = fma(z, ps, kTrig[2]);
+    ps = fma(z, ps, kTrig[3]);
+    ps = fma(z, ps, kTrig[4]);
+    ps = fma(z, ps, kTrig[5]);
+    double pc = fma(z, kTrig[6], kTrig[7]);
+    pc = fma(z, pc, kTrig[8]);
+    pc = fma(z, pc, kTrig[9]);
+    pc = fma(z, pc, kTrig[10]);
+    pc = fma(z, pc, kTrig[11]);
     const double sn = fma(z * r, ps, r);
     const double cs = fma(z * z, pc, fma(-0.5, z, 1.0));
     const double a = (k & 1) ? cs : sn, b = (k & 1) ? sn : cs;
@@ -449,7 +457,8 @@ struct QuadCost {
     T dt;
     T xt[n];
     T Qs[n][n], Rs[m][m], Qfs[n][n];
-    int diag;   // all three weights diagonal (true for every reference script)
+    int diag;       // all three weights diagonal (true for every reference script)
+    int monotone;   // diagonal and non-negative: running cost sums are monotone (enables early rejection)
 
     ILQR_DEV T stage(const T *x, const T *u) const
     {

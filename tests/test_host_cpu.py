@@ -1,0 +1,105 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/ilqr_b200.h declares (no
+compute calls without a GPU), host-side argument checking mirrors the reference's, the horizon rule,
+and the struct layout the ctypes binding assumes."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, PKG
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "ilqr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ilqr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_what_binding_expects():
+    from class_files import _cabi
+    assert header_functions() == sorted(_cabi.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    from class_files import _cabi
+    assert os.path.exists(_cabi.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = _cabi.load()
+    for name in header_functions():
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.ilqr_version()
+    assert lib.ilqr_strerror(-3).decode().startswith("workspace")
+
+
+def test_problem_struct_matches_header_layout():
+    from class_files import _cabi
+    # 10 int32 + 4 double + 16 + 144 + 16 + 144 + 12 + 144 + 144 + 48 + 1 doubles
+    assert C.sizeof(_cabi.Problem) == 10 * 4 + 8 * (4 + 16 + 144 + 16 + 144 + 12 + 144 + 144 + 48 + 1)
+    assert _cabi.Problem.dt.offset == 40 and _cabi.Problem.phys.offset == 72
+
+
+def test_create_rejects_bad_problems_without_touching_cuda():
+    """ilqr_create validates before any CUDA call, so the ValueError counterparts work on a CPU box."""
+    from class_files import _cabi
+    lib = _cabi.load()
+    p = _cabi.Problem()
+    h = C.c_void_p()
+    p.model, p.integrator, p.n, p.m, p.N, p.B, p.n_alpha, p.maxiter, p.dt = 2, 7, 4, 1, 10, 1, 10, 5, 0.01
+    assert lib.ilqr_create(C.byref(p), C.byref(h)) == -1            # unknown integrator
+    p.integrator, p.n = 2, 3
+    assert lib.ilqr_create(C.byref(p), C.byref(h)) == -1            # dimension/model mismatch
+    p.n, p.n_alpha = 4, 99
+    assert lib.ilqr_create(C.byref(p), C.byref(h)) == -1
+    assert lib.ilqr_destroy(None) == -1 and lib.ilqr_workspace_bytes(None) == 0
+
+
+def test_unknown_integrator_and_shapes_raise_like_the_reference():
+    from class_files.systems.pendulum_sys import MyPendulum
+    from class_files.systems.UA_double_pendulum_sys import MyUADoublePendulum
+    from class_files.iLQR_class import iLQR
+    kw = dict(dt=0.01, x_target=np.array([np.pi, 0.0]), Q=np.eye(2), R=np.eye(1), Q_f=np.eye(2))
+    with pytest.raises(ValueError, match="Unknown integrator: 'rk5'"):          # system_base.py:197-198
+        MyPendulum(integrator="rk5", **kw)
+    s = MyPendulum(integrator="backward_euler", **kw)
+    assert (s.n_x, s.n_u, s.dt) == (2, 1, 0.01)
+    with pytest.raises(ValueError, match=r"U_init must have shape \(1, 400\), but got \(1, 399\)"):   # iLQR_class.py:50-52
+        iLQR(s, 4.0, np.array([1.0, 0.0]), np.zeros((1, 399)))
+    with pytest.raises(ValueError, match="x_0 must have shape"):
+        iLQR(s, 4.0, np.zeros(3), np.zeros((1, 400)))
+    ua = MyUADoublePendulum(dt=0.01, x_target=np.zeros(4), Q=np.eye(4), R=np.eye(1), Q_f=np.eye(4))
+    with pytest.raises(ValueError, match="Q must have shape"):
+        MyUADoublePendulum(dt=0.01, x_target=np.zeros(4), Q=np.eye(3), R=np.eye(1), Q_f=np.eye(4)).make_problem(10, 1)
+    p = ua.make_problem(N=500, B=7, maxiter=3)
+    assert (p.model, p.integrator, p.n, p.m, p.N, p.B, p.maxiter) == (2, 2, 4, 1, 500, 7, 3)
+    assert list(p.phys)[:9] == [9.81, 1.0, 1.0, 1.0, 1.0, 0.01, 0.01, 0.0, 0.0]
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the solver refuses to construct (after the reference's own argument checks)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from class_files.systems.pendulum_sys import MyPendulum
+    from class_files.iLQR_class import iLQR
+    s = MyPendulum(dt=0.01, x_target=np.array([np.pi, 0.0]), Q=np.eye(2), R=np.eye(1), Q_f=np.eye(2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        iLQR(s, 1.0, np.zeros(2), np.zeros((1, 100)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        s.f_fcn(np.zeros(2), np.zeros(1))
+
+
+@pytest.mark.parametrize("T,N", [(1.0, 100), (2.0, 200), (3.0, 300), (4.0, 400), (5.0, 500), (8.0, 800), (0.5, 50)])
+def test_horizon_rule(T, N, oracle):
+    """N = len(arange(0, T+dt, dt)) - 1 (iLQR_class.py:46-47)."""
+    assert oracle.horizon(T, 0.01) == N
+    assert len(np.arange(0, T + 0.01, 0.01)) - 1 == N
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may reference it."""
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "ilqr_oracle" not in txt and "jaxshim" not in txt, os.path.join(dirpath, f)
