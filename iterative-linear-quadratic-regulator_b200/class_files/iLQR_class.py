@@ -26,7 +26,8 @@ from .systems.system_base import System
 
 class iLQR:
     def __init__(self, system: System, T: float, x_0, U_init, tol: float = 1e-5, maxiter: int = 100,
-                 alpha_factor: float = 0.5, min_alpha: float = 1e-8, verbose: bool = True, n_alpha: int = 10):
+                 alpha_factor: float = 0.5, min_alpha: float = 1e-8, verbose: bool = True, n_alpha: int = 10,
+                 phi=None):
         self.system = system
         self.T = T
         self.tol = tol
@@ -76,6 +77,12 @@ class iLQR:
         self._iters = torch.zeros((B,), dtype=torch.int32, device="cuda")
         self._status = torch.full((B,), 3, dtype=torch.int32, device="cuda")
         self._trace = None
+        # per-trajectory phase of the synthetic LTV system (config 4); unused by the pendulum models
+        self._phi = None
+        if phi is not None:
+            self._phi = D.to_device(phi, self._tdt).reshape(-1).contiguous()
+            if self._phi.shape[0] != self.B:
+                raise ValueError(f"phi must hold {self.B} value(s), got {tuple(self._phi.shape)}")
         self.x_0 = x_0
         self.U = U_init
         self.total_iterations = 0
@@ -188,7 +195,7 @@ class iLQR:
         K = torch.empty_like(self._K)
         k = torch.empty_like(self._k)
         ws = h.workspace()
-        h.check(h.lib.ilqr_backward_pass(h.h, None, D.ptr(X), D.ptr(U), D.ptr(K), D.ptr(k), D.ptr(ws), ws.numel(),
+        h.check(h.lib.ilqr_backward_pass(h.h, D.ptr(self._phi), D.ptr(X), D.ptr(U), D.ptr(K), D.ptr(k), D.ptr(ws), ws.numel(),
                                          D.stream_ptr()))
         return self._out_time_major(k), self._finish(K.permute(3, 0, 1, 2))
 
@@ -205,7 +212,7 @@ class iLQR:
         Kd = self._K_in(K)
         Xn, Un = torch.empty_like(self._X), torch.empty_like(self._U)
         cost = torch.empty_like(self._cost)
-        h.check(h.lib.ilqr_rollout(h.h, None, D.ptr(x0), float(alpha), D.ptr(Xo), D.ptr(Uo), D.ptr(k), D.ptr(Kd),
+        h.check(h.lib.ilqr_rollout(h.h, D.ptr(self._phi), D.ptr(x0), float(alpha), D.ptr(Xo), D.ptr(Uo), D.ptr(k), D.ptr(Kd),
                                    D.ptr(Xn), D.ptr(Un), D.ptr(cost), D.stream_ptr()))
         c = self._finish(cost) if self.batched else self._scalar(cost)
         return self._out_time_major(Xn), self._out_time_major(Un), c
@@ -217,7 +224,7 @@ class iLQR:
         h = self._handle
         ws = h.workspace()
         tot = C.c_int64(0)
-        h.check(h.lib.ilqr_solve(h.h, None, D.ptr(self._x0), D.ptr(self._X), D.ptr(self._U), D.ptr(self._K),
+        h.check(h.lib.ilqr_solve(h.h, D.ptr(self._phi), D.ptr(self._x0), D.ptr(self._X), D.ptr(self._U), D.ptr(self._K),
                                  D.ptr(self._k), D.ptr(self._cost), D.ptr(self._iters), D.ptr(self._status), D.ptr(ws),
                                  ws.numel(), D.stream_ptr(), C.byref(tot) if sync else None))
         if sync:

@@ -112,11 +112,11 @@ class System(ABC):
             ud = ud.t().contiguous()
         return xd.t().contiguous(), ud, P, single, torch_out
 
-    def _handle(self, P):
-        h = self._point_handles.get(P)
+    def _handle(self, P, N=1):
+        h = self._point_handles.get((P, N))
         if h is None:
-            h = D.Handle(self.make_problem(N=1, B=P))
-            self._point_handles[P] = h
+            h = D.Handle(self.make_problem(N=N, B=P))
+            self._point_handles[(P, N)] = h
         return h
 
     def _out(self, t, single, torch_out):
@@ -128,11 +128,19 @@ class System(ABC):
             return t
         return D.host(t.cpu().numpy())
 
-    def _f(self, x, u):
+    def _phi(self, phi, P, dtype):
+        if phi is None:
+            return None
+        t = D.to_device(phi, dtype).reshape(-1)
+        return (t.expand(P) if t.shape[0] == 1 else t).contiguous()
+
+    def _f(self, x, u, t=0, phi=None, N=1):
+        """f(x,u); `t`, `phi` and the horizon `N` (period of the modulation) only matter for MyLTVSystem"""
         xd, ud, P, single, tout = self._points(x, u)
-        h = self._handle(P)
+        h = self._handle(P, N)
         xn = torch.empty_like(xd)
-        h.check(h.lib.ilqr_step(h.h, 0, None, D.ptr(xd), D.ptr(ud), D.ptr(xn), D.stream_ptr()))
+        ph = self._phi(phi, P, xd.dtype)
+        h.check(h.lib.ilqr_step(h.h, int(t), D.ptr(ph), D.ptr(xd), D.ptr(ud), D.ptr(xn), D.stream_ptr()))
         return self._out(xn, single, tout)
 
     def _jac(self, x, u):

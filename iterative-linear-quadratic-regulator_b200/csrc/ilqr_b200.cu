@@ -37,8 +37,8 @@ struct Control {
 };
 
 template <class Sys, int INTEG, typename T>
-__global__ void step_kernel(Sys sys, T dt, int B, const T *__restrict__ x, const T *__restrict__ u,
-                            T *__restrict__ xn)
+__global__ void step_kernel(const __grid_constant__ Sys sys, T dt, int B, int t, const T *__restrict__ phi,
+                            const T *__restrict__ x, const T *__restrict__ u, T *__restrict__ xn)
 {
     constexpr int n = Sys::N, m = Sys::M;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -48,7 +48,7 @@ __global__ void step_kernel(Sys sys, T dt, int B, const T *__restrict__ x, const
     for (int i = 0; i < n; ++i) xv[i] = x[(size_t)i * B + b];
 #pragma unroll
     for (int j = 0; j < m; ++j) uv[j] = u[(size_t)j * B + b];
-    step<INTEG>(sys, dt, xv, uv, out);
+    step<INTEG>(sys, dt, xv, uv, out, sys.time_scalar(t, phi ? phi[b] : T(0)));
 #pragma unroll
     for (int i = 0; i < n; ++i) xn[(size_t)i * B + b] = out[i];
 }
@@ -57,7 +57,8 @@ __global__ void step_kernel(Sys sys, T dt, int B, const T *__restrict__ x, const
 // copies the accepted candidate (Xc/Uc slab winner[b]) into the nominal X/U; if the trajectory is
 // active it then writes the discrete Jacobians about that nominal point.
 template <class Sys, int INTEG, typename T>
-__global__ void commit_linearize_kernel(Sys sys, T dt, int N, int B, T *__restrict__ X, T *__restrict__ U,
+__global__ void commit_linearize_kernel(const __grid_constant__ Sys sys, T dt, int N, int B,
+                                        const T *__restrict__ phi, T *__restrict__ X, T *__restrict__ U,
                                         T *__restrict__ A, T *__restrict__ Bd, const T *__restrict__ Xc,
                                         const T *__restrict__ Uc, const int *__restrict__ winner,
                                         const int *__restrict__ active, int do_linearize,
@@ -94,7 +95,7 @@ __global__ void commit_linearize_kernel(Sys sys, T dt, int N, int B, T *__restri
     }
     if (!act) return;
     T Aj[n][n], Bj[n][m];
-    step_jac<INTEG>(sys, dt, x, u, Aj, Bj);
+    step_jac<INTEG>(sys, dt, x, u, Aj, Bj, sys.time_scalar(t, phi ? phi[b] : T(0)));
 #pragma unroll
     for (int i = 0; i < n; ++i) {
 #pragma unroll
@@ -158,7 +159,7 @@ ILQR_DEV void bwd_read(BwdIn<T, n, m> &d, const T *stage)
 }
 
 template <typename T, int n, int m, int DEPTH>
-__global__ void backward_kernel(QuadCost<T, n, m> qc, int N, int B, const T *__restrict__ X,
+__global__ void backward_kernel(const __grid_constant__ QuadCost<T, n, m> qc, int N, int B, const T *__restrict__ X,
                                 const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
                                 T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
                                 const unsigned int *__restrict__ gate)
@@ -334,7 +335,8 @@ ILQR_DEV void fwd_load(FwdIn<T, n, m> &d, int t, int b, int B, const T *__restri
 // one step of the forward pass: control law (iLQR_class.py:181-182), store, stage cost (:187), dynamics (:185)
 template <int INTEG, class Sys, typename T>
 ILQR_DEV void rollout_step(const Sys &sys, const QuadCost<T, Sys::N, Sys::M> &qc, const FwdIn<T, Sys::N, Sys::M> &in,
-                           T alpha, int t, int b, int B, T *x, T &cost, T *__restrict__ Xw, T *__restrict__ Uw)
+                           T alpha, int t, int b, int B, T phi, T *x, T &cost, T *__restrict__ Xw,
+                           T *__restrict__ Uw)
 {
     constexpr int n = Sys::N, m = Sys::M;
     T u[m], xn[n];
@@ -350,14 +352,15 @@ ILQR_DEV void rollout_step(const Sys &sys, const QuadCost<T, Sys::N, Sys::M> &qc
 #pragma unroll
     for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + b] = u[j];
     cost += qc.stage(x, u);
-    step<INTEG>(sys, qc.dt, x, u, xn);
+    step<INTEG>(sys, qc.dt, x, u, xn, sys.time_scalar(t, phi));
 #pragma unroll
     for (int i = 0; i < n; ++i) x[i] = xn[i];
 }
 
 template <class Sys, int INTEG, typename T>
-__global__ void rollout_kernel(Sys sys, QuadCost<T, Sys::N, Sys::M> qc, int N, int B, int n_alpha,
-                               const __grid_constant__ AlphaList alphas,
+__global__ void rollout_kernel(const __grid_constant__ Sys sys, const __grid_constant__ QuadCost<T, Sys::N, Sys::M> qc,
+                               int N, int B, int n_alpha, const __grid_constant__ AlphaList alphas,
+                               const T *__restrict__ phi,
                                const T *__restrict__ x0, const T *__restrict__ X_old, const T *__restrict__ U_old,
                                const T *__restrict__ k, const T *__restrict__ K, T *__restrict__ Xc,
                                T *__restrict__ Uc, T *__restrict__ cost_alpha, const int *__restrict__ active,
@@ -378,6 +381,7 @@ __global__ void rollout_kernel(Sys sys, QuadCost<T, Sys::N, Sys::M> qc, int N, i
     // is monotone in floating point, so once it exceeds the cost to beat the acceptance test
     // `cost_new <= cost` (iLQR_class.py:289) is already decided.  Exactly the reference's decision,
     // without rolling a diverged candidate to the end of the horizon.
+    const T ph = phi ? phi[b] : T(0);
     const bool can_reject = cost_ref != nullptr && qc.monotone;
     const T c_ref = can_reject ? cost_ref[b] : T(0);
     // the time loop is unrolled by two over a ping-pong pair of input buffers so that the next step's
@@ -393,10 +397,10 @@ __global__ void rollout_kernel(Sys sys, QuadCost<T, Sys::N, Sys::M> qc, int N, i
     fwd_load(in0, 0, b, B, X_old, U_old, k, K);
     for (int t = 0; t < N; t += 2) {
         if (t + 1 < N) fwd_load(in1, t + 1, b, B, X_old, U_old, k, K);
-        rollout_step<INTEG>(sys, qc, in0, alpha, t, b, B, x, cost, Xw, Uw);
+        rollout_step<INTEG>(sys, qc, in0, alpha, t, b, B, ph, x, cost, Xw, Uw);
         if (t + 1 >= N) break;
         if (t + 2 < N) fwd_load(in0, t + 2, b, B, X_old, U_old, k, K);
-        rollout_step<INTEG>(sys, qc, in1, alpha, t + 1, b, B, x, cost, Xw, Uw);
+        rollout_step<INTEG>(sys, qc, in1, alpha, t + 1, b, B, ph, x, cost, Xw, Uw);
 #if ILQR_REJECT
         if (can_reject && !(cost <= c_ref)) {
             cost_alpha[(size_t)ai * B + b] = cost;                       // already > cost to beat (or NaN): rejected
@@ -409,7 +413,7 @@ __global__ void rollout_kernel(Sys sys, QuadCost<T, Sys::N, Sys::M> qc, int N, i
     fwd_load(in0, 0, b, B, X_old, U_old, k, K);
     for (int t = 0; t < N; ++t) {
         if (t + 1 < N) fwd_load(in1, t + 1, b, B, X_old, U_old, k, K);
-        rollout_step<INTEG>(sys, qc, in0, alpha, t, b, B, x, cost, Xw, Uw);
+        rollout_step<INTEG>(sys, qc, in0, alpha, t, b, B, ph, x, cost, Xw, Uw);
         in0 = in1;
 #if ILQR_REJECT
         if (can_reject && !(cost <= c_ref)) {
@@ -502,7 +506,7 @@ __global__ void winner_kernel(int B, int n_alpha, const T *__restrict__ cost_alp
 
 // materialised cost expansion (system_base.py:212-219); one thread per (t,b), t in [0,N]
 template <typename T, int n, int m>
-__global__ void cost_expansion_kernel(QuadCost<T, n, m> qc, int N, int B, const T *__restrict__ X,
+__global__ void cost_expansion_kernel(const __grid_constant__ QuadCost<T, n, m> qc, int N, int B, const T *__restrict__ X,
                                       const T *__restrict__ U, T *__restrict__ l, T *__restrict__ lx,
                                       T *__restrict__ lu, T *__restrict__ lxx, T *__restrict__ luu,
                                       T *__restrict__ lux, T *__restrict__ lf, T *__restrict__ lfx,
@@ -591,6 +595,18 @@ template <typename T, int M> DoublePendulumSys<T, M> make_double(const ilqr_prob
     s.g2 = (T)(m2 * g * l1 + (m1 * g * l1) / 2);
     s.d1 = (T)d1;
     s.d2 = (T)d2;
+    return s;
+}
+
+template <typename T> LtvSys<T> make_ltv(const ilqr_problem_t &p)
+{
+    LtvSys<T> s;
+    for (int i = 0; i < 12; ++i) {
+        for (int j = 0; j < 12; ++j) { s.Ac[i][j] = (T)p.Ac[i * 12 + j]; s.E[i][j] = (T)p.E[i * 12 + j]; }
+        for (int j = 0; j < 4; ++j) s.Bc[i][j] = (T)p.Bc[i * 4 + j];
+    }
+    s.amp = (T)p.ltv_amp;
+    s.two_pi_over_N = (T)(2.0 * 3.14159265358979323846 / (double)p.N);
     return s;
 }
 
@@ -700,6 +716,11 @@ template <typename T, class F> static int dispatch_model(const Handle *h, F &&f)
     case ILQR_PENDULUM: return dispatch_integ<T>(h, make_pendulum<T>(h->p), f);
     case ILQR_DOUBLE_PENDULUM: return dispatch_integ<T>(h, make_double<T, 2>(h->p), f);
     case ILQR_UA_DOUBLE_PENDULUM: return dispatch_integ<T>(h, make_double<T, 1>(h->p), f);
+    case ILQR_LTV: {   // forward Euler only (validated in ilqr_create)
+        auto sys = make_ltv<T>(h->p);
+        auto qc = make_cost<T, 12, 4>(h->p);
+        return f(T(0), sys, qc, std::integral_constant<int, EULER>{});
+    }
     }
     return ILQR_E_INVALID;
 }
@@ -712,7 +733,7 @@ template <class F> static int dispatch(const Handle *h, F &&f)
 
 // ---- launch helpers -----------------------------------------------------------------------
 
-static int launch_commit_linearize(Handle *h, void *X, void *U, void *A, void *Bd, const void *Xc, const void *Uc,
+static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U, void *A, void *Bd, const void *Xc, const void *Uc,
                                    const int *winner, const int *active, int do_lin, const unsigned int *g0,
                                    const unsigned int *g1, cudaStream_t st)
 {
@@ -723,7 +744,7 @@ static int launch_commit_linearize(Handle *h, void *X, void *U, void *A, void *B
         const size_t threads = (size_t)(h->p.N + 1) * h->p.B;
         const int bs = 128;
         commit_linearize_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
-            sys, qc.dt, h->p.N, h->p.B, (T *)X, (T *)U, (T *)A, (T *)Bd, (const T *)Xc, (const T *)Uc, winner, active,
+            sys, qc.dt, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (T *)A, (T *)Bd, (const T *)Xc, (const T *)Uc, winner, active,
             do_lin, g0, g1);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
@@ -758,13 +779,18 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
         using Sys = decltype(sys);
         // small batches: one warp per block and a deep ring (latency bound); large batches: shallower
         // ring so that more warps fit per SM (HBM bound)
-        if (h->p.B <= 32768)
-            return launch_backward_depth<T, Sys::N, Sys::M, 8>(h, 32, qc, X, U, A, Bd, K, k, active, gate, st);
-        return launch_backward_depth<T, Sys::N, Sys::M, 4>(h, 64, qc, X, U, A, Bd, K, k, active, gate, st);
+        if constexpr (Sys::N > 4) {
+            // n = 12, m = 4: a ring stage is 208 rows; two stages of one warp fit the 227 KB limit
+            return launch_backward_depth<T, Sys::N, Sys::M, 2>(h, 32, qc, X, U, A, Bd, K, k, active, gate, st);
+        } else {
+            if (h->p.B <= 32768)
+                return launch_backward_depth<T, Sys::N, Sys::M, 8>(h, 32, qc, X, U, A, Bd, K, k, active, gate, st);
+            return launch_backward_depth<T, Sys::N, Sys::M, 4>(h, 64, qc, X, U, A, Bd, K, k, active, gate, st);
+        }
     });
 }
 
-static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const void *x0, const void *X, const void *U,
+static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const void *phi, const void *x0, const void *X, const void *U,
                           const void *k, const void *K, void *Xc, void *Uc, void *cost_alpha, const int *active,
                           const unsigned int *gate, const void *cost_ref, cudaStream_t st)
 {
@@ -776,7 +802,7 @@ static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const voi
         const char *bs_env = getenv("ILQR_ROLLOUT_BS");
         const int bs = bs_env ? atoi(bs_env) : block_for(threads);
         rollout_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
-            sys, qc, h->p.N, h->p.B, n_alpha, al, (const T *)x0, (const T *)X, (const T *)U, (const T *)k,
+            sys, qc, h->p.N, h->p.B, n_alpha, al, (const T *)phi, (const T *)x0, (const T *)X, (const T *)U, (const T *)k,
             (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
@@ -845,6 +871,7 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
     case ILQR_PENDULUM: n = 2; m = 1; break;
     case ILQR_DOUBLE_PENDULUM: n = 4; m = 2; break;
     case ILQR_UA_DOUBLE_PENDULUM: n = 4; m = 1; break;
+    case ILQR_LTV: n = 12; m = 4; if (p->integrator != ILQR_EULER) return ILQR_E_INVALID; break;
     default: return ILQR_E_INVALID;
     }
     if (p->n != n || p->m != m) return ILQR_E_INVALID;
@@ -900,7 +927,7 @@ size_t ilqr_workspace_bytes(ilqr_handle_t hh)
 int64_t ilqr_launch_count(ilqr_handle_t hh) { return hh ? ((Handle *)hh)->launches : 0; }
 int ilqr_last_cuda_error(ilqr_handle_t hh) { return hh ? ((Handle *)hh)->last_cuda : 0; }
 
-int ilqr_step(ilqr_handle_t hh, int /*t*/, const void * /*phi*/, const void *x, const void *u, void *xn, void *stream)
+int ilqr_step(ilqr_handle_t hh, int t, const void *phi, const void *x, const void *u, void *xn, void *stream)
 {
     Handle *h = (Handle *)hh;
     if (!h || !x || !u || !xn) return ILQR_E_INVALID;
@@ -910,17 +937,17 @@ int ilqr_step(ilqr_handle_t hh, int /*t*/, const void * /*phi*/, const void *x, 
         using Sys = decltype(sys);
         constexpr int I = decltype(integ)::value;
         const int bs = block_for(h->p.B);
-        step_kernel<Sys, I, T><<<grid_for(h->p.B, bs), bs, 0, st>>>(sys, qc.dt, h->p.B, (const T *)x, (const T *)u, (T *)xn);
+        step_kernel<Sys, I, T><<<grid_for(h->p.B, bs), bs, 0, st>>>(sys, qc.dt, h->p.B, t, (const T *)phi, (const T *)x, (const T *)u, (T *)xn);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });
 }
 
-int ilqr_linearize(ilqr_handle_t hh, const void * /*phi*/, const void *X, const void *U, void *A, void *Bd, void *stream)
+int ilqr_linearize(ilqr_handle_t hh, const void *phi, const void *X, const void *U, void *A, void *Bd, void *stream)
 {
     Handle *h = (Handle *)hh;
     if (!h || !X || !U || !A || !Bd) return ILQR_E_INVALID;
-    return launch_commit_linearize(h, (void *)X, (void *)U, A, Bd, nullptr, nullptr, nullptr, nullptr, 1, nullptr,
+    return launch_commit_linearize(h, phi, (void *)X, (void *)U, A, Bd, nullptr, nullptr, nullptr, nullptr, 1, nullptr,
                                    nullptr, (cudaStream_t)stream);
 }
 
@@ -973,7 +1000,7 @@ int ilqr_backward_pass(ilqr_handle_t hh, const void *phi, const void *X, const v
     return ilqr_backward(hh, X, U, w + L.A, w + L.Bd, K, k, stream);
 }
 
-int ilqr_rollout(ilqr_handle_t hh, const void * /*phi*/, const void *x0, double alpha, const void *X_old,
+int ilqr_rollout(ilqr_handle_t hh, const void *phi, const void *x0, double alpha, const void *X_old,
                  const void *U_old, const void *k, const void *K, void *X_new, void *U_new, void *cost, void *stream)
 {
     Handle *h = (Handle *)hh;
@@ -981,17 +1008,17 @@ int ilqr_rollout(ilqr_handle_t hh, const void * /*phi*/, const void *x0, double 
     AlphaList al;
     std::memset(&al, 0, sizeof al);
     al.a[0] = alpha;
-    return launch_rollout(h, 1, al, x0, X_old, U_old, k, K, X_new, U_new, cost, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    return launch_rollout(h, 1, al, phi, x0, X_old, U_old, k, K, X_new, U_new, cost, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-int ilqr_forward_linesearch(ilqr_handle_t hh, const void * /*phi*/, const void *x0, const void *X, const void *U,
+int ilqr_forward_linesearch(ilqr_handle_t hh, const void *phi, const void *x0, const void *X, const void *U,
                             const void *k, const void *K, const void *cost, void *Xc, void *Uc, void *cost_alpha,
                             int32_t *winner, void *stream)
 {
     Handle *h = (Handle *)hh;
     if (!h || !x0 || !X || !U || !k || !K || !cost || !Xc || !Uc || !cost_alpha || !winner) return ILQR_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_rollout(h, h->n_alpha_eff, h->alphas, x0, X, U, k, K, Xc, Uc, cost_alpha, nullptr, nullptr, cost, st);
+    int rc = launch_rollout(h, h->n_alpha_eff, h->alphas, phi, x0, X, U, k, K, Xc, Uc, cost_alpha, nullptr, nullptr, cost, st);
     if (rc) return rc;
     const int bs = 128;
     if (h->p.dtype == ILQR_F64)
@@ -1004,7 +1031,7 @@ int ilqr_forward_linesearch(ilqr_handle_t hh, const void * /*phi*/, const void *
     return ILQR_OK;
 }
 
-int ilqr_solve(ilqr_handle_t hh, const void * /*phi*/, const void *x0, void *X, void *U, void *K, void *k, void *cost,
+int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void *U, void *K, void *k, void *cost,
                int32_t *iters, int32_t *status, void *ws, size_t ws_bytes, void *stream, int64_t *total_iters)
 {
     Handle *h = (Handle *)hh;
@@ -1026,7 +1053,7 @@ int ilqr_solve(ilqr_handle_t hh, const void * /*phi*/, const void *x0, void *X, 
     std::memset(&a0, 0, sizeof a0);
     if (h->profiling) { cudaStreamSynchronize(st); prof_collect(h); }
     prof_mark(h, ILQR_KC_OTHER, st);
-    if ((rc = launch_rollout(h, 1, a0, x0, X, U, k, K, Xc, Uc, ca, nullptr, nullptr, nullptr, st))) return rc;
+    if ((rc = launch_rollout(h, 1, a0, phi, x0, X, U, k, K, Xc, Uc, ca, nullptr, nullptr, nullptr, st))) return rc;
     prof_mark(h, ILQR_KC_INIT_ROLLOUT, st);
     if (p.dtype == ILQR_F64)
         init_kernel<double><<<grid_for(B, bsB), bsB, 0, st>>>(B, (const double *)ca, (double *)cost, winner, active,
@@ -1048,11 +1075,11 @@ int ilqr_solve(ilqr_handle_t hh, const void * /*phi*/, const void *x0, void *X, 
             const unsigned int *g = &ctl->n_active[it];
             const unsigned int *gprev = it > 0 ? &ctl->n_active[it - 1] : g;
             prof_mark(h, ILQR_KC_OTHER, st);
-            if ((rc = launch_commit_linearize(h, X, U, A, Bd, Xc, Uc, winner, active, 1, g, gprev, st))) return rc;
+            if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, active, 1, g, gprev, st))) return rc;
             prof_mark(h, ILQR_KC_LINEARIZE, st);
             if ((rc = launch_backward(h, X, U, A, Bd, K, k, active, g, st))) return rc;
             prof_mark(h, ILQR_KC_BACKWARD, st);
-            if ((rc = launch_rollout(h, h->n_alpha_eff, h->alphas, x0, X, U, k, K, Xc, Uc, ca, active, g, cost, st))) return rc;
+            if ((rc = launch_rollout(h, h->n_alpha_eff, h->alphas, phi, x0, X, U, k, K, Xc, Uc, ca, active, g, cost, st))) return rc;
             prof_mark(h, ILQR_KC_ROLLOUT, st);
             if (p.dtype == ILQR_F64)
                 select_kernel<double><<<grid_for(B, bsB), bsB, 0, st>>>(B, h->n_alpha_eff, (const double *)ca,
@@ -1078,7 +1105,7 @@ int ilqr_solve(ilqr_handle_t hh, const void * /*phi*/, const void *x0, void *X, 
         }
     }
     // commit the candidates accepted in the last executed iteration (no linearization)
-    if ((rc = launch_commit_linearize(h, X, U, A, Bd, Xc, Uc, winner, nullptr, 0, nullptr, nullptr, st))) return rc;
+    if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, nullptr, 0, nullptr, nullptr, st))) return rc;
     if (total_iters) {
         unsigned long long tot = 0;
         CU(cudaMemcpyAsync(&tot, &ctl->total_iters, sizeof tot, cudaMemcpyDeviceToHost, st));

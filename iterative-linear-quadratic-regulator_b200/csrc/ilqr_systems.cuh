@@ -90,7 +90,9 @@ ILQR_DEV float abs_t(float x) { return fabsf(x); }
 template <typename T>
 struct PendulumSys {
     static constexpr int NQ = 1, N = 2, M = 1;
+    static constexpr bool FIRST_ORDER = false;
     T gl, d;   // g/l, damping
+    ILQR_DEV T time_scalar(int, T) const { return T(0); }
     ILQR_DEV void acc(const T *x, const T *u, T *a) const
     {
         a[0] = u[0] - d * x[1] - gl * sin_t(x[0]);
@@ -109,6 +111,8 @@ struct PendulumSys {
 template <typename T, int M_>
 struct DoublePendulumSys {
     static constexpr int NQ = 2, N = 4, M = M_;
+    static constexpr bool FIRST_ORDER = false;
+    ILQR_DEV T time_scalar(int, T) const { return T(0); }
     // derived constants (host, double precision):
     //   c = m2 l1 l2, m11_0 = m1 l1^2/4 + m2 l1^2 + m2 l2^2/4 + th1 + th2, m12_0 = m22 = m2 l2^2/4 + th2,
     //   g1 = m2 g l2/2, g2 = m2 g l1 + m1 g l1/2
@@ -165,6 +169,34 @@ struct DoublePendulumSys {
         }
         Bq[0][0] = i00; Bq[1][0] = i01;
         if (M == 2) { Bq[0][M - 1] = i01; Bq[1][M - 1] = i11; }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Synthetic linear time-varying system (BASELINE.json config 4; closest reference
+// artefact matlab/CLASSES/Linear_iLQR_CLASS.m): first order, n = 12, m = 4,
+//     x_dot = (Ac + w E) x + Bc u,   w = amp * sin(2 pi t / N + phi_b)  (per trajectory phase),
+// discretised with forward Euler only.  The matrices are generated in the kernel from the constants,
+// never stored per trajectory.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct LtvSys {
+    static constexpr int NQ = 0, N = 12, M = 4;
+    static constexpr bool FIRST_ORDER = true;
+    T Ac[N][N], E[N][N], Bc[N][M];
+    T amp, two_pi_over_N;
+    ILQR_DEV T time_scalar(int t, T phi) const { return amp * sin_t(two_pi_over_N * T(t) + phi); }
+    ILQR_DEV void xdot(T w, const T *x, const T *u, T *xd) const
+    {
+        for (int i = 0; i < N; ++i) {
+            T s1 = T(0), s2 = T(0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) { s1 += Ac[i][j] * x[j]; s2 += E[i][j] * x[j]; }
+            T s3 = T(0);
+#pragma unroll
+            for (int j = 0; j < M; ++j) s3 += Bc[i][j] * u[j];
+            xd[i] = (s1 + w * s2) + s3;
+        }
     }
 };
 
@@ -277,9 +309,15 @@ ILQR_DEV void backward_euler_step(const Sys &s, T dt, const T *x, const T *u, T 
 }
 
 template <int INTEG, class Sys, typename T>
-ILQR_DEV void step(const Sys &s, T dt, const T *x, const T *u, T *xn)
+ILQR_DEV void step(const Sys &s, T dt, const T *x, const T *u, T *xn, T w = T(0))
 {
     constexpr int n = Sys::N;
+    if constexpr (Sys::FIRST_ORDER) {
+        T xd[n];
+        s.xdot(w, x, u, xd);
+#pragma unroll
+        for (int i = 0; i < n; ++i) xn[i] = x[i] + xd[i] * dt;
+    } else
     if (INTEG == EULER) {
         T k1[n];
         f_cont(s, x, u, k1);
@@ -332,9 +370,17 @@ ILQR_DEV void mul_Ac(const T (*J)[n], const T (*S)[cols], T (*out)[cols])
 
 // discrete Jacobians A = d step/dx (n x n), Bd = d step/du (n x m)
 template <int INTEG, class Sys, typename T>
-ILQR_DEV void step_jac(const Sys &s, T dt, const T *x, const T *u, T (*A)[Sys::N], T (*Bd)[Sys::M])
+ILQR_DEV void step_jac(const Sys &s, T dt, const T *x, const T *u, T (*A)[Sys::N], T (*Bd)[Sys::M], T w = T(0))
 {
     constexpr int n = Sys::N, NQ = Sys::NQ, M = Sys::M;
+    if constexpr (Sys::FIRST_ORDER) {
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) A[i][j] = ((i == j) ? T(1) : T(0)) + dt * (s.Ac[i][j] + w * s.E[i][j]);
+#pragma unroll
+            for (int j = 0; j < M; ++j) Bd[i][j] = dt * s.Bc[i][j];
+        }
+    } else {
     T a[NQ], J[NQ][n], Bq[NQ][M];
     if (INTEG == EULER) {
         s.acc_jac(x, u, a, J, Bq);
@@ -444,6 +490,7 @@ ILQR_DEV void step_jac(const Sys &s, T dt, const T *x, const T *u, T (*A)[Sys::N
 #pragma unroll
             for (int j = 0; j < M; ++j) Bd[i][j] = h * Au[i][j];
         }
+    }
     }
 }
 
