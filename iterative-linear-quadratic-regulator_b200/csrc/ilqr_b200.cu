@@ -312,6 +312,148 @@ __global__ void backward_kernel(const __grid_constant__ QuadCost<T, n, m> qc, in
     }
 }
 
+// K2, small-batch variant for n = 4, m = 1 (the double-pendulum headline case): FOUR lanes per
+// trajectory.  With a few thousand trajectories the one-thread-per-trajectory scan runs one warp per
+// SM and is bound by dependent-instruction issue (~490 instructions per step in one thread).  Here
+// lane j of a 4-lane group owns column j: it computes Y[:,j] = V_xx A[:,j], Q_xx[:,j] = l_xx[:,j] +
+// A' Y[:,j], Q_ux[j] = B' Y[:,j], Q_x[j], K[j] and the new V_xx[:,j], V_x[j]; Q_uu, Q_u, k are cheap and
+// computed redundantly.  Every lane keeps a full copy of V_xx, V_x, re-assembled each step through a
+// shared-memory exchange (two __syncwarp per step).  A warp holds 8 trajectories; their A_t,B_t,x_t,u_t
+// (25 values each) arrive through a DEPTH-deep cp.async ring filled cooperatively (7 LDGSTS per step
+// per warp, 64-byte global segments).  ~115 instructions per lane per step.
+template <typename T, int DEPTH>
+__global__ void __launch_bounds__(32)
+backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, int B, const T *__restrict__ X,
+                           const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
+                           T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
+                           const unsigned int *__restrict__ gate)
+{
+    constexpr int n = 4, L = 25, LP = 26, SLOTS = 8;       // LP: padded slot stride (bank-conflict free LDS.128)
+    extern __shared__ __align__(16) unsigned char lanes_raw[];
+    T *ring = reinterpret_cast<T *>(lanes_raw);             // [DEPTH][SLOTS][LP]
+    T *exQ = ring + DEPTH * SLOTS * LP;                     // [SLOTS][4]   Q_ux exchange
+    T *exV = exQ + SLOTS * 4;                               // [SLOTS][20]  V_xx (row-major 16) + V_x (4)
+    if (gate && *gate == 0u) return;
+    const int lane = threadIdx.x, s = lane >> 2, j = lane & 3;
+    const int b_raw = blockIdx.x * SLOTS + s;
+    const bool valid = b_raw < B && (!active || active[b_raw < B ? b_raw : B - 1] != 0);
+    if (__ballot_sync(0xffffffffu, valid) == 0u) return;
+    const int b = b_raw < B ? b_raw : B - 1;                // clamped: out-of-range slots compute on a copy, never store
+
+    // cooperative fill of one ring stage: element e = row * 8 + slot, 32 elements per LDGSTS
+    const int f_slot = lane & 7, f_row0 = lane >> 3;
+    const int f_b = min(blockIdx.x * SLOTS + f_slot, B - 1);
+    auto issue = [&](int stage, int t) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int row = f_row0 + 4 * i;
+            if (row < L) {
+                const T *src = row < 16 ? A + ((size_t)t * 16 + row) * B + f_b
+                             : row < 20 ? Bd + ((size_t)t * 4 + (row - 16)) * B + f_b
+                             : row < 24 ? X + ((size_t)t * 4 + (row - 20)) * B + f_b
+                                        : U + (size_t)t * B + f_b;
+                cp_async<sizeof(T)>(ring + (stage * SLOTS + f_slot) * LP + row, src);
+            }
+        }
+    };
+#pragma unroll
+    for (int st = 0; st < DEPTH; ++st) {
+        if (N - 1 - st >= 0) issue(st, N - 1 - st);
+        cp_async_commit();
+    }
+    // per-lane constants: row j of dt*Qs (for l_x[j]) and column j of dt*Qs (for l_xx[:,j])
+    T qrow[n], qcol[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) { qrow[i] = qc.Qs[j][i] * qc.dt; qcol[i] = qc.Qs[i][j] * qc.dt; }
+    const T xtj[n] = { qc.xt[0], qc.xt[1], qc.xt[2], qc.xt[3] };
+    const T luu = qc.Rs[0][0] * qc.dt;
+    T Vx[n], Vxx[n][n];
+    {
+        T xN[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) xN[i] = X[((size_t)N * n + i) * B + b];
+        qc.terminal_grad(xN, Vx);                                        // iLQR_class.py:136-138
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int c = 0; c < n; ++c) Vxx[i][c] = qc.Qfs[i][c];
+    }
+    int stage = 0;
+    for (int t = N - 1; t >= 0; --t) {
+        cp_async_wait<DEPTH - 1>();
+        __syncwarp();                                                    // other lanes' copies are visible
+        const T *in = ring + (stage * SLOTS + s) * LP;
+        T Am[n][n], Bv[n], x[n], Acol[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int c = 0; c < n; ++c) Am[i][c] = in[i * 4 + c];
+            Bv[i] = in[16 + i];
+            x[i] = in[20 + i];
+            Acol[i] = in[i * 4 + j];
+        }
+        const T u = in[24];
+        // Y = V_xx A[:,j] ; Q_xx[:,j] = l_xx[:,j] + A' Y ; Q_ux[j] = B' Y          (iLQR_class.py:102-103)
+        T Y[n], Qxxc[n], Quxj = T(0), Qxj = T(0), Qu = T(0), Quu = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T sum = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) sum += Vxx[i][l] * Acol[l];
+            Y[i] = sum;
+        }
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T sum = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) sum += Am[l][i] * Y[l];
+            Qxxc[i] = qcol[i] + sum;
+            Quxj += Bv[i] * Y[i];
+        }
+        // Q_uu = l_uu + B' V_xx B, Q_u = l_u + B' V_x (redundant in the 4 lanes) ; Q_x[j]   (:100-101,104)
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T vb = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) vb += Vxx[i][l] * Bv[l];
+            Quu += Bv[i] * vb;
+            Qu += Bv[i] * Vx[i];
+            Qxj += Acol[i] * Vx[i];
+        }
+        Quu += luu;
+        Qu += luu * u;
+        T lxj = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) lxj += qrow[i] * (x[i] - xtj[i]);
+        Qxj += lxj;
+        const T r = -rcp_t(Quu);                                         // (:109-110)
+        const T Kj = Quxj * r, kk = Qu * r;
+        const T Vxj = Qxj + Kj * Qu;                                     // (:113)
+        exQ[s * 4 + j] = Quxj;
+        __syncwarp();
+        T Quxa[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) Quxa[i] = exQ[s * 4 + i];
+#pragma unroll
+        for (int i = 0; i < n; ++i) exV[s * 20 + i * 4 + j] = Qxxc[i] + Quxa[i] * Kj;     // V_xx[:,j]   (:114)
+        exV[s * 20 + 16 + j] = Vxj;
+        if (valid) {
+            K[((size_t)t * n + j) * B + b] = Kj;
+            if (j == 0) k[(size_t)t * B + b] = kk;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int c = 0; c < n; ++c) Vxx[i][c] = exV[s * 20 + i * 4 + c];
+            Vx[i] = exV[s * 20 + 16 + i];
+        }
+        if (t - DEPTH >= 0) issue(stage, t - DEPTH);                     // every lane is past its reads of this stage
+        cp_async_commit();
+        stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
+    }
+}
+
 // K3.  One thread per (alpha, b); b fastest so loads of the shared nominal/gains coalesce and are
 // served once from L2 for all alphas.
 template <typename T, int n, int m>
@@ -446,47 +588,64 @@ __global__ void init_kernel(int B, const T *__restrict__ cost_alpha, T *__restri
 }
 
 // K4.  iLQR_class.py:265-271 (convergence), :281-307 (first acceptable alpha, failure => stop)
+// The line search may be split in two waves of step sizes (alphas [0,n_first) rolled out eagerly,
+// [n_first,n_alpha) only for trajectories that accepted none of the first wave; see ilqr_solve).
+//   wave 0: every active trajectory; tries a in [a_lo,a_hi); if none is acceptable and a second wave
+//           exists (defer != nullptr) the trajectory is marked in defer[] instead of failing.
+//   wave 1: the marked trajectories only; tries the remaining step sizes and finalises.
+// n2_count points at the deferred-trajectory counter of this iteration (gate of the second wave).
 template <typename T>
-__global__ void select_kernel(int B, int n_alpha, const T *__restrict__ cost_alpha, T *__restrict__ cost,
-                              int *__restrict__ winner, int *__restrict__ active, int *__restrict__ iters,
-                              int *__restrict__ status, T tol, int it, int maxiter, Control *ctl,
+__global__ void select_kernel(int B, int a_lo, int a_hi, int wave, const T *__restrict__ cost_alpha,
+                              T *__restrict__ cost, int *__restrict__ winner, int *__restrict__ active,
+                              int *__restrict__ defer, int *__restrict__ iters, int *__restrict__ status, T tol,
+                              int it, int maxiter, Control *ctl, unsigned int *n2_count,
                               int *__restrict__ tr_alpha, T *__restrict__ tr_cost)
 {
     if (ctl->n_active[it] == 0u) return;
+    if (wave == 1 && *n2_count == 0u) return;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    bool still = false, ran = false;
+    bool still = false, ran = false, deferred = false;
     if (b < B) {
-        if (!active[b]) {
-            winner[b] = -1;
+        const bool mine = wave == 0 ? active[b] != 0 : defer[b] != 0;
+        if (!mine) {
+            if (wave == 0) winner[b] = -1;
         } else {
-            ran = true;
+            ran = wave == 0;
+            if (wave == 1) defer[b] = 0;
             const T c0 = cost[b];
             int w = -1;
             T cw = c0;
-            for (int a = 0; a < n_alpha; ++a) {
+            for (int a = a_lo; a < a_hi; ++a) {
                 const T c = cost_alpha[(size_t)a * B + b];
                 if (c <= c0) { w = a; cw = c; break; }                   // NaN compares false, as in Python
             }
             winner[b] = w;
             iters[b] = it + 1;
-            if (tr_alpha) tr_alpha[(size_t)it * B + b] = w;
-            if (tr_cost) tr_cost[(size_t)(it + 1) * B + b] = cw;
-            if (w < 0) {
-                status[b] = ILQR_ST_LS_FAILED;
-                active[b] = 0;
+            if (w < 0 && wave == 0 && defer != nullptr) {
+                defer[b] = 1;                                            // decided by the second wave
+                deferred = true;
             } else {
-                cost[b] = cw;
-                if (it + 1 >= maxiter) { status[b] = ILQR_ST_MAXITER; active[b] = 0; }
-                else if (abs_t(cw - c0) <= tol) { status[b] = ILQR_ST_CONVERGED; active[b] = 0; }
-                else still = true;
+                if (tr_alpha) tr_alpha[(size_t)it * B + b] = w;
+                if (tr_cost) tr_cost[(size_t)(it + 1) * B + b] = cw;
+                if (w < 0) {
+                    status[b] = ILQR_ST_LS_FAILED;
+                    active[b] = 0;
+                } else {
+                    cost[b] = cw;
+                    if (it + 1 >= maxiter) { status[b] = ILQR_ST_MAXITER; active[b] = 0; }
+                    else if (abs_t(cw - c0) <= tol) { status[b] = ILQR_ST_CONVERGED; active[b] = 0; }
+                    else still = true;
+                }
             }
         }
     }
     const unsigned full = 0xffffffffu;
     const unsigned ns = __popc(__ballot_sync(full, still)), nr = __popc(__ballot_sync(full, ran));
+    const unsigned nd = __popc(__ballot_sync(full, deferred));
     if ((threadIdx.x & 31) == 0) {
         if (ns) atomicAdd(&ctl->n_active[it + 1], ns);
         if (nr) atomicAdd(&ctl->total_iters, (unsigned long long)nr);
+        if (nd) atomicAdd(n2_count, nd);
     }
 }
 
@@ -642,6 +801,7 @@ template <typename T, int n, int m> QuadCost<T, n, m> make_cost(const ilqr_probl
 struct Handle {
     ilqr_problem_t p;
     int n_alpha_eff;          // tries actually made: stops once alpha < min_alpha (iLQR_class.py:300-302)
+    int n_first;              // step sizes rolled out eagerly (first wave); the rest only where needed
     AlphaList alphas;
     long long launches;
     int last_cuda;
@@ -668,7 +828,7 @@ static inline int block_for(size_t threads)
 }
 
 struct WsLayout {
-    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, active, total;
+    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, active, defer, total;
 };
 
 static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
@@ -678,7 +838,8 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     WsLayout L;
     size_t off = 0;
-    L.ctl = off; off = al(off + sizeof(Control) + sizeof(unsigned int) * (size_t)(p.maxiter + 2));
+    // n_active[maxiter + 2] followed by the per-iteration deferred (second-wave) counters [maxiter + 2]
+    L.ctl = off; off = al(off + sizeof(Control) + sizeof(unsigned int) * 2 * (size_t)(p.maxiter + 2));
     L.A = off; off = al(off + w * N * n * n * B);
     L.Bd = off; off = al(off + w * N * n * m * B);
     L.Xc = off; off = al(off + w * (size_t)n_alpha * (N + 1) * n * B);
@@ -686,6 +847,7 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
     L.cost_alpha = off; off = al(off + w * (size_t)n_alpha * B);
     L.winner = off; off = al(off + 4 * B);
     L.active = off; off = al(off + 4 * B);
+    L.defer = off; off = al(off + 4 * B);
     L.total = off;
     return L;
 }
@@ -779,6 +941,20 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
         using Sys = decltype(sys);
         // small batches: one warp per block and a deep ring (latency bound); large batches: shallower
         // ring so that more warps fit per SM (HBM bound)
+        if constexpr (Sys::N == 4 && Sys::M == 1) {
+            // small batches of the n=4, m=1 case: four lanes per trajectory (latency bound regime)
+            const char *lanes_env = getenv("ILQR_BACKWARD_LANES");
+            const bool lanes = lanes_env ? atoi(lanes_env) != 0 : h->p.B <= 32768;
+            if (lanes) {
+                constexpr int DEPTH = 8, SLOTS = 8, LP = 26;
+                const size_t smem = sizeof(T) * (size_t)(DEPTH * SLOTS * LP + SLOTS * 4 + SLOTS * 20);
+                backward_n4m1_lanes_kernel<T, DEPTH><<<grid_for(h->p.B, SLOTS), 32, smem, st>>>(
+                    qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active,
+                    gate);
+                ILQR_CHECK_LAUNCH(h);
+                return ILQR_OK;
+            }
+        }
         if constexpr (Sys::N > 4) {
             // n = 12, m = 4: a ring stage is 208 rows; two stages of one warp fit the 227 KB limit
             return launch_backward_depth<T, Sys::N, Sys::M, 2>(h, 32, qc, X, U, A, Bd, K, k, active, gate, st);
@@ -807,6 +983,44 @@ static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const voi
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });
+}
+
+static int launch_select(Handle *h, int a_lo, int a_hi, int wave, const void *ca, void *cost, int *winner, int *active,
+                         int *defer, int *iters, int *status, int it, Control *ctl, unsigned int *n2c, cudaStream_t st)
+{
+    const int B = h->p.B, bs = 128;
+    if (h->p.dtype == ILQR_F64)
+        select_kernel<double><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, (const double *)ca, (double *)cost, winner,
+                                                              active, defer, iters, status, h->p.tol, it, h->p.maxiter, ctl,
+                                                              n2c, h->tr_alpha, (double *)h->tr_cost);
+    else
+        select_kernel<float><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, (const float *)ca, (float *)cost, winner,
+                                                             active, defer, iters, status, (float)h->p.tol, it, h->p.maxiter,
+                                                             ctl, n2c, h->tr_alpha, (float *)h->tr_cost);
+    ILQR_CHECK_LAUNCH(h);
+    return ILQR_OK;
+}
+
+// How many of the n_alpha step sizes to roll out eagerly.  The rollout kernel is FP64-pipe bound and
+// its time is set by the busiest SM sub-partition: warps = ceil(B/32) * n_alpha spread over 148 * 4
+// sub-partitions.  When dropping the last (smallest, rarely needed) step sizes from the eager wave
+// lowers the warps-per-sub-partition ceiling, they are deferred to a second wave that only runs for
+// trajectories that accepted none of the first.  ILQR_FIRST_WAVE overrides.
+static int first_wave_size(int B, int n_alpha)
+{
+    if (const char *e = getenv("ILQR_FIRST_WAVE")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= n_alpha) return v;
+    }
+    const long slots = 148L * 4L;
+    const long wb = (B + 31) / 32;
+    auto ceil_div = [](long a, long b) { return (a + b - 1) / b; };
+    const long full = ceil_div(wb * n_alpha, slots);
+    int best = n_alpha;
+    // defer at most a third of the step sizes, and only if that removes a whole warp per sub-partition
+    for (int n1 = n_alpha - 1; n1 >= 1 && n1 >= n_alpha - n_alpha / 3; --n1)
+        if (ceil_div(wb * n1, slots) < full) { best = n1; break; }
+    return best;
 }
 
 // record a chained event after a launch of kernel class `kind` (no-op unless profiling)
@@ -892,6 +1106,7 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
         if (a < p->min_alpha) break;
     }
     h->n_alpha_eff = cnt;
+    h->n_first = first_wave_size(p->B, cnt);
     if (cudaMallocHost((void **)&h->h_flag, 2 * sizeof(unsigned int)) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming) != cudaSuccess) {
@@ -1043,11 +1258,19 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     char *w = (char *)ws;
     Control *ctl = (Control *)(w + L.ctl);
     void *A = w + L.A, *Bd = w + L.Bd, *Xc = w + L.Xc, *Uc = w + L.Uc, *ca = w + L.cost_alpha;
-    int *winner = (int *)(w + L.winner), *active = (int *)(w + L.active);
+    int *winner = (int *)(w + L.winner), *active = (int *)(w + L.active), *defer = (int *)(w + L.defer);
     const int B = p.B, bsB = 128;
     int rc;
+    // two-wave line search (see select_kernel): n1 eager step sizes, n2 deferred ones
+    const int n1 = h->n_first, n2 = h->n_alpha_eff - h->n_first;
+    const size_t wbytes = p.dtype == ILQR_F64 ? 8 : 4;
+    const size_t xc_slab = wbytes * (size_t)(p.N + 1) * p.n * B, uc_slab = wbytes * (size_t)p.N * p.m * B;
+    AlphaList al2;
+    std::memset(&al2, 0, sizeof al2);
+    for (int i = 0; i < n2; ++i) al2.a[i] = h->alphas.a[n1 + i];
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { h->last_cuda = (int)e_; return ILQR_E_CUDA; } } while (0)
-    CU(cudaMemsetAsync(ctl, 0, sizeof(Control) + sizeof(unsigned int) * (size_t)(p.maxiter + 2), st));
+    CU(cudaMemsetAsync(ctl, 0, sizeof(Control) + sizeof(unsigned int) * 2 * (size_t)(p.maxiter + 2), st));
+    CU(cudaMemsetAsync(defer, 0, sizeof(int) * (size_t)B, st));
     // initial rollout, alpha = 0, with the incoming X,K,k (iLQR_class.py:257-259) into candidate slab 0
     AlphaList a0;
     std::memset(&a0, 0, sizeof a0);
@@ -1079,19 +1302,18 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
             prof_mark(h, ILQR_KC_LINEARIZE, st);
             if ((rc = launch_backward(h, X, U, A, Bd, K, k, active, g, st))) return rc;
             prof_mark(h, ILQR_KC_BACKWARD, st);
-            if ((rc = launch_rollout(h, h->n_alpha_eff, h->alphas, phi, x0, X, U, k, K, Xc, Uc, ca, active, g, cost, st))) return rc;
+            // line search, wave 1: the first n1 step sizes for every active trajectory
+            if ((rc = launch_rollout(h, n1, h->alphas, phi, x0, X, U, k, K, Xc, Uc, ca, active, g, nullptr, st))) return rc;
             prof_mark(h, ILQR_KC_ROLLOUT, st);
-            if (p.dtype == ILQR_F64)
-                select_kernel<double><<<grid_for(B, bsB), bsB, 0, st>>>(B, h->n_alpha_eff, (const double *)ca,
-                                                                          (double *)cost, winner, active, iters, status,
-                                                                          p.tol, it, p.maxiter, ctl, h->tr_alpha,
-                                                                          (double *)h->tr_cost);
-            else
-                select_kernel<float><<<grid_for(B, bsB), bsB, 0, st>>>(B, h->n_alpha_eff, (const float *)ca,
-                                                                         (float *)cost, winner, active, iters, status,
-                                                                         (float)p.tol, it, p.maxiter, ctl, h->tr_alpha,
-                                                                         (float *)h->tr_cost);
-            ILQR_CHECK_LAUNCH(h);
+            unsigned int *n2c = &ctl->n_active[p.maxiter + 2 + it];
+            if ((rc = launch_select(h, 0, n1, 0, ca, cost, winner, active, n2 > 0 ? defer : nullptr, iters, status, it, ctl, n2c, st))) return rc;
+            if (n2 > 0) {
+                // wave 2: the remaining step sizes, only for trajectories that accepted none so far; both
+                // launches return at once while the deferred counter of this iteration is zero
+                if ((rc = launch_rollout(h, n2, al2, phi, x0, X, U, k, K, (char *)Xc + xc_slab * n1, (char *)Uc + uc_slab * n1,
+                                         (char *)ca + wbytes * (size_t)n1 * B, defer, n2c, nullptr, st))) return rc;
+                if ((rc = launch_select(h, n1, n1 + n2, 1, ca, cost, winner, active, defer, iters, status, it, ctl, n2c, st))) return rc;
+            }
         }
         if (pending >= 0) {
             CU(cudaEventSynchronize(h->ev[pending]));

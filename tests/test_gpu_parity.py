@@ -193,3 +193,34 @@ def test_errors():
         iLQR(s, 1.0, np.zeros(4), np.zeros((1, 99)))
     with pytest.raises(ValueError, match="Unknown integrator"):
         ua_system(integrator="rk5")
+
+
+def test_two_wave_line_search_is_exact(monkeypatch):
+    """Deferring the small step sizes to a second wave (ilqr_solve) must not change a single bit: the
+    same rollouts are evaluated, only later and only where needed."""
+    from class_files.iLQR_class import iLQR
+    B, N = 256, 100
+    x0 = cfg2_x0(B, seed=3)
+    out = {}
+    for fw in ("10", "3", "1"):
+        monkeypatch.setenv("ILQR_FIRST_WAVE", fw)
+        sol = iLQR(ua_system(), 1.0, x0, np.zeros((1, N)), maxiter=12, verbose=False)
+        X, U, cost = sol.optimize_trajectory()
+        out[fw] = (X.copy(), U.copy(), cost.copy(), sol.K.copy(), sol.iterations.copy(), sol.status.copy())
+    for fw in ("3", "1"):
+        for a, b in zip(out["10"], out[fw]):
+            assert np.array_equal(a, b)
+
+
+def test_backward_variants_agree(monkeypatch):
+    """four-lanes-per-trajectory and one-thread-per-trajectory Riccati kernels on the same inputs"""
+    from class_files.iLQR_class import iLQR
+    g = load_golden("solve_cfg2_ua_rk4_b0")
+    s = system_from_golden(g)
+    res = {}
+    for lanes in ("1", "0"):
+        monkeypatch.setenv("ILQR_BACKWARD_LANES", lanes)
+        sol = iLQR(s, float(g["T"]), g["x0"], np.zeros((1, int(g["N"]))), verbose=False)
+        res[lanes] = sol.backward_pass(g["it_X"][3], g["it_U"][3])
+    assert rel_err(res["1"][1], res["0"][1]) < 1e-11 and rel_err(res["1"][0], res["0"][0], floor=1e-6) < 1e-10
+    assert rel_err(res["1"][1], g["it_K"][3]) < TOL
