@@ -36,6 +36,21 @@ struct Control {
     unsigned int n_active[1];                 // [maxiter + 2], n_active[it] = trajectories entering iteration it
 };
 
+// Speculative evaluation of the deferred (second-wave) step sizes.  Trajectories that needed a small
+// step in the previous iteration are put on a list by select_kernel; the first-wave rollout launch
+// carries `cap * n2` extra threads (the warp slots left over when the wave is sized to the SM
+// sub-partitions) that roll out the deferred step sizes for the listed trajectories, so that the
+// separate, latency-bound second wave is almost never needed.  Which rollouts are evaluated never
+// changes which one is accepted.
+struct SpecArgs {
+    int cap;                              // list capacity; 0 switches speculation off
+    int n2;                               // deferred step sizes per trajectory
+    int threshold;                        // accepted try index from which a trajectory is listed
+    int *list_cur, *list_next;            // [cap]
+    unsigned int *count_cur, *count_next; // entries appended this / next iteration (may exceed cap)
+    int *mark;                            // [B]: mark[b] == it + 1 <=> b is on the list of iteration it
+};
+
 template <class Sys, int INTEG, typename T>
 __global__ void step_kernel(const __grid_constant__ Sys sys, T dt, int B, int t, const T *__restrict__ phi,
                             const T *__restrict__ x, const T *__restrict__ u, T *__restrict__ xn)
@@ -506,13 +521,25 @@ __global__ void rollout_kernel(const __grid_constant__ Sys sys, const __grid_con
                                const T *__restrict__ x0, const T *__restrict__ X_old, const T *__restrict__ U_old,
                                const T *__restrict__ k, const T *__restrict__ K, T *__restrict__ Xc,
                                T *__restrict__ Uc, T *__restrict__ cost_alpha, const int *__restrict__ active,
-                               const unsigned int *__restrict__ gate, const T *__restrict__ cost_ref)
+                               const unsigned int *__restrict__ gate, const T *__restrict__ cost_ref,
+                               const __grid_constant__ SpecArgs sp)
 {
     constexpr int n = Sys::N, m = Sys::M;
     if (gate && *gate == 0u) return;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)n_alpha * B) return;
-    const int ai = (int)(gid / B), b = (int)(gid % B);
+    int ai, b;
+    if (gid < (size_t)n_alpha * B) {
+        ai = (int)(gid / B);
+        b = (int)(gid % B);
+    } else {                                                             // speculative extra threads
+        const size_t e = gid - (size_t)n_alpha * B;
+        if (sp.cap == 0 || e >= (size_t)sp.cap * sp.n2) return;
+        const int q = (int)(e % sp.cap);
+        const unsigned int cnt = min(*sp.count_cur, (unsigned int)sp.cap);
+        if ((unsigned int)q >= cnt) return;
+        b = sp.list_cur[q];
+        ai = n_alpha + (int)(e / sp.cap);
+    }
     if (active && !active[b]) return;
     const T alpha = (T)alphas.a[ai];
     T *Xw = Xc + (size_t)ai * (N + 1) * n * B, *Uw = Uc + (size_t)ai * N * m * B;
@@ -599,7 +626,7 @@ __global__ void select_kernel(int B, int a_lo, int a_hi, int wave, const T *__re
                               T *__restrict__ cost, int *__restrict__ winner, int *__restrict__ active,
                               int *__restrict__ defer, int *__restrict__ iters, int *__restrict__ status, T tol,
                               int it, int maxiter, Control *ctl, unsigned int *n2_count,
-                              int *__restrict__ tr_alpha, T *__restrict__ tr_cost)
+                              int *__restrict__ tr_alpha, T *__restrict__ tr_cost, const __grid_constant__ SpecArgs sp)
 {
     if (ctl->n_active[it] == 0u) return;
     if (wave == 1 && *n2_count == 0u) return;
@@ -615,13 +642,16 @@ __global__ void select_kernel(int B, int a_lo, int a_hi, int wave, const T *__re
             const T c0 = cost[b];
             int w = -1;
             T cw = c0;
-            for (int a = a_lo; a < a_hi; ++a) {
+            // a listed trajectory had its deferred step sizes rolled out speculatively in the first wave
+            const bool listed = wave == 0 && sp.cap > 0 && sp.mark[b] == it + 1;
+            const int hi = listed ? a_hi + sp.n2 : a_hi;
+            for (int a = a_lo; a < hi; ++a) {
                 const T c = cost_alpha[(size_t)a * B + b];
                 if (c <= c0) { w = a; cw = c; break; }                   // NaN compares false, as in Python
             }
             winner[b] = w;
             iters[b] = it + 1;
-            if (w < 0 && wave == 0 && defer != nullptr) {
+            if (w < 0 && wave == 0 && defer != nullptr && !listed) {
                 defer[b] = 1;                                            // decided by the second wave
                 deferred = true;
             } else {
@@ -635,6 +665,10 @@ __global__ void select_kernel(int B, int a_lo, int a_hi, int wave, const T *__re
                     if (it + 1 >= maxiter) { status[b] = ILQR_ST_MAXITER; active[b] = 0; }
                     else if (abs_t(cw - c0) <= tol) { status[b] = ILQR_ST_CONVERGED; active[b] = 0; }
                     else still = true;
+                    if (still && sp.cap > 0 && w >= sp.threshold) {      // small step needed: list it for next time
+                        const unsigned int pos = atomicAdd(sp.count_next, 1u);
+                        if (pos < (unsigned int)sp.cap) { sp.list_next[pos] = b; sp.mark[b] = it + 2; }
+                    }
                 }
             }
         }
@@ -802,6 +836,7 @@ struct Handle {
     ilqr_problem_t p;
     int n_alpha_eff;          // tries actually made: stops once alpha < min_alpha (iLQR_class.py:300-302)
     int n_first;              // step sizes rolled out eagerly (first wave); the rest only where needed
+    int spec_cap;             // trajectories whose deferred step sizes ride along speculatively (SpecArgs)
     AlphaList alphas;
     long long launches;
     int last_cuda;
@@ -828,7 +863,7 @@ static inline int block_for(size_t threads)
 }
 
 struct WsLayout {
-    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, active, defer, total;
+    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, active, defer, mark, lists, total;
 };
 
 static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
@@ -838,8 +873,9 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     WsLayout L;
     size_t off = 0;
-    // n_active[maxiter + 2] followed by the per-iteration deferred (second-wave) counters [maxiter + 2]
-    L.ctl = off; off = al(off + sizeof(Control) + sizeof(unsigned int) * 2 * (size_t)(p.maxiter + 2));
+    // n_active[maxiter + 2], then the per-iteration deferred (second-wave) counters [maxiter + 2], then the
+    // per-iteration speculation-list counters [maxiter + 2]
+    L.ctl = off; off = al(off + sizeof(Control) + sizeof(unsigned int) * 3 * (size_t)(p.maxiter + 2));
     L.A = off; off = al(off + w * N * n * n * B);
     L.Bd = off; off = al(off + w * N * n * m * B);
     L.Xc = off; off = al(off + w * (size_t)n_alpha * (N + 1) * n * B);
@@ -848,6 +884,8 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
     L.winner = off; off = al(off + 4 * B);
     L.active = off; off = al(off + 4 * B);
     L.defer = off; off = al(off + 4 * B);
+    L.mark = off; off = al(off + 4 * B);
+    L.lists = off; off = al(off + 4 * 2 * B);     // two speculation lists (capacity <= B each)
     L.total = off;
     return L;
 }
@@ -968,35 +1006,39 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
 
 static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const void *phi, const void *x0, const void *X, const void *U,
                           const void *k, const void *K, void *Xc, void *Uc, void *cost_alpha, const int *active,
-                          const unsigned int *gate, const void *cost_ref, cudaStream_t st)
+                          const unsigned int *gate, const void *cost_ref, cudaStream_t st, const SpecArgs *spec = nullptr)
 {
+    SpecArgs sp;
+    std::memset(&sp, 0, sizeof sp);
+    if (spec) sp = *spec;
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
         using T = decltype(tz);
         using Sys = decltype(sys);
         constexpr int I = decltype(integ)::value;
-        const size_t threads = (size_t)n_alpha * h->p.B;
+        const size_t threads = (size_t)n_alpha * h->p.B + (size_t)sp.cap * sp.n2;
         const char *bs_env = getenv("ILQR_ROLLOUT_BS");
         const int bs = bs_env ? atoi(bs_env) : block_for(threads);
         rollout_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
             sys, qc, h->p.N, h->p.B, n_alpha, al, (const T *)phi, (const T *)x0, (const T *)X, (const T *)U, (const T *)k,
-            (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref);
+            (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref, sp);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });
 }
 
 static int launch_select(Handle *h, int a_lo, int a_hi, int wave, const void *ca, void *cost, int *winner, int *active,
-                         int *defer, int *iters, int *status, int it, Control *ctl, unsigned int *n2c, cudaStream_t st)
+                         int *defer, int *iters, int *status, int it, Control *ctl, unsigned int *n2c, const SpecArgs &sp,
+                         cudaStream_t st)
 {
     const int B = h->p.B, bs = 128;
     if (h->p.dtype == ILQR_F64)
         select_kernel<double><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, (const double *)ca, (double *)cost, winner,
                                                               active, defer, iters, status, h->p.tol, it, h->p.maxiter, ctl,
-                                                              n2c, h->tr_alpha, (double *)h->tr_cost);
+                                                              n2c, h->tr_alpha, (double *)h->tr_cost, sp);
     else
         select_kernel<float><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, (const float *)ca, (float *)cost, winner,
                                                              active, defer, iters, status, (float)h->p.tol, it, h->p.maxiter,
-                                                             ctl, n2c, h->tr_alpha, (float *)h->tr_cost);
+                                                             ctl, n2c, h->tr_alpha, (float *)h->tr_cost, sp);
     ILQR_CHECK_LAUNCH(h);
     return ILQR_OK;
 }
@@ -1021,6 +1063,23 @@ static int first_wave_size(int B, int n_alpha)
     for (int n1 = n_alpha - 1; n1 >= 1 && n1 >= n_alpha - n_alpha / 3; --n1)
         if (ceil_div(wb * n1, slots) < full) { best = n1; break; }
     return best;
+}
+
+// Speculation capacity: the warp slots left over in the first wave once it is rounded up to whole
+// warps per SM sub-partition, shared by the n2 deferred step sizes.  ILQR_SPEC_CAP overrides.
+static int spec_capacity(int B, int n1, int n_alpha)
+{
+    const int n2 = n_alpha - n1;
+    if (n2 <= 0) return 0;
+    if (const char *e = getenv("ILQR_SPEC_CAP")) {
+        const int v = atoi(e);
+        return v < 0 ? 0 : (v > B ? B : v);
+    }
+    const long slots = 148L * 4L, wb = (B + 31) / 32;
+    const long warps1 = wb * n1, per = (warps1 + slots - 1) / slots;
+    long cap = (per * slots - warps1) * 32 / n2;
+    if (cap > B) cap = B;
+    return (int)cap;
 }
 
 // record a chained event after a launch of kernel class `kind` (no-op unless profiling)
@@ -1107,6 +1166,7 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
     }
     h->n_alpha_eff = cnt;
     h->n_first = first_wave_size(p->B, cnt);
+    h->spec_cap = spec_capacity(p->B, h->n_first, cnt);
     if (cudaMallocHost((void **)&h->h_flag, 2 * sizeof(unsigned int)) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming) != cudaSuccess) {
@@ -1259,6 +1319,7 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     Control *ctl = (Control *)(w + L.ctl);
     void *A = w + L.A, *Bd = w + L.Bd, *Xc = w + L.Xc, *Uc = w + L.Uc, *ca = w + L.cost_alpha;
     int *winner = (int *)(w + L.winner), *active = (int *)(w + L.active), *defer = (int *)(w + L.defer);
+    int *mark = (int *)(w + L.mark), *lists = (int *)(w + L.lists);
     const int B = p.B, bsB = 128;
     int rc;
     // two-wave line search (see select_kernel): n1 eager step sizes, n2 deferred ones
@@ -1269,8 +1330,9 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     std::memset(&al2, 0, sizeof al2);
     for (int i = 0; i < n2; ++i) al2.a[i] = h->alphas.a[n1 + i];
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { h->last_cuda = (int)e_; return ILQR_E_CUDA; } } while (0)
-    CU(cudaMemsetAsync(ctl, 0, sizeof(Control) + sizeof(unsigned int) * 2 * (size_t)(p.maxiter + 2), st));
+    CU(cudaMemsetAsync(ctl, 0, sizeof(Control) + sizeof(unsigned int) * 3 * (size_t)(p.maxiter + 2), st));
     CU(cudaMemsetAsync(defer, 0, sizeof(int) * (size_t)B, st));
+    CU(cudaMemsetAsync(mark, 0, sizeof(int) * (size_t)B, st));
     // initial rollout, alpha = 0, with the incoming X,K,k (iLQR_class.py:257-259) into candidate slab 0
     AlphaList a0;
     std::memset(&a0, 0, sizeof a0);
@@ -1302,17 +1364,31 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
             prof_mark(h, ILQR_KC_LINEARIZE, st);
             if ((rc = launch_backward(h, X, U, A, Bd, K, k, active, g, st))) return rc;
             prof_mark(h, ILQR_KC_BACKWARD, st);
-            // line search, wave 1: the first n1 step sizes for every active trajectory
-            if ((rc = launch_rollout(h, n1, h->alphas, phi, x0, X, U, k, K, Xc, Uc, ca, active, g, nullptr, st))) return rc;
+            // line search, wave 1: the first n1 step sizes for every active trajectory (+ the deferred ones of
+            // the trajectories on this iteration's speculation list)
+            SpecArgs sp;
+            std::memset(&sp, 0, sizeof sp);
+            if (n2 > 0 && h->spec_cap > 0) {
+                unsigned int *n_spec = &ctl->n_active[2 * (p.maxiter + 2)];
+                sp.cap = h->spec_cap;
+                sp.n2 = n2;
+                sp.threshold = n1 - 4 > 1 ? n1 - 4 : 1;
+                sp.list_cur = lists + (size_t)(it & 1) * B;
+                sp.list_next = lists + (size_t)((it + 1) & 1) * B;
+                sp.count_cur = n_spec + it;
+                sp.count_next = n_spec + it + 1;
+                sp.mark = mark;
+            }
+            if ((rc = launch_rollout(h, n1, h->alphas, phi, x0, X, U, k, K, Xc, Uc, ca, active, g, nullptr, st, &sp))) return rc;
             prof_mark(h, ILQR_KC_ROLLOUT, st);
             unsigned int *n2c = &ctl->n_active[p.maxiter + 2 + it];
-            if ((rc = launch_select(h, 0, n1, 0, ca, cost, winner, active, n2 > 0 ? defer : nullptr, iters, status, it, ctl, n2c, st))) return rc;
+            if ((rc = launch_select(h, 0, n1, 0, ca, cost, winner, active, n2 > 0 ? defer : nullptr, iters, status, it, ctl, n2c, sp, st))) return rc;
             if (n2 > 0) {
                 // wave 2: the remaining step sizes, only for trajectories that accepted none so far; both
                 // launches return at once while the deferred counter of this iteration is zero
                 if ((rc = launch_rollout(h, n2, al2, phi, x0, X, U, k, K, (char *)Xc + xc_slab * n1, (char *)Uc + uc_slab * n1,
                                          (char *)ca + wbytes * (size_t)n1 * B, defer, n2c, nullptr, st))) return rc;
-                if ((rc = launch_select(h, n1, n1 + n2, 1, ca, cost, winner, active, defer, iters, status, it, ctl, n2c, st))) return rc;
+                if ((rc = launch_select(h, n1, n1 + n2, 1, ca, cost, winner, active, defer, iters, status, it, ctl, n2c, sp, st))) return rc;
             }
         }
         if (pending >= 0) {
