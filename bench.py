@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="trajectories per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=512, help="trajectories per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="trajectories per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
