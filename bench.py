@@ -256,7 +256,8 @@ def main():
         tot, cnt = ktimes[name]
         if cnt == 0:
             return None
-        avg = tot / cnt
+        # per iLQR iteration (the lazy line-search schedule launches the rollout kernel once per wave)
+        avg = tot / max(1, ktimes["linearize"][1])
         alg = BYTES[name] * N_H * B + (8 * N_ALPHA * B if name == "rollout" else 0)
         return {"avg_ms": avg, "launches": cnt, "share_of_step": tot / ms, "algorithmic_bytes": alg,
                 "achieved_GBps": alg / avg / 1e6}

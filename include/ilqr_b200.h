@@ -33,6 +33,7 @@ extern "C" {
 #define ILQR_NMAX 12
 #define ILQR_MMAX 4
 #define ILQR_MAX_ALPHAS 16
+#define ILQR_MAX_WAVES 8
 
 enum { ILQR_PENDULUM = 0, ILQR_DOUBLE_PENDULUM = 1, ILQR_UA_DOUBLE_PENDULUM = 2, ILQR_LTV = 3 };
 enum { ILQR_EULER = 0, ILQR_MIDPOINT = 1, ILQR_RK4 = 2, ILQR_BACKWARD_EULER = 3 };
@@ -128,6 +129,15 @@ int ilqr_forward_linesearch(ilqr_handle_t h, const void *phi, const void *x0, co
 int ilqr_solve(ilqr_handle_t h, const void *phi, const void *x0, void *X, void *U, void *K, void *k,
                void *cost, int32_t *iters, int32_t *status, void *workspace, size_t workspace_bytes,
                void *stream, int64_t *total_iters);
+
+/* Schedule of the line search inside ilqr_solve.  The reference tries its step sizes one after the other
+ * and stops at the first acceptable one (iLQR_class.py:279-302).  On the GPU the tries of a WAVE are rolled
+ * out concurrently; trajectories that accepted none of them go on a compacted list and only those are
+ * rolled out in the next wave.  sizes[n_waves] are the tries per wave (their sum is clamped to the number of
+ * tries actually made).  n_waves = 0 selects the eager schedule (all tries in one or two dense waves), which
+ * is the default for small batches where the rollout is latency bound; large batches default to waves of
+ * 2,2,2,rest.  The accepted step size of every trajectory is the same under every schedule. */
+int ilqr_set_linesearch_waves(ilqr_handle_t h, int n_waves, const int32_t *sizes);
 
 /* Optional per-iteration trace written by ilqr_solve (the information the reference prints when
  * verbose=True, iLQR_class.py:262,296,306): alpha_idx[maxiter][B] (int32: accepted try index, -1 = line

@@ -294,6 +294,15 @@ class iLQR:
     def launches(self):
         return self._handle.launches()
 
+    def set_linesearch_waves(self, sizes):
+        """Line-search schedule of optimize_trajectory (see ilqr_set_linesearch_waves): `sizes` = tries per
+        lazily evaluated wave, e.g. (2, 2, 2, 4); () or None = all tries eagerly.  The accepted step size of
+        every trajectory is the same under every schedule; only the amount of speculative work changes."""
+        h = self._handle
+        sizes = [int(v) for v in (sizes or ())]
+        arr = (C.c_int32 * max(len(sizes), 1))(*sizes)
+        h.check(h.lib.ilqr_set_linesearch_waves(h.h, len(sizes), arr))
+
     def set_profiling(self, enable=True):
         """chain CUDA events between the solve's kernels (see ilqr_set_profiling)"""
         h = self._handle

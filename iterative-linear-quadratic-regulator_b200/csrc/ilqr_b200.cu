@@ -76,7 +76,7 @@ __global__ void commit_linearize_kernel(const __grid_constant__ Sys sys, T dt, i
                                         const T *__restrict__ phi, T *__restrict__ X, T *__restrict__ U,
                                         T *__restrict__ A, T *__restrict__ Bd, const T *__restrict__ Xc,
                                         const T *__restrict__ Uc, const int *__restrict__ winner,
-                                        const int *__restrict__ active, int do_linearize,
+                                        const int *__restrict__ wslot, const int *__restrict__ active, int do_linearize,
                                         const unsigned int *__restrict__ gate0, const unsigned int *__restrict__ gate1)
 {
     constexpr int n = Sys::N, m = Sys::M;
@@ -89,16 +89,18 @@ __global__ void commit_linearize_kernel(const __grid_constant__ Sys sys, T dt, i
     if (w < 0 && !act) return;
     T x[n], u[m];
     if (w >= 0) {
+        // lazy line search: candidates of the later waves are stored at the trajectory's list position
+        const int col = wslot ? wslot[b] : b;
         const T *xs = Xc + (size_t)w * (N + 1) * n * B, *us = Uc + (size_t)w * N * m * B;
 #pragma unroll
         for (int i = 0; i < n; ++i) {
-            x[i] = xs[((size_t)t * n + i) * B + b];
+            x[i] = xs[((size_t)t * n + i) * B + col];
             X[((size_t)t * n + i) * B + b] = x[i];
         }
         if (t < N) {
 #pragma unroll
             for (int j = 0; j < m; ++j) {
-                u[j] = us[((size_t)t * m + j) * B + b];
+                u[j] = us[((size_t)t * m + j) * B + col];
                 U[((size_t)t * m + j) * B + b] = u[j];
             }
         }
@@ -469,6 +471,217 @@ backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, 
     }
 }
 
+// K2 for the synthetic LTV system (n = 12, m = 4; BASELINE.json config 4).  One thread per trajectory
+// would need V_xx alone in 288 registers, so SIXTEEN lanes share a trajectory: lane c owns column c of
+// [A_t | B_t] (12 + 4 columns).  A_t = I + dt (Ac + w_t E) is generated in the kernel from the constants and
+// the trajectory's phase -- it is never read from (or written to) HBM -- and B_t = dt Bc is constant.
+// Per step lane c computes
+//     W[:,c]  = V_xx [A|B][:,c]                    (V_xx read from shared memory, 16-byte broadcasts)
+//     G[:,c]  = [A|B]' W[:,c]                       (A' from shared memory, B' constant)
+//               -> c < 12: Q_xx[:,c], Q_ux[:,c]      c >= 12: Q_uu[:,c-12]          (iLQR_class.py:102-104)
+//     Q_x[c] / Q_u[c-12]                                                             (:100-101)
+// then every lane factors the 4x4 Q_uu (LU, partial pivoting, as the reference's solve) and solves for its
+// own right-hand side: K[:,c] (c < 12) or k (:109-110), and writes its column of the new V_xx and V_x[c]
+// (:113-114).  TPB trajectories per block; the 52 gain values of a step go through a shared-memory stage so
+// that every global store is a row of TPB consecutive trajectories (full 128-byte lines for TPB = 16); x_t,
+// u_t arrive the same way, prefetched one step ahead.  One block barrier per step.
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+#ifndef ILQR_LTV_MINBLOCKS
+#define ILQR_LTV_MINBLOCKS 2
+#endif
+template <typename T, int TPB>
+__global__ void __launch_bounds__(TPB * 16, ILQR_LTV_MINBLOCKS)
+backward_ltv_kernel(const __grid_constant__ LtvSys<T> sys, const __grid_constant__ QuadCost<T, 12, 4> qc, int N, int B,
+                    const T *__restrict__ phi, const T *__restrict__ X, const T *__restrict__ U, T *__restrict__ K,
+                    T *__restrict__ k, const int *__restrict__ active, const unsigned int *__restrict__ gate)
+{
+    constexpr int n = 12, m = 4, NT = TPB * 16, ROWS = n * m + m;   // 52 gain rows per step
+    using V2 = typename Vec2<T>::type;
+    extern __shared__ __align__(16) unsigned char ltv_raw[];
+    T *sm = reinterpret_cast<T *>(ltv_raw);
+    T *VxxS = sm;                       // [TPB][12][12]  row-major V_xx
+    T *ATS = VxxS + TPB * 144;          // [TPB][12][12]  ATS[i][l] = A[l][i]
+    T *VxS = ATS + TPB * 144;           // [TPB][12]
+    T *QuxS = VxS + TPB * 12;           // [TPB][4][12]
+    T *QuuS = QuxS + TPB * 48;          // [TPB][4][4]
+    T *QuS = QuuS + TPB * 16;           // [TPB][4]
+    T *xsS = QuS + TPB * 4;             // [2][TPB][16]   x_t (12), u_t (4), double buffered
+    T *KS = xsS + 2 * TPB * 16;         // [2][52][TPB]   gain stage, double buffered
+    T *BdT = KS + 2 * ROWS * TPB;       // [4][12]        BdT[j][l] = dt Bc[l][j]
+    T *QsS = BdT + 48;                  // [12][12]       symmetrised Q
+    T *RsS = QsS + 144;                 // [4][4]
+    T *AcT = RsS + 16;                  // [12][12]       AcT[c][l] = Ac[l][c]
+    T *ET = AcT + 144;                  // [12][12]       ET[c][l]  = E[l][c]
+    __shared__ int vflag[TPB];
+    if (gate && *gate == 0u) return;
+    const int tid = threadIdx.x, s = tid >> 4, c = tid & 15;
+    const int b0 = blockIdx.x * TPB;
+    const int b_raw = b0 + s;
+    const bool valid = b_raw < B && (!active || active[b_raw] != 0);
+    if (__syncthreads_or(valid) == 0) return;
+    const int b = b_raw < B ? b_raw : B - 1;        // out-of-range / inactive slots compute on a copy, never store
+    if (c == 0) vflag[s] = valid;
+    for (int e = tid; e < 48; e += NT) BdT[e] = qc.dt * sys.Bc[e % 12][e / 12];
+    for (int e = tid; e < 144; e += NT) {
+        QsS[e] = qc.Qs[e / 12][e % 12];
+        AcT[e] = sys.Ac[e % 12][e / 12];
+        ET[e] = sys.E[e % 12][e / 12];
+    }
+    if (tid < 16) RsS[tid] = qc.Rs[tid >> 2][tid & 3];
+    // staged loads: thread (r, bb) fetches row r (x_0..x_11, u_0..u_3) of trajectory b0 + bb
+    const int ld_r = tid / TPB, ld_bb = tid % TPB;
+    const int ld_b = min(b0 + ld_bb, B - 1);
+    auto fetch = [&](int t) -> T {
+        if (ld_r < n) return X[((size_t)t * n + ld_r) * B + ld_b];
+        return t < N ? U[((size_t)t * m + (ld_r - n)) * B + ld_b] : T(0);
+    };
+    // column c of [A_t | B_t]: rebuilt every step from AcT/ET (c < 12), constant dt Bc[:,c-12] otherwise
+    T M[n];
+#pragma unroll
+    for (int l = 0; l < n; ++l) M[l] = c < n ? T(0) : qc.dt * sys.Bc[l][c - n];
+    const T ph = phi ? phi[b] : T(0);
+    T w = sys.time_scalar(N - 1, ph);
+    T *Vxx = VxxS + s * 144, *AT = ATS + s * 144, *Vx = VxS + s * 12, *Qux = QuxS + s * 48, *Quu = QuuS + s * 16,
+      *Qu = QuS + s * 4;
+    // terminal condition (iLQR_class.py:136-138): V_x = Q_f (x_N - x_target), V_xx = Q_f
+    xsS[ld_bb * 16 + ld_r] = fetch(N);
+    __syncthreads();
+    if (c < n) {
+        T g = T(0);
+#pragma unroll
+        for (int j = 0; j < n; ++j) g += qc.Qfs[c][j] * (xsS[s * 16 + j] - qc.xt[j]);
+        Vx[c] = g;
+#pragma unroll
+        for (int i = 0; i < n; ++i) Vxx[i * 12 + c] = qc.Qfs[i][c];
+    }
+    T pre = fetch(N - 1);
+    __syncthreads();
+    xsS[TPB * 16 + ld_bb * 16 + ld_r] = pre;        // buffer 1 holds step N-1 (buffer index = (N - t) & 1)
+    __syncthreads();
+    for (int t = N - 1; t >= 0; --t) {
+        const int buf = (N - t) & 1;
+        const T *xs = xsS + buf * TPB * 16 + s * 16;
+        if (t > 0) pre = fetch(t - 1);
+        if (c < n) {
+#pragma unroll
+            for (int l = 0; l < n; l += 2) {
+                const V2 a = *reinterpret_cast<const V2 *>(AcT + c * 12 + l), e = *reinterpret_cast<const V2 *>(ET + c * 12 + l);
+                M[l] = ((l == c) ? T(1) : T(0)) + qc.dt * (a.x + w * e.x);
+                M[l + 1] = ((l + 1 == c) ? T(1) : T(0)) + qc.dt * (a.y + w * e.y);
+                *reinterpret_cast<V2 *>(AT + c * 12 + l) = V2{M[l], M[l + 1]};
+            }
+        }
+        __syncwarp();
+        if (t > 0) w = sys.time_scalar(t - 1, ph);      // next step's scalar: independent work for the solve's latency
+        // W[:,c] = V_xx [A|B][:,c]
+        T W[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T acc = T(0);
+#pragma unroll
+            for (int l = 0; l < n; l += 2) {
+                const V2 v = *reinterpret_cast<const V2 *>(Vxx + i * 12 + l);
+                acc += v.x * M[l];
+                acc += v.y * M[l + 1];
+            }
+            W[i] = acc;
+        }
+        // G = [A|B]' W[:,c]
+        T G[n + m];
+#pragma unroll
+        for (int r = 0; r < n + m; ++r) {
+            const T *row = r < n ? AT + r * 12 : BdT + (r - n) * 12;
+            T acc = T(0);
+#pragma unroll
+            for (int l = 0; l < n; l += 2) {
+                const V2 v = *reinterpret_cast<const V2 *>(row + l);
+                acc += v.x * W[l];
+                acc += v.y * W[l + 1];
+            }
+            G[r] = acc;
+        }
+        // q = [A|B][:,c]' V_x ; cost gradient entry of this lane
+        T q = T(0);
+#pragma unroll
+        for (int l = 0; l < n; ++l) q += M[l] * Vx[l];
+        T rhs[m][1], Qc;
+        if (c < n) {
+            T g = T(0);
+            if (qc.diag) g = QsS[c * 12 + c] * (xs[c] - qc.xt[c]);
+            else {
+#pragma unroll
+                for (int j = 0; j < n; ++j) g += QsS[c * 12 + j] * (xs[j] - qc.xt[j]);
+            }
+            Qc = g * qc.dt + q;                                          // Q_x[c]
+#pragma unroll
+            for (int i = 0; i < n; ++i) G[i] = QsS[i * 12 + c] * qc.dt + G[i];          // Q_xx[:,c]
+#pragma unroll
+            for (int j = 0; j < m; ++j) { Qux[j * 12 + c] = G[n + j]; rhs[j][0] = G[n + j]; }
+        } else {
+            const int jj = c - n;
+            T g = T(0);
+            if (qc.diag) g = RsS[jj * 4 + jj] * xs[n + jj];
+            else {
+#pragma unroll
+                for (int i = 0; i < m; ++i) g += RsS[jj * 4 + i] * xs[n + i];
+            }
+            Qc = g * qc.dt + q;                                          // Q_u[c-12]
+            Qu[jj] = Qc;
+#pragma unroll
+            for (int i = 0; i < m; ++i) Quu[i * 4 + jj] = RsS[i * 4 + jj] * qc.dt + G[n + i];    // Q_uu[:,c-12]
+        }
+        __syncwarp();
+        // K[:,c] = -Q_uu^-1 Q_ux[:,c] (c < 12) ; k = -Q_uu^-1 Q_u (lanes 12..15, lane 12+j keeps k[j])
+        T Lm[m][m], Quv[m];
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+#pragma unroll
+            for (int j = 0; j < m; ++j) Lm[i][j] = Quu[i * 4 + j];
+            Quv[i] = Qu[i];
+            if (c >= n) rhs[i][0] = Quv[i];
+        }
+        lu_solve_inplace<m, 1, T, true>(Lm, rhs);
+        T *ks = KS + ((N - t) & 1) * ROWS * TPB;
+        if (c < n) {
+            // V_xx[:,c] = Q_xx[:,c] + Q_ux' K[:,c] ; V_x[c] = Q_x[c] + K[:,c]' Q_u
+            T Kc[m];
+#pragma unroll
+            for (int j = 0; j < m; ++j) Kc[j] = -rhs[j][0];
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                T acc = T(0);
+#pragma unroll
+                for (int j = 0; j < m; ++j) acc += Qux[j * 12 + i] * Kc[j];
+                G[i] += acc;
+            }
+            T vx = T(0);
+#pragma unroll
+            for (int j = 0; j < m; ++j) vx += Kc[j] * Quv[j];
+            vx = Qc + vx;
+#pragma unroll
+            for (int i = 0; i < n; ++i) Vxx[i * 12 + c] = G[i];
+            Vx[c] = vx;
+#pragma unroll
+            for (int j = 0; j < m; ++j) ks[(j * n + c) * TPB + s] = Kc[j];
+        } else {
+            ks[(n * m + (c - n)) * TPB + s] = -rhs[c - n][0];
+        }
+        if (t > 0) xsS[(buf ^ 1) * TPB * 16 + ld_bb * 16 + ld_r] = pre;
+        __syncthreads();
+        // coalesced store of the step's gains: rows of TPB consecutive trajectories
+        for (int e = tid; e < ROWS * TPB; e += NT) {
+            const int row = e / TPB, bb = e % TPB;
+            if (vflag[bb]) {
+                if (row < n * m) K[((size_t)t * n * m + row) * B + b0 + bb] = ks[e];
+                else k[((size_t)t * m + (row - n * m)) * B + b0 + bb] = ks[e];
+            }
+        }
+    }
+}
+
 // K3.  One thread per (alpha, b); b fastest so loads of the shared nominal/gains coalesce and are
 // served once from L2 for all alphas.
 template <typename T, int n, int m>
@@ -492,7 +705,7 @@ ILQR_DEV void fwd_load(FwdIn<T, n, m> &d, int t, int b, int B, const T *__restri
 // one step of the forward pass: control law (iLQR_class.py:181-182), store, stage cost (:187), dynamics (:185)
 template <int INTEG, class Sys, typename T>
 ILQR_DEV void rollout_step(const Sys &sys, const QuadCost<T, Sys::N, Sys::M> &qc, const FwdIn<T, Sys::N, Sys::M> &in,
-                           T alpha, int t, int b, int B, T phi, T *x, T &cost, T *__restrict__ Xw,
+                           T alpha, int t, int bw, int B, T phi, T *x, T &cost, T *__restrict__ Xw,
                            T *__restrict__ Uw)
 {
     constexpr int n = Sys::N, m = Sys::M;
@@ -505,39 +718,58 @@ ILQR_DEV void rollout_step(const Sys &sys, const QuadCost<T, Sys::N, Sys::M> &qc
         u[j] = in.uo[j] + alpha * in.kk[j] + s;
     }
 #pragma unroll
-    for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + b] = x[i];
+    for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + bw] = x[i];
 #pragma unroll
-    for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + b] = u[j];
+    for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + bw] = u[j];
     cost += qc.stage(x, u);
     step<INTEG>(sys, qc.dt, x, u, xn, sys.time_scalar(t, phi));
 #pragma unroll
     for (int i = 0; i < n; ++i) x[i] = xn[i];
 }
 
+#ifdef ILQR_ROLLOUT_LB
+#define ILQR_ROLLOUT_BOUNDS __launch_bounds__(128, ILQR_ROLLOUT_LB)
+#else
+#define ILQR_ROLLOUT_BOUNDS
+#endif
 template <class Sys, int INTEG, typename T>
-__global__ void rollout_kernel(const __grid_constant__ Sys sys, const __grid_constant__ QuadCost<T, Sys::N, Sys::M> qc,
+__global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys sys, const __grid_constant__ QuadCost<T, Sys::N, Sys::M> qc,
                                int N, int B, int n_alpha, const __grid_constant__ AlphaList alphas,
                                const T *__restrict__ phi,
                                const T *__restrict__ x0, const T *__restrict__ X_old, const T *__restrict__ U_old,
                                const T *__restrict__ k, const T *__restrict__ K, T *__restrict__ Xc,
                                T *__restrict__ Uc, T *__restrict__ cost_alpha, const int *__restrict__ active,
                                const unsigned int *__restrict__ gate, const T *__restrict__ cost_ref,
-                               const __grid_constant__ SpecArgs sp)
+                               const __grid_constant__ SpecArgs sp, const int *__restrict__ list,
+                               const unsigned int *__restrict__ list_count)
 {
     constexpr int n = Sys::N, m = Sys::M;
     if (gate && *gate == 0u) return;
+    // Warp w of the grid handles step size (w % n_alpha) of trajectory group (w / n_alpha): the warps that
+    // re-read the same nominal trajectory and gains run next to each other, so at large batches those
+    // reads come from L1/L2 instead of once per step size from HBM.
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int ai, b;
-    if (gid < (size_t)n_alpha * B) {
-        ai = (int)(gid / B);
-        b = (int)(gid % B);
+    const size_t wg = gid >> 5, ngrp = ((size_t)B + 31) >> 5;
+    int ai, b, bw;        // bw: column of the candidate slabs / cost_alpha this thread writes
+    if (wg < ngrp * n_alpha) {
+        ai = (int)(wg % n_alpha);
+        const unsigned int idx = (unsigned int)(wg / n_alpha) * 32u + (threadIdx.x & 31u);
+        if (list) {                                                      // lazy wave: compacted trajectory list;
+            if (idx >= min(*list_count, (unsigned int)B)) return;        // results stored at the list position
+            b = list[idx];
+        } else {
+            if (idx >= (unsigned int)B) return;
+            b = (int)idx;
+        }
+        bw = (int)idx;
     } else {                                                             // speculative extra threads
-        const size_t e = gid - (size_t)n_alpha * B;
-        if (sp.cap == 0 || e >= (size_t)sp.cap * sp.n2) return;
+        const size_t e = gid - ngrp * n_alpha * 32;
+        if (list || sp.cap == 0 || e >= (size_t)sp.cap * sp.n2) return;
         const int q = (int)(e % sp.cap);
         const unsigned int cnt = min(*sp.count_cur, (unsigned int)sp.cap);
         if ((unsigned int)q >= cnt) return;
         b = sp.list_cur[q];
+        bw = b;
         ai = n_alpha + (int)(e / sp.cap);
     }
     if (active && !active[b]) return;
@@ -561,18 +793,43 @@ __global__ void rollout_kernel(const __grid_constant__ Sys sys, const __grid_con
 #ifndef ILQR_REJECT
 #define ILQR_REJECT 0
 #endif
+    if constexpr (n > 4) {
+        // large state (n = 12, m = 4): the nominal and the 48 gains of a step are consumed as they arrive;
+        // a register-resident prefetch buffer would spill, and these batches have enough warps per SM to
+        // cover the load latency by occupancy
+        for (int t = 0; t < N; ++t) {
+            T dx[n], u[m], xn[n];
+#pragma unroll
+            for (int i = 0; i < n; ++i) dx[i] = x[i] - X_old[((size_t)t * n + i) * B + b];
+#pragma unroll
+            for (int j = 0; j < m; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int i = 0; i < n; ++i) s += K[(((size_t)t * m + j) * n + i) * B + b] * dx[i];
+                u[j] = U_old[((size_t)t * m + j) * B + b] + alpha * k[((size_t)t * m + j) * B + b] + s;
+            }
+#pragma unroll
+            for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + bw] = x[i];
+#pragma unroll
+            for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + bw] = u[j];
+            cost += qc.stage(x, u);
+            step<INTEG>(sys, qc.dt, x, u, xn, sys.time_scalar(t, ph));
+#pragma unroll
+            for (int i = 0; i < n; ++i) x[i] = xn[i];
+        }
+    } else {
 #if ILQR_UNROLL2
     FwdIn<T, n, m> in0, in1;
     fwd_load(in0, 0, b, B, X_old, U_old, k, K);
     for (int t = 0; t < N; t += 2) {
         if (t + 1 < N) fwd_load(in1, t + 1, b, B, X_old, U_old, k, K);
-        rollout_step<INTEG>(sys, qc, in0, alpha, t, b, B, ph, x, cost, Xw, Uw);
+        rollout_step<INTEG>(sys, qc, in0, alpha, t, bw, B, ph, x, cost, Xw, Uw);
         if (t + 1 >= N) break;
         if (t + 2 < N) fwd_load(in0, t + 2, b, B, X_old, U_old, k, K);
-        rollout_step<INTEG>(sys, qc, in1, alpha, t + 1, b, B, ph, x, cost, Xw, Uw);
+        rollout_step<INTEG>(sys, qc, in1, alpha, t + 1, bw, B, ph, x, cost, Xw, Uw);
 #if ILQR_REJECT
         if (can_reject && !(cost <= c_ref)) {
-            cost_alpha[(size_t)ai * B + b] = cost;                       // already > cost to beat (or NaN): rejected
+            cost_alpha[(size_t)ai * B + bw] = cost;                       // already > cost to beat (or NaN): rejected
             return;
         }
 #endif
@@ -582,19 +839,20 @@ __global__ void rollout_kernel(const __grid_constant__ Sys sys, const __grid_con
     fwd_load(in0, 0, b, B, X_old, U_old, k, K);
     for (int t = 0; t < N; ++t) {
         if (t + 1 < N) fwd_load(in1, t + 1, b, B, X_old, U_old, k, K);
-        rollout_step<INTEG>(sys, qc, in0, alpha, t, b, B, ph, x, cost, Xw, Uw);
+        rollout_step<INTEG>(sys, qc, in0, alpha, t, bw, B, ph, x, cost, Xw, Uw);
         in0 = in1;
 #if ILQR_REJECT
         if (can_reject && !(cost <= c_ref)) {
-            cost_alpha[(size_t)ai * B + b] = cost;
+            cost_alpha[(size_t)ai * B + bw] = cost;
             return;
         }
 #endif
     }
 #endif
+    }
 #pragma unroll
-    for (int i = 0; i < n; ++i) Xw[((size_t)N * n + i) * B + b] = x[i];
-    cost_alpha[(size_t)ai * B + b] = cost + qc.terminal(x);              // :245
+    for (int i = 0; i < n; ++i) Xw[((size_t)N * n + i) * B + bw] = x[i];
+    cost_alpha[(size_t)ai * B + bw] = cost + qc.terminal(x);              // :245
 }
 
 // after the alpha = 0 rollout (iLQR_class.py:257-263): everything active, candidate 0 is the nominal
@@ -680,6 +938,78 @@ __global__ void select_kernel(int B, int a_lo, int a_hi, int wave, const T *__re
         if (ns) atomicAdd(&ctl->n_active[it + 1], ns);
         if (nr) atomicAdd(&ctl->total_iters, (unsigned long long)nr);
         if (nd) atomicAdd(n2_count, nd);
+    }
+}
+
+// K4, lazy multi-wave form (large batches).  The step sizes are split into consecutive waves
+// [a_lo, a_hi).  Wave 0 covers every active trajectory; a trajectory that accepts none of a wave's step
+// sizes is appended to a compacted list (warp-aggregated atomics keep a warp's entries contiguous) and
+// only the listed trajectories are rolled out in the next wave.  The decision per trajectory is the
+// reference's (lowest-index acceptable step size); only the amount of work changes.
+template <typename T>
+__global__ void select_lazy_kernel(int B, int a_lo, int a_hi, int wave, int last, const T *__restrict__ cost_alpha,
+                                   T *__restrict__ cost, int *__restrict__ winner, int *__restrict__ active,
+                                   int *__restrict__ iters, int *__restrict__ status, T tol, int it, int maxiter,
+                                   Control *ctl, const int *__restrict__ list_in, const unsigned int *cnt_in,
+                                   int *__restrict__ list_out, unsigned int *cnt_out, int *__restrict__ wslot,
+                                   int *__restrict__ tr_alpha, T *__restrict__ tr_cost)
+{
+    if (ctl->n_active[it] == 0u) return;
+    if (wave > 0 && *cnt_in == 0u) return;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = gid;
+    bool mine = false;
+    if (wave == 0) {
+        if (gid < B) {
+            mine = active[gid] != 0;
+            if (!mine) winner[gid] = -1;
+        }
+    } else if ((unsigned int)gid < min(*cnt_in, (unsigned int)B)) {
+        mine = true;
+        b = list_in[gid];
+    }
+    bool still = false, app = false;
+    if (mine) {
+        const T c0 = cost[b];
+        int w = -1;
+        T cw = c0;
+        for (int a = a_lo; a < a_hi; ++a) {
+            const T c = cost_alpha[(size_t)a * B + gid];                 // stored at the list position (wave 0: gid == b)
+            if (c <= c0) { w = a; cw = c; break; }                       // NaN compares false, as in Python
+        }
+        if (w < 0 && !last) {
+            app = true;                                                  // decided by a later wave
+        } else {
+            winner[b] = w;
+            wslot[b] = gid;
+            iters[b] = it + 1;
+            if (tr_alpha) tr_alpha[(size_t)it * B + b] = w;
+            if (tr_cost) tr_cost[(size_t)(it + 1) * B + b] = cw;
+            if (w < 0) {
+                status[b] = ILQR_ST_LS_FAILED;
+                active[b] = 0;
+            } else {
+                cost[b] = cw;
+                if (it + 1 >= maxiter) { status[b] = ILQR_ST_MAXITER; active[b] = 0; }
+                else if (abs_t(cw - c0) <= tol) { status[b] = ILQR_ST_CONVERGED; active[b] = 0; }
+                else still = true;
+            }
+        }
+    }
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
+    const unsigned ma = __ballot_sync(full, app);
+    if (ma) {
+        const int leader = __ffs(ma) - 1;
+        unsigned int base = 0;
+        if ((int)lane == leader) base = atomicAdd(cnt_out, (unsigned int)__popc(ma));
+        base = __shfl_sync(full, base, leader);
+        if (app) list_out[base + __popc(ma & ((1u << lane) - 1u))] = b;
+    }
+    const unsigned ns = __popc(__ballot_sync(full, still));
+    const unsigned nr = __popc(__ballot_sync(full, mine && wave == 0));
+    if (lane == 0) {
+        if (ns) atomicAdd(&ctl->n_active[it + 1], ns);
+        if (nr) atomicAdd(&ctl->total_iters, (unsigned long long)nr);
     }
 }
 
@@ -837,6 +1167,9 @@ struct Handle {
     int n_alpha_eff;          // tries actually made: stops once alpha < min_alpha (iLQR_class.py:300-302)
     int n_first;              // step sizes rolled out eagerly (first wave); the rest only where needed
     int spec_cap;             // trajectories whose deferred step sizes ride along speculatively (SpecArgs)
+    int lazy;                 // large batches: lazy multi-wave line search over compacted lists (select_lazy_kernel)
+    int n_waves;
+    int wave_lo[ILQR_MAX_WAVES + 1];
     AlphaList alphas;
     long long launches;
     int last_cuda;
@@ -863,8 +1196,13 @@ static inline int block_for(size_t threads)
 }
 
 struct WsLayout {
-    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, active, defer, mark, lists, total;
+    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, wslot, active, defer, mark, lists, total;
 };
+
+static size_t ctl_bytes(int maxiter)
+{
+    return sizeof(Control) + sizeof(unsigned int) * (3 + ILQR_MAX_WAVES) * (size_t)(maxiter + 2);
+}
 
 static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
 {
@@ -874,14 +1212,18 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
     WsLayout L;
     size_t off = 0;
     // n_active[maxiter + 2], then the per-iteration deferred (second-wave) counters [maxiter + 2], then the
-    // per-iteration speculation-list counters [maxiter + 2]
-    L.ctl = off; off = al(off + sizeof(Control) + sizeof(unsigned int) * 3 * (size_t)(p.maxiter + 2));
-    L.A = off; off = al(off + w * N * n * n * B);
-    L.Bd = off; off = al(off + w * N * n * m * B);
+    // per-iteration speculation-list counters [maxiter + 2], then the lazy-wave list counters
+    // [maxiter + 2][ILQR_MAX_WAVES]
+    L.ctl = off; off = al(off + ctl_bytes(p.maxiter));
+    // the LTV model generates A_t, B_t inside its kernels: no per-trajectory linearization is stored
+    const size_t lin = p.model == ILQR_LTV ? 0 : 1;
+    L.A = off; off = al(off + lin * w * N * n * n * B);
+    L.Bd = off; off = al(off + lin * w * N * n * m * B);
     L.Xc = off; off = al(off + w * (size_t)n_alpha * (N + 1) * n * B);
     L.Uc = off; off = al(off + w * (size_t)n_alpha * N * m * B);
     L.cost_alpha = off; off = al(off + w * (size_t)n_alpha * B);
     L.winner = off; off = al(off + 4 * B);
+    L.wslot = off; off = al(off + 4 * B);
     L.active = off; off = al(off + 4 * B);
     L.defer = off; off = al(off + 4 * B);
     L.mark = off; off = al(off + 4 * B);
@@ -934,7 +1276,7 @@ template <class F> static int dispatch(const Handle *h, F &&f)
 // ---- launch helpers -----------------------------------------------------------------------
 
 static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U, void *A, void *Bd, const void *Xc, const void *Uc,
-                                   const int *winner, const int *active, int do_lin, const unsigned int *g0,
+                                   const int *winner, const int *wslot, const int *active, int do_lin, const unsigned int *g0,
                                    const unsigned int *g1, cudaStream_t st)
 {
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
@@ -944,8 +1286,8 @@ static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U,
         const size_t threads = (size_t)(h->p.N + 1) * h->p.B;
         const int bs = 128;
         commit_linearize_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
-            sys, qc.dt, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (T *)A, (T *)Bd, (const T *)Xc, (const T *)Uc, winner, active,
-            do_lin, g0, g1);
+            sys, qc.dt, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (T *)A, (T *)Bd, (const T *)Xc, (const T *)Uc, winner, wslot,
+            active, do_lin, g0, g1);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });
@@ -1004,9 +1346,34 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
     });
 }
 
+// K2 of the LTV model: A_t, B_t generated in the kernel (no linearization buffers)
+static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const void *U, void *K, void *k,
+                               const int *active, const unsigned int *gate, cudaStream_t st)
+{
+    constexpr int TPB = 16;
+    auto go = [&](auto tz) -> int {
+        using T = decltype(tz);
+        const size_t smem = sizeof(T) * (size_t)(504 * TPB + 48 + 144 + 16 + 288);
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(backward_ltv_kernel<T, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem);
+            if (e != cudaSuccess) { h->last_cuda = (int)e; return ILQR_E_CUDA; }
+            configured = true;
+        }
+        backward_ltv_kernel<T, TPB><<<grid_for(h->p.B, TPB), TPB * 16, smem, st>>>(
+            make_ltv<T>(h->p), make_cost<T, 12, 4>(h->p), h->p.N, h->p.B, (const T *)phi, (const T *)X, (const T *)U,
+            (T *)K, (T *)k, active, gate);
+        ILQR_CHECK_LAUNCH(h);
+        return ILQR_OK;
+    };
+    return h->p.dtype == ILQR_F64 ? go(double(0)) : go(float(0));
+}
+
 static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const void *phi, const void *x0, const void *X, const void *U,
                           const void *k, const void *K, void *Xc, void *Uc, void *cost_alpha, const int *active,
-                          const unsigned int *gate, const void *cost_ref, cudaStream_t st, const SpecArgs *spec = nullptr)
+                          const unsigned int *gate, const void *cost_ref, cudaStream_t st, const SpecArgs *spec = nullptr,
+                          const int *list = nullptr, const unsigned int *list_count = nullptr)
 {
     SpecArgs sp;
     std::memset(&sp, 0, sizeof sp);
@@ -1015,12 +1382,16 @@ static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const voi
         using T = decltype(tz);
         using Sys = decltype(sys);
         constexpr int I = decltype(integ)::value;
-        const size_t threads = (size_t)n_alpha * h->p.B + (size_t)sp.cap * sp.n2;
+        const size_t threads = (size_t)n_alpha * (((size_t)h->p.B + 31) / 32 * 32) + (size_t)sp.cap * sp.n2;
         const char *bs_env = getenv("ILQR_ROLLOUT_BS");
-        const int bs = bs_env ? atoi(bs_env) : block_for(threads);
+        // <= 128 threads per block: the kernel's ~150 registers then leave room for 12 warps per SM
+        int bs = bs_env ? atoi(bs_env) : block_for(threads);
+        if (!bs_env && bs > 128) bs = 128;
+        // lazy waves: the warps of one trajectory group (one per step size) share a block, hence an L1
+        if (!bs_env && h->lazy && n_alpha <= 4 && threads >= (size_t)148 * 16 * 32 * n_alpha) bs = 32 * n_alpha;
         rollout_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
             sys, qc, h->p.N, h->p.B, n_alpha, al, (const T *)phi, (const T *)x0, (const T *)X, (const T *)U, (const T *)k,
-            (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref, sp);
+            (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref, sp, list, list_count);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });
@@ -1041,6 +1412,59 @@ static int launch_select(Handle *h, int a_lo, int a_hi, int wave, const void *ca
                                                              ctl, n2c, h->tr_alpha, (float *)h->tr_cost, sp);
     ILQR_CHECK_LAUNCH(h);
     return ILQR_OK;
+}
+
+static int launch_select_lazy(Handle *h, int a_lo, int a_hi, int wave, int last, const void *ca, void *cost, int *winner,
+                              int *active, int *iters, int *status, int it, Control *ctl, const int *list_in,
+                              const unsigned int *cnt_in, int *list_out, unsigned int *cnt_out, int *wslot, cudaStream_t st)
+{
+    const int B = h->p.B, bs = 128;
+    if (h->p.dtype == ILQR_F64)
+        select_lazy_kernel<double><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, last, (const double *)ca,
+                                                                   (double *)cost, winner, active, iters, status, h->p.tol,
+                                                                   it, h->p.maxiter, ctl, list_in, cnt_in, list_out, cnt_out,
+                                                                   wslot, h->tr_alpha, (double *)h->tr_cost);
+    else
+        select_lazy_kernel<float><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, last, (const float *)ca,
+                                                                  (float *)cost, winner, active, iters, status,
+                                                                  (float)h->p.tol, it, h->p.maxiter, ctl, list_in, cnt_in,
+                                                                  list_out, cnt_out, wslot, h->tr_alpha, (float *)h->tr_cost);
+    ILQR_CHECK_LAUNCH(h);
+    return ILQR_OK;
+}
+
+// wave boundaries from per-wave sizes (clamped to the number of tries actually made)
+static void set_waves(Handle *h, int n_waves, const int *sizes)
+{
+    h->n_waves = 0;
+    h->wave_lo[0] = 0;
+    int lo = 0;
+    for (int v = 0; v < n_waves && v < ILQR_MAX_WAVES && lo < h->n_alpha_eff; ++v) {
+        int sz = sizes[v] < 1 ? 1 : sizes[v];
+        if (v == n_waves - 1 || v == ILQR_MAX_WAVES - 1 || lo + sz > h->n_alpha_eff) sz = h->n_alpha_eff - lo;
+        lo += sz;
+        h->wave_lo[++h->n_waves] = lo;
+    }
+    h->lazy = h->n_waves > 0;
+}
+
+// default schedule: lazy waves of 2,2,2,rest from 16384 trajectories up (FP64-throughput-bound rollouts),
+// eager below (latency-bound rollouts).  ILQR_WAVES="2,2,2,4" / ILQR_WAVES=0 override.
+static void default_waves(Handle *h)
+{
+    int sizes[ILQR_MAX_WAVES] = { 2, 2, 2, ILQR_MAX_ALPHAS, 0, 0, 0, 0 };
+    int nw = h->p.B >= 16384 ? 4 : 0;
+    if (const char *e = getenv("ILQR_WAVES")) {
+        nw = 0;
+        for (const char *q = e; *q && nw < ILQR_MAX_WAVES;) {
+            const int v = atoi(q);
+            if (v <= 0) break;
+            sizes[nw++] = v;
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+    }
+    set_waves(h, nw, sizes);
 }
 
 // How many of the n_alpha step sizes to roll out eagerly.  The rollout kernel is FP64-pipe bound and
@@ -1167,6 +1591,7 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
     h->n_alpha_eff = cnt;
     h->n_first = first_wave_size(p->B, cnt);
     h->spec_cap = spec_capacity(p->B, h->n_first, cnt);
+    default_waves(h);
     if (cudaMallocHost((void **)&h->h_flag, 2 * sizeof(unsigned int)) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming) != cudaSuccess) {
@@ -1222,8 +1647,8 @@ int ilqr_linearize(ilqr_handle_t hh, const void *phi, const void *X, const void 
 {
     Handle *h = (Handle *)hh;
     if (!h || !X || !U || !A || !Bd) return ILQR_E_INVALID;
-    return launch_commit_linearize(h, phi, (void *)X, (void *)U, A, Bd, nullptr, nullptr, nullptr, nullptr, 1, nullptr,
-                                   nullptr, (cudaStream_t)stream);
+    return launch_commit_linearize(h, phi, (void *)X, (void *)U, A, Bd, nullptr, nullptr, nullptr, nullptr, nullptr, 1,
+                                   nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int ilqr_cost_expansion(ilqr_handle_t hh, const void *X, const void *U, void *l, void *lx, void *lu, void *lxx,
@@ -1270,6 +1695,8 @@ int ilqr_backward_pass(ilqr_handle_t hh, const void *phi, const void *X, const v
     const WsLayout L = ws_layout(h->p, h->n_alpha_eff);
     if (ws_bytes < L.total) return ILQR_E_WORKSPACE;
     char *w = (char *)ws;
+    if (!X || !U || !K || !k) return ILQR_E_INVALID;
+    if (h->p.model == ILQR_LTV) return launch_backward_ltv(h, phi, X, U, K, k, nullptr, nullptr, (cudaStream_t)stream);
     int rc = ilqr_linearize(hh, phi, X, U, w + L.A, w + L.Bd, stream);
     if (rc) return rc;
     return ilqr_backward(hh, X, U, w + L.A, w + L.Bd, K, k, stream);
@@ -1320,6 +1747,7 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     void *A = w + L.A, *Bd = w + L.Bd, *Xc = w + L.Xc, *Uc = w + L.Uc, *ca = w + L.cost_alpha;
     int *winner = (int *)(w + L.winner), *active = (int *)(w + L.active), *defer = (int *)(w + L.defer);
     int *mark = (int *)(w + L.mark), *lists = (int *)(w + L.lists);
+    int *wslot = h->lazy ? (int *)(w + L.wslot) : nullptr;      // only the lazy schedule stores candidates by list position
     const int B = p.B, bsB = 128;
     int rc;
     // two-wave line search (see select_kernel): n1 eager step sizes, n2 deferred ones
@@ -1330,7 +1758,7 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     std::memset(&al2, 0, sizeof al2);
     for (int i = 0; i < n2; ++i) al2.a[i] = h->alphas.a[n1 + i];
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { h->last_cuda = (int)e_; return ILQR_E_CUDA; } } while (0)
-    CU(cudaMemsetAsync(ctl, 0, sizeof(Control) + sizeof(unsigned int) * 3 * (size_t)(p.maxiter + 2), st));
+    CU(cudaMemsetAsync(ctl, 0, ctl_bytes(p.maxiter), st));
     CU(cudaMemsetAsync(defer, 0, sizeof(int) * (size_t)B, st));
     CU(cudaMemsetAsync(mark, 0, sizeof(int) * (size_t)B, st));
     // initial rollout, alpha = 0, with the incoming X,K,k (iLQR_class.py:257-259) into candidate slab 0
@@ -1360,10 +1788,35 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
             const unsigned int *g = &ctl->n_active[it];
             const unsigned int *gprev = it > 0 ? &ctl->n_active[it - 1] : g;
             prof_mark(h, ILQR_KC_OTHER, st);
-            if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, active, 1, g, gprev, st))) return rc;
+            const bool ltv = p.model == ILQR_LTV;      // commit only: A_t, B_t are generated inside the LTV kernels
+            if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, it > 0 ? wslot : nullptr, active,
+                                              ltv ? 0 : 1, g, gprev, st))) return rc;
             prof_mark(h, ILQR_KC_LINEARIZE, st);
-            if ((rc = launch_backward(h, X, U, A, Bd, K, k, active, g, st))) return rc;
+            if ((rc = ltv ? launch_backward_ltv(h, phi, X, U, K, k, active, g, st)
+                          : launch_backward(h, X, U, A, Bd, K, k, active, g, st))) return rc;
             prof_mark(h, ILQR_KC_BACKWARD, st);
+            if (h->lazy) {
+                // lazy line search: wave v rolls out step sizes [wave_lo[v], wave_lo[v+1]) for the trajectories
+                // that accepted none so far (wave 0: every active one); later waves return at once while
+                // their list is empty
+                unsigned int *wcnt = &ctl->n_active[3 * (p.maxiter + 2)] + (size_t)it * ILQR_MAX_WAVES;
+                for (int v = 0; v < h->n_waves; ++v) {
+                    const int lo = h->wave_lo[v], hi = h->wave_lo[v + 1];
+                    AlphaList alv;
+                    std::memset(&alv, 0, sizeof alv);
+                    for (int i = lo; i < hi; ++i) alv.a[i - lo] = h->alphas.a[i];
+                    const int *lin = v ? lists + (size_t)((v - 1) & 1) * B : nullptr;
+                    int *lout = lists + (size_t)(v & 1) * B;
+                    const unsigned int *cin = v ? wcnt + v - 1 : nullptr;
+                    if ((rc = launch_rollout(h, hi - lo, alv, phi, x0, X, U, k, K, (char *)Xc + xc_slab * lo,
+                                             (char *)Uc + uc_slab * lo, (char *)ca + wbytes * (size_t)lo * B,
+                                             v ? nullptr : active, v ? cin : g, nullptr, st, nullptr, lin, cin))) return rc;
+                    prof_mark(h, ILQR_KC_ROLLOUT, st);
+                    if ((rc = launch_select_lazy(h, lo, hi, v, v == h->n_waves - 1, ca, cost, winner, active, iters, status,
+                                                 it, ctl, lin, cin, lout, wcnt + v, wslot, st))) return rc;
+                }
+                continue;
+            }
             // line search, wave 1: the first n1 step sizes for every active trajectory (+ the deferred ones of
             // the trajectories on this iteration's speculation list)
             SpecArgs sp;
@@ -1403,7 +1856,8 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
         }
     }
     // commit the candidates accepted in the last executed iteration (no linearization)
-    if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, nullptr, 0, nullptr, nullptr, st))) return rc;
+    if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, it > 0 ? wslot : nullptr, nullptr, 0, nullptr,
+                                      nullptr, st))) return rc;
     if (total_iters) {
         unsigned long long tot = 0;
         CU(cudaMemcpyAsync(&tot, &ctl->total_iters, sizeof tot, cudaMemcpyDeviceToHost, st));
@@ -1412,6 +1866,14 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
         prof_collect(h);
     }
 #undef CU
+    return ILQR_OK;
+}
+
+int ilqr_set_linesearch_waves(ilqr_handle_t hh, int n_waves, const int32_t *sizes)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || n_waves < 0 || n_waves > ILQR_MAX_WAVES || (n_waves > 0 && !sizes)) return ILQR_E_INVALID;
+    set_waves(h, n_waves, sizes);
     return ILQR_OK;
 }
 

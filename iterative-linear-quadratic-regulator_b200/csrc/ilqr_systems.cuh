@@ -188,6 +188,7 @@ struct LtvSys {
     ILQR_DEV T time_scalar(int t, T phi) const { return amp * sin_t(two_pi_over_N * T(t) + phi); }
     ILQR_DEV void xdot(T w, const T *x, const T *u, T *xd) const
     {
+#pragma unroll
         for (int i = 0; i < N; ++i) {
             T s1 = T(0), s2 = T(0);
 #pragma unroll
@@ -204,7 +205,8 @@ struct LtvSys {
 // small dense LU with partial pivoting, fully unrolled (used by backward Euler and by the
 // Q_uu solve for m >= 2).  Rows are swapped by value so all indices stay compile-time.
 // ------------------------------------------------------------------------------------------
-template <int n, int nrhs, typename T>
+// FAST_RCP: reciprocals of the pivots by rcp_t (MUFU seed + Newton, ~1 ulp) instead of IEEE division.
+template <int n, int nrhs, typename T, bool FAST_RCP = false>
 ILQR_DEV void lu_solve_inplace(T (*a)[n], T (*b)[nrhs])
 {
 #pragma unroll
@@ -218,7 +220,7 @@ ILQR_DEV void lu_solve_inplace(T (*a)[n], T (*b)[nrhs])
 #pragma unroll
             for (int c = 0; c < nrhs; ++c) { const T u = b[j][c], v = b[i][c]; b[j][c] = sw ? v : u; b[i][c] = sw ? u : v; }
         }
-        const T r = T(1) / a[j][j];
+        const T r = FAST_RCP ? rcp_t(a[j][j]) : T(1) / a[j][j];
 #pragma unroll
         for (int i = j + 1; i < n; ++i) {
             const T l = a[i][j] * r;
@@ -230,7 +232,7 @@ ILQR_DEV void lu_solve_inplace(T (*a)[n], T (*b)[nrhs])
     }
 #pragma unroll
     for (int i = n - 1; i >= 0; --i) {
-        const T r = T(1) / a[i][i];
+        const T r = FAST_RCP ? rcp_t(a[i][i]) : T(1) / a[i][i];
 #pragma unroll
         for (int c = 0; c < nrhs; ++c) {
             T s = b[i][c];
@@ -374,6 +376,7 @@ ILQR_DEV void step_jac(const Sys &s, T dt, const T *x, const T *u, T (*A)[Sys::N
 {
     constexpr int n = Sys::N, NQ = Sys::NQ, M = Sys::M;
     if constexpr (Sys::FIRST_ORDER) {
+#pragma unroll
         for (int i = 0; i < n; ++i) {
 #pragma unroll
             for (int j = 0; j < n; ++j) A[i][j] = ((i == j) ? T(1) : T(0)) + dt * (s.Ac[i][j] + w * s.E[i][j]);

@@ -224,3 +224,22 @@ def test_backward_variants_agree(monkeypatch):
         res[lanes] = sol.backward_pass(g["it_X"][3], g["it_U"][3])
     assert rel_err(res["1"][1], res["0"][1]) < 1e-11 and rel_err(res["1"][0], res["0"][0], floor=1e-6) < 1e-10
     assert rel_err(res["1"][1], g["it_K"][3]) < TOL
+
+
+def test_lazy_wave_line_search_is_exact():
+    """The lazy multi-wave schedule used for large batches (compacted lists of trajectories that accepted
+    none of the step sizes tried so far) evaluates a subset of the eager schedule's rollouts and must pick
+    exactly the same step size for every trajectory in every iteration: bit-identical results."""
+    from class_files.iLQR_class import iLQR
+    B, N = 1000, 80       # not a multiple of the warp or block size: ragged last warp in the lists
+    x0 = cfg2_x0(B, seed=5)
+    out = {}
+    for name, waves in (("eager", ()), ("2224", (2, 2, 2, 4)), ("ones", (1,) * 7 + (3,)), ("37", (3, 7)), ("big", (16,))):
+        sol = iLQR(ua_system(), 0.8, x0, np.zeros((1, N)), maxiter=12, verbose=False)
+        sol.set_linesearch_waves(waves)
+        X, U, cost = sol.optimize_trajectory()
+        out[name] = (X.copy(), U.copy(), cost.copy(), sol.K.copy(), sol.iterations.copy(), sol.status.copy())
+    assert len(np.unique(out["eager"][4])) > 1          # the batch really has trajectories at different stages
+    for name in ("2224", "ones", "37", "big"):
+        for a, b in zip(out["eager"], out[name]):
+            assert np.array_equal(a, b), name
