@@ -136,6 +136,40 @@ def workload_config(args, world):
                          "no explicit flush"}
 
 
+def large_batch_line(torch, iLQR, sysm, BL, steps=3, warmup=2):
+    """The bench step at BL trajectories on this GPU (x0 from the same generator): traj-iter/s and per-kernel
+    times per iLQR iteration.  At this size the backward pass streams its linearization at HBM speed."""
+    x0 = torch.as_tensor(cfg2_x0(BL, seed=1)).cuda()
+    U0 = torch.zeros((1, N_H), dtype=torch.float64, device="cuda")
+    sol = iLQR(sysm, T_H, x0, U0, tol=0.0, maxiter=ITERS, verbose=False, n_alpha=N_ALPHA)
+
+    def step():
+        sol.reset_state()
+        sol._U.zero_()
+        return sol.solve_device(sync=True)
+    for _ in range(warmup):
+        step()
+    sol.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    units = sum(step() for _ in range(steps))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    kt = sol.kernel_times()
+    nit = max(1, kt["linearize"][1])
+    kern = {}
+    for name in ("linearize", "backward", "rollout"):
+        avg = kt[name][0] / nit
+        alg = BYTES[name] * N_H * BL + (8 * N_ALPHA * BL if name == "rollout" else 0)
+        kern[name] = {"ms_per_iteration": avg, "achieved_GBps": alg / avg / 1e6}
+    return {"batch": BL, "value": units / (ms * 1e-3), "unit": UNIT, "steps": steps, "ms_per_step": ms / steps,
+            "line_search": "lazy waves of 2,2,2,4 step sizes over compacted lists", "kernels": kern,
+            "roofline_backward": {"bound": "hbm", "kernel": "backward", "unit": "GB/s",
+                                  "achieved": kern["backward"]["achieved_GBps"]}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -145,6 +179,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="trajectories per GPU")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="trajectories per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--large-batch", type=int, default=131072,
+                    help="N=1 only: also time a few steps at this batch (config 5's per-GPU shard at 8 GPUs), where "
+                         "the passes are throughput bound; reported under 'large_batch'.  0 disables.")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,6 +270,13 @@ def main():
     h2d = x0_host.nbytes + U_host.nbytes
     d2h = X.nbytes + U.nbytes + cost.nbytes
 
+    # ---- N=1 only: the same solve at config 5's per-GPU shard size (HBM/FP64-throughput-bound regime) ------
+    large = None
+    if world == 1 and args.large_batch > 0:
+        del sol_h
+        torch.cuda.empty_cache()
+        large = large_batch_line(torch, iLQR, sysm, args.large_batch)
+
     if world > 1:
         t = torch.tensor([ms, te, float(units), float(units_e)], dtype=torch.float64, device="cuda")
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -264,13 +308,20 @@ def main():
     kern = {k: kinfo(k) for k in ("linearize", "backward", "rollout")}
     kern["init_rollout_ms"] = ktimes["init_rollout"][0] / max(1, ktimes["init_rollout"][1])
     kern["other_ms_per_iteration"] = ktimes["other"][0] / max(1, ktimes["other"][1])
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+    # command (profiles/traffic.json, written by scripts/ncu_summary.py --traffic); null when absent
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"B{B}", {})
+    except Exception:
+        pass
     dom = max(("linearize", "backward", "rollout"), key=lambda k: ktimes[k][0])
     roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
-            "frac": kern[dom]["achieved_GBps"] / peak, "traffic": None, "peak_source": peak_src,
+            "frac": kern[dom]["achieved_GBps"] / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
             "note": "rollout is FP64-pipe/latency bound at this batch, not HBM bound (DESIGN.md); "
                     "see roofline_backward for the HBM-bound kernel north_star names"}
     roof_b = {"bound": "hbm", "kernel": "backward", "achieved": kern["backward"]["achieved_GBps"], "peak": peak,
-              "unit": "GB/s", "frac": kern["backward"]["achieved_GBps"] / peak, "traffic": None}
+              "unit": "GB/s", "frac": kern["backward"]["achieved_GBps"] / peak, "traffic": traffic.get("backward")}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -295,7 +346,10 @@ def main():
            "e2e": {"value": units_e / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": te / args.steps * 1e3},
            "gpu_launches": int(launches), "roofline": roof, "roofline_backward": roof_b, "kernels": kern,
-           "cpu_baseline": cpu, "clocks": clocks}
+           "large_batch": large, "cpu_baseline": cpu, "clocks": clocks}
+    if large:
+        large["roofline_backward"]["peak"] = peak
+        large["roofline_backward"]["frac"] = large["roofline_backward"]["achieved"] / peak
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -69,6 +69,13 @@ typedef struct ilqr_problem_t {
     /* ILQR_LTV: x+ = x + dt ((Ac + ltv_amp sin(2 pi t/N + phi_b) E) x + Bc u) */
     double Ac[ILQR_NMAX * ILQR_NMAX], E[ILQR_NMAX * ILQR_NMAX], Bc[ILQR_NMAX * ILQR_MMAX];
     double ltv_amp;
+    /* EXTENSION (the reference has no regularisation, iLQR_class.py:109-110): per-trajectory Levenberg-
+     * Marquardt term, Q_uu + mu I, scheduled on the device.  reg_factor <= 1 (default 0) disables it and
+     * keeps the reference behaviour exactly.  Enabled: mu starts at reg_init; an iteration whose line search
+     * accepts no step size is retried with mu <- max(mu reg_factor, reg_min) instead of ending the solve
+     * (:304-307), which fails only once mu > reg_max; after an accepted step mu <- mu / reg_factor (0 below
+     * reg_min). */
+    double reg_init, reg_factor, reg_min, reg_max;
 } ilqr_problem_t;
 
 typedef struct ilqr_handle_s *ilqr_handle_t;
@@ -138,6 +145,11 @@ int ilqr_solve(ilqr_handle_t h, const void *phi, const void *x0, void *X, void *
  * is the default for small batches where the rollout is latency bound; large batches default to waves of
  * 2,2,2,rest.  The accepted step size of every trajectory is the same under every schedule. */
 int ilqr_set_linesearch_waves(ilqr_handle_t h, int n_waves, const int32_t *sizes);
+
+/* Optional device buffer mu[B] (element type of the handle) for the regularisation state of ilqr_solve:
+ * initialised to reg_init at the start of every solve and left holding the final values.  NULL (default)
+ * keeps the state in the workspace.  Ignored while reg_factor <= 1. */
+int ilqr_set_mu_buffer(ilqr_handle_t h, void *mu);
 
 /* Optional per-iteration trace written by ilqr_solve (the information the reference prints when
  * verbose=True, iLQR_class.py:262,296,306): alpha_idx[maxiter][B] (int32: accepted try index, -1 = line

@@ -30,6 +30,7 @@ class Problem(C.Structure):
         ("Qf", C.c_double * (NMAX * NMAX)), ("x_target", C.c_double * NMAX),
         ("Ac", C.c_double * (NMAX * NMAX)), ("E", C.c_double * (NMAX * NMAX)),
         ("Bc", C.c_double * (NMAX * MMAX)), ("ltv_amp", C.c_double),
+        ("reg_init", C.c_double), ("reg_factor", C.c_double), ("reg_min", C.c_double), ("reg_max", C.c_double),
     ]
 
 
@@ -49,6 +50,7 @@ SIGNATURES = {
     "ilqr_solve": (C.c_int, [_VP] * 8 + [_VP, _VP, _VP, C.c_size_t, _VP, _I64P]),
     "ilqr_set_trace": (C.c_int, [_VP, _VP, _VP]),
     "ilqr_set_linesearch_waves": (C.c_int, [_VP, C.c_int, _I32P]),
+    "ilqr_set_mu_buffer": (C.c_int, [_VP, _VP]),
     "ilqr_set_profiling": (C.c_int, [_VP, C.c_int]),
     "ilqr_get_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_double), _I64P]),
     "ilqr_mpc_shift": (C.c_int, [_VP, _VP, _VP, _VP]),

@@ -27,7 +27,8 @@ from .systems.system_base import System
 class iLQR:
     def __init__(self, system: System, T: float, x_0, U_init, tol: float = 1e-5, maxiter: int = 100,
                  alpha_factor: float = 0.5, min_alpha: float = 1e-8, verbose: bool = True, n_alpha: int = 10,
-                 phi=None):
+                 phi=None, reg_init: float = 0.0, reg_factor: float = 0.0, reg_min: float = 1e-6,
+                 reg_max: float = 1e10):
         self.system = system
         self.T = T
         self.tol = tol
@@ -63,8 +64,13 @@ class iLQR:
 
         self._torch_out = D.is_torch(x_0) and x_0.is_cuda
         self._tdt = D.torch_dtype(system.dtype)
+        # Extension (no counterpart in the reference): Levenberg-Marquardt regularisation Q_uu + mu I with the
+        # per-trajectory mu scheduled on the device; reg_factor <= 1 (default) keeps the reference behaviour
+        self.reg_factor = reg_factor
         self._handle = D.Handle(system.make_problem(self.N, self.B, tol=tol, maxiter=maxiter,
-                                                    alpha_factor=alpha_factor, min_alpha=min_alpha, n_alpha=n_alpha))
+                                                    alpha_factor=alpha_factor, min_alpha=min_alpha, n_alpha=n_alpha,
+                                                    reg_init=reg_init, reg_factor=reg_factor, reg_min=reg_min,
+                                                    reg_max=reg_max))
         n, m, N, B = self.n_x, self.n_u, self.N, self.B
         dev = dict(dtype=self._tdt, device="cuda")
         # device state, batch-innermost (include/ilqr_b200.h)
@@ -77,6 +83,10 @@ class iLQR:
         self._iters = torch.zeros((B,), dtype=torch.int32, device="cuda")
         self._status = torch.full((B,), 3, dtype=torch.int32, device="cuda")
         self._trace = None
+        self._mu = None
+        if reg_factor > 1.0:
+            self._mu = torch.full((B,), float(reg_init), **dev)
+            self._handle.check(self._handle.lib.ilqr_set_mu_buffer(self._handle.h, D.ptr(self._mu)))
         # per-trajectory phase of the synthetic LTV system (config 4); unused by the pendulum models
         self._phi = None
         if phi is not None:
@@ -179,6 +189,14 @@ class iLQR:
     def status(self):
         """per-trajectory exit status code (0 converged, 1 line search failed, 2 maxiter)"""
         v = self._status if self.batched else self._status[0]
+        return v if self._torch_out else v.cpu().numpy()
+
+    @property
+    def mu(self):
+        """per-trajectory regularisation after the last solve (None unless reg_factor > 1)"""
+        if self._mu is None:
+            return None
+        v = self._mu if self.batched else self._mu[0]
         return v if self._torch_out else v.cpu().numpy()
 
     def _scalar(self, t):

@@ -43,11 +43,16 @@ class MyLTVSystem(System):
         return p
 
     @staticmethod
-    def synthetic(dt=0.01, seed=2, dtype="float64"):
-        """The seeded config-4 instance: spectral radius of Ac and E scaled to 1, Q = I, R = 0.1 I, Q_f = 10 I."""
+    def synthetic(dt=0.01, seed=2, dtype="float64", shift=1.0):
+        """The seeded config-4 instance: Ac = G / rho(G) - shift * I and E = H / rho(H) with G, H standard normal,
+        Q = I, R = 0.1 I, Q_f = 10 I.  shift = 1 makes Ac Hurwitz.  With an open-loop unstable Ac (shift = 0) the
+        reference's backward recursion -- V_xx = Q_xx + Q_ux' K, neither symmetrised nor regularised
+        (iLQR_class.py:113-114) -- is itself numerically unstable over N = 1000 steps: the CPU oracle and the
+        GPU both end in NaN gains for part of the batch, so the full-size configuration uses the stable system."""
         rng = np.random.default_rng(seed)
         Ac = rng.standard_normal((12, 12))
         Ac *= 1.0 / max(abs(np.linalg.eigvals(Ac)))
+        Ac = Ac - shift * np.eye(12)
         E = rng.standard_normal((12, 12))
         E *= 1.0 / max(abs(np.linalg.eigvals(E)))
         Bc = rng.standard_normal((12, 4))

@@ -75,7 +75,8 @@ class System(ABC):
         return self.Q, self.R, self.Q_f, self.x_target
 
     # ---- problem struct ---------------------------------------------------------------
-    def make_problem(self, N, B, tol=1e-5, maxiter=100, alpha_factor=0.5, min_alpha=1e-8, n_alpha=10):
+    def make_problem(self, N, B, tol=1e-5, maxiter=100, alpha_factor=0.5, min_alpha=1e-8, n_alpha=10,
+                     reg_init=0.0, reg_factor=0.0, reg_min=1e-6, reg_max=1e10):
         model, phys = self._device_model()
         n, m = self.n_x, self.n_u
         Q, R, Q_f, x_t = self._cost_weights()
@@ -92,6 +93,7 @@ class System(ABC):
         if xt.shape != (n,):
             raise ValueError(f"x_target must have shape {(n,)}, but got {xt.shape}")
         _cabi.fill(p.x_target, xt)
+        p.reg_init, p.reg_factor, p.reg_min, p.reg_max = float(reg_init), float(reg_factor), float(reg_min), float(reg_max)
         return p
 
     # ---- point evaluations ------------------------------------------------------------

@@ -51,6 +51,38 @@ struct SpecArgs {
     int *mark;                            // [B]: mark[b] == it + 1 <=> b is on the list of iteration it
 };
 
+// Levenberg-Marquardt regularisation of Q_uu, kept per trajectory on the device (an EXTENSION: the
+// reference has none, iLQR_class.py:109-110, and with factor <= 1 nothing here changes its behaviour).
+// The backward pass solves with Q_uu + mu I.  When the line search of an iteration accepts no step size,
+// the reference stops the solve (:304-307); with the schedule enabled the trajectory instead retries the
+// iteration with mu <- max(mu * factor, mu_min), and fails only once mu exceeds mu_max.  After an accepted
+// step mu <- mu / factor (snapped to 0 below mu_min).  All of it runs in the select kernels.
+struct RegArgs {
+    void *mu;                 // [B], T; nullptr <=> schedule disabled
+    double factor, mu_min, mu_max;
+};
+
+template <typename T>
+ILQR_DEV bool reg_on_failure(const RegArgs &rg, int b)
+{
+    // true: retry with a larger mu; false: give up (reference behaviour)
+    if (!rg.mu) return false;
+    T *mu = (T *)rg.mu;
+    const T next = mu[b] * (T)rg.factor > (T)rg.mu_min ? mu[b] * (T)rg.factor : (T)rg.mu_min;
+    if (next > (T)rg.mu_max) return false;
+    mu[b] = next;
+    return true;
+}
+
+template <typename T>
+ILQR_DEV void reg_on_success(const RegArgs &rg, int b)
+{
+    if (!rg.mu) return;
+    T *mu = (T *)rg.mu;
+    const T next = mu[b] / (T)rg.factor;
+    mu[b] = next < (T)rg.mu_min ? T(0) : next;
+}
+
 template <class Sys, int INTEG, typename T>
 __global__ void step_kernel(const __grid_constant__ Sys sys, T dt, int B, int t, const T *__restrict__ phi,
                             const T *__restrict__ x, const T *__restrict__ u, T *__restrict__ xn)
@@ -179,7 +211,7 @@ template <typename T, int n, int m, int DEPTH>
 __global__ void backward_kernel(const __grid_constant__ QuadCost<T, n, m> qc, int N, int B, const T *__restrict__ X,
                                 const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
                                 T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
-                                const unsigned int *__restrict__ gate)
+                                const unsigned int *__restrict__ gate, const T *__restrict__ mu)
 {
     constexpr int L = n * n + n * m + n + m;
     extern __shared__ __align__(16) unsigned char ring_raw[];
@@ -194,6 +226,7 @@ __global__ void backward_kernel(const __grid_constant__ QuadCost<T, n, m> qc, in
         if (N - 1 - s >= 0) bwd_issue<T, n, m>(ring + s * stage_elems, N - 1 - s, b, B, X, U, A, Bd);
         cp_async_commit();
     }
+    const T mu_b = mu ? mu[b] : T(0);                                    // regularisation (RegArgs), 0 in the reference
     T Vx[n], Vxx[n][n];
     {
         T xN[n];
@@ -272,6 +305,7 @@ __global__ void backward_kernel(const __grid_constant__ QuadCost<T, n, m> qc, in
 #pragma unroll
                 for (int l = 0; l < n; ++l) s += T2[i][l] * cur.Bd[l][j];
                 Quu[i][j] = qc.Rs[i][j] * qc.dt + s;
+                if (i == j) Quu[i][j] += mu_b;
             }
         }
         // K = -Q_uu^-1 Q_ux, k = -Q_uu^-1 Q_u                            (:109-110; no regularisation)
@@ -343,7 +377,7 @@ __global__ void __launch_bounds__(32)
 backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, int B, const T *__restrict__ X,
                            const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
                            T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
-                           const unsigned int *__restrict__ gate)
+                           const unsigned int *__restrict__ gate, const T *__restrict__ mu)
 {
     constexpr int n = 4, L = 25, LP = 26, SLOTS = 8;       // LP: padded slot stride (bank-conflict free LDS.128)
     extern __shared__ __align__(16) unsigned char lanes_raw[];
@@ -384,6 +418,7 @@ backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, 
     for (int i = 0; i < n; ++i) { qrow[i] = qc.Qs[j][i] * qc.dt; qcol[i] = qc.Qs[i][j] * qc.dt; }
     const T xtj[n] = { qc.xt[0], qc.xt[1], qc.xt[2], qc.xt[3] };
     const T luu = qc.Rs[0][0] * qc.dt;
+    const T mu_b = mu ? mu[b] : T(0);                                    // regularisation (RegArgs), 0 in the reference
     T Vx[n], Vxx[n][n];
     {
         T xN[n];
@@ -438,6 +473,7 @@ backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, 
             Qxj += Acol[i] * Vx[i];
         }
         Quu += luu;
+        Quu += mu_b;
         Qu += luu * u;
         T lxj = T(0);
 #pragma unroll
@@ -496,7 +532,8 @@ template <typename T, int TPB>
 __global__ void __launch_bounds__(TPB * 16, ILQR_LTV_MINBLOCKS)
 backward_ltv_kernel(const __grid_constant__ LtvSys<T> sys, const __grid_constant__ QuadCost<T, 12, 4> qc, int N, int B,
                     const T *__restrict__ phi, const T *__restrict__ X, const T *__restrict__ U, T *__restrict__ K,
-                    T *__restrict__ k, const int *__restrict__ active, const unsigned int *__restrict__ gate)
+                    T *__restrict__ k, const int *__restrict__ active, const unsigned int *__restrict__ gate,
+                    const T *__restrict__ mu)
 {
     constexpr int n = 12, m = 4, NT = TPB * 16, ROWS = n * m + m;   // 52 gain rows per step
     using V2 = typename Vec2<T>::type;
@@ -543,6 +580,7 @@ backward_ltv_kernel(const __grid_constant__ LtvSys<T> sys, const __grid_constant
 #pragma unroll
     for (int l = 0; l < n; ++l) M[l] = c < n ? T(0) : qc.dt * sys.Bc[l][c - n];
     const T ph = phi ? phi[b] : T(0);
+    const T mu_b = mu ? mu[b] : T(0);                                    // regularisation (RegArgs), 0 in the reference
     T w = sys.time_scalar(N - 1, ph);
     T *Vxx = VxxS + s * 144, *AT = ATS + s * 144, *Vx = VxS + s * 12, *Qux = QuxS + s * 48, *Quu = QuuS + s * 16,
       *Qu = QuS + s * 4;
@@ -631,7 +669,8 @@ backward_ltv_kernel(const __grid_constant__ LtvSys<T> sys, const __grid_constant
             Qc = g * qc.dt + q;                                          // Q_u[c-12]
             Qu[jj] = Qc;
 #pragma unroll
-            for (int i = 0; i < m; ++i) Quu[i * 4 + jj] = RsS[i * 4 + jj] * qc.dt + G[n + i];    // Q_uu[:,c-12]
+            for (int i = 0; i < m; ++i)
+                Quu[i * 4 + jj] = (RsS[i * 4 + jj] * qc.dt + G[n + i]) + (i == jj ? mu_b : T(0));            // Q_uu[:,c-12]
         }
         __syncwarp();
         // K[:,c] = -Q_uu^-1 Q_ux[:,c] (c < 12) ; k = -Q_uu^-1 Q_u (lanes 12..15, lane 12+j keeps k[j])
@@ -859,7 +898,7 @@ __global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys s
 template <typename T>
 __global__ void init_kernel(int B, const T *__restrict__ cost_alpha, T *__restrict__ cost, int *__restrict__ winner,
                             int *__restrict__ active, int *__restrict__ iters, int *__restrict__ status, int maxiter,
-                            Control *ctl, T *__restrict__ tr_cost)
+                            Control *ctl, T *__restrict__ tr_cost, T *__restrict__ mu, T mu_init)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0) ctl->n_active[0] = maxiter > 0 ? (unsigned)B : 0u;
@@ -870,6 +909,7 @@ __global__ void init_kernel(int B, const T *__restrict__ cost_alpha, T *__restri
     active[b] = maxiter > 0;
     iters[b] = 0;
     status[b] = maxiter > 0 ? ILQR_ST_RUNNING : ILQR_ST_MAXITER;
+    if (mu) mu[b] = mu_init;
 }
 
 // K4.  iLQR_class.py:265-271 (convergence), :281-307 (first acceptable alpha, failure => stop)
@@ -884,7 +924,8 @@ __global__ void select_kernel(int B, int a_lo, int a_hi, int wave, const T *__re
                               T *__restrict__ cost, int *__restrict__ winner, int *__restrict__ active,
                               int *__restrict__ defer, int *__restrict__ iters, int *__restrict__ status, T tol,
                               int it, int maxiter, Control *ctl, unsigned int *n2_count,
-                              int *__restrict__ tr_alpha, T *__restrict__ tr_cost, const __grid_constant__ SpecArgs sp)
+                              int *__restrict__ tr_alpha, T *__restrict__ tr_cost, const __grid_constant__ SpecArgs sp,
+                              const __grid_constant__ RegArgs rg)
 {
     if (ctl->n_active[it] == 0u) return;
     if (wave == 1 && *n2_count == 0u) return;
@@ -916,10 +957,16 @@ __global__ void select_kernel(int B, int a_lo, int a_hi, int wave, const T *__re
                 if (tr_alpha) tr_alpha[(size_t)it * B + b] = w;
                 if (tr_cost) tr_cost[(size_t)(it + 1) * B + b] = cw;
                 if (w < 0) {
-                    status[b] = ILQR_ST_LS_FAILED;
-                    active[b] = 0;
+                    if (reg_on_failure<T>(rg, b)) {                      // retry this iteration with a larger mu
+                        if (it + 1 >= maxiter) { status[b] = ILQR_ST_MAXITER; active[b] = 0; }
+                        else still = true;
+                    } else {
+                        status[b] = ILQR_ST_LS_FAILED;
+                        active[b] = 0;
+                    }
                 } else {
                     cost[b] = cw;
+                    reg_on_success<T>(rg, b);
                     if (it + 1 >= maxiter) { status[b] = ILQR_ST_MAXITER; active[b] = 0; }
                     else if (abs_t(cw - c0) <= tol) { status[b] = ILQR_ST_CONVERGED; active[b] = 0; }
                     else still = true;
@@ -952,7 +999,7 @@ __global__ void select_lazy_kernel(int B, int a_lo, int a_hi, int wave, int last
                                    int *__restrict__ iters, int *__restrict__ status, T tol, int it, int maxiter,
                                    Control *ctl, const int *__restrict__ list_in, const unsigned int *cnt_in,
                                    int *__restrict__ list_out, unsigned int *cnt_out, int *__restrict__ wslot,
-                                   int *__restrict__ tr_alpha, T *__restrict__ tr_cost)
+                                   int *__restrict__ tr_alpha, T *__restrict__ tr_cost, const __grid_constant__ RegArgs rg)
 {
     if (ctl->n_active[it] == 0u) return;
     if (wave > 0 && *cnt_in == 0u) return;
@@ -986,10 +1033,16 @@ __global__ void select_lazy_kernel(int B, int a_lo, int a_hi, int wave, int last
             if (tr_alpha) tr_alpha[(size_t)it * B + b] = w;
             if (tr_cost) tr_cost[(size_t)(it + 1) * B + b] = cw;
             if (w < 0) {
-                status[b] = ILQR_ST_LS_FAILED;
-                active[b] = 0;
+                if (reg_on_failure<T>(rg, b)) {                          // retry this iteration with a larger mu
+                    if (it + 1 >= maxiter) { status[b] = ILQR_ST_MAXITER; active[b] = 0; }
+                    else still = true;
+                } else {
+                    status[b] = ILQR_ST_LS_FAILED;
+                    active[b] = 0;
+                }
             } else {
                 cost[b] = cw;
+                reg_on_success<T>(rg, b);
                 if (it + 1 >= maxiter) { status[b] = ILQR_ST_MAXITER; active[b] = 0; }
                 else if (abs_t(cw - c0) <= tol) { status[b] = ILQR_ST_CONVERGED; active[b] = 0; }
                 else still = true;
@@ -1167,6 +1220,7 @@ struct Handle {
     int n_alpha_eff;          // tries actually made: stops once alpha < min_alpha (iLQR_class.py:300-302)
     int n_first;              // step sizes rolled out eagerly (first wave); the rest only where needed
     int spec_cap;             // trajectories whose deferred step sizes ride along speculatively (SpecArgs)
+    void *mu_user;            // optional caller buffer for the per-trajectory regularisation (ilqr_set_mu_buffer)
     int lazy;                 // large batches: lazy multi-wave line search over compacted lists (select_lazy_kernel)
     int n_waves;
     int wave_lo[ILQR_MAX_WAVES + 1];
@@ -1196,7 +1250,7 @@ static inline int block_for(size_t threads)
 }
 
 struct WsLayout {
-    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, wslot, active, defer, mark, lists, total;
+    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, wslot, active, defer, mark, lists, mu, total;
 };
 
 static size_t ctl_bytes(int maxiter)
@@ -1228,6 +1282,7 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
     L.defer = off; off = al(off + 4 * B);
     L.mark = off; off = al(off + 4 * B);
     L.lists = off; off = al(off + 4 * 2 * B);     // two speculation lists (capacity <= B each)
+    L.mu = off; off = al(off + w * B);
     L.total = off;
     return L;
 }
@@ -1296,7 +1351,7 @@ static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U,
 template <typename T, int n, int m, int DEPTH>
 static int launch_backward_depth(Handle *h, int bs, const QuadCost<T, n, m> &qc, const void *X, const void *U,
                                  const void *A, const void *Bd, void *K, void *k, const int *active,
-                                 const unsigned int *gate, cudaStream_t st)
+                                 const unsigned int *gate, const void *mu, cudaStream_t st)
 {
     constexpr int L = n * n + n * m + n + m;
     const size_t smem = (size_t)DEPTH * L * bs * sizeof(T);
@@ -1308,13 +1363,14 @@ static int launch_backward_depth(Handle *h, int bs, const QuadCost<T, n, m> &qc,
         configured = smem;
     }
     backward_kernel<T, n, m, DEPTH><<<grid_for(h->p.B, bs), bs, smem, st>>>(
-        qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active, gate);
+        qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active, gate,
+        (const T *)mu);
     ILQR_CHECK_LAUNCH(h);
     return ILQR_OK;
 }
 
 static int launch_backward(Handle *h, const void *X, const void *U, const void *A, const void *Bd, void *K, void *k,
-                           const int *active, const unsigned int *gate, cudaStream_t st)
+                           const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr)
 {
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto) -> int {
         using T = decltype(tz);
@@ -1330,25 +1386,25 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
                 const size_t smem = sizeof(T) * (size_t)(DEPTH * SLOTS * LP + SLOTS * 4 + SLOTS * 20);
                 backward_n4m1_lanes_kernel<T, DEPTH><<<grid_for(h->p.B, SLOTS), 32, smem, st>>>(
                     qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active,
-                    gate);
+                    gate, (const T *)mu);
                 ILQR_CHECK_LAUNCH(h);
                 return ILQR_OK;
             }
         }
         if constexpr (Sys::N > 4) {
             // n = 12, m = 4: a ring stage is 208 rows; two stages of one warp fit the 227 KB limit
-            return launch_backward_depth<T, Sys::N, Sys::M, 2>(h, 32, qc, X, U, A, Bd, K, k, active, gate, st);
+            return launch_backward_depth<T, Sys::N, Sys::M, 2>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st);
         } else {
             if (h->p.B <= 32768)
-                return launch_backward_depth<T, Sys::N, Sys::M, 8>(h, 32, qc, X, U, A, Bd, K, k, active, gate, st);
-            return launch_backward_depth<T, Sys::N, Sys::M, 4>(h, 64, qc, X, U, A, Bd, K, k, active, gate, st);
+                return launch_backward_depth<T, Sys::N, Sys::M, 8>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st);
+            return launch_backward_depth<T, Sys::N, Sys::M, 4>(h, 64, qc, X, U, A, Bd, K, k, active, gate, mu, st);
         }
     });
 }
 
 // K2 of the LTV model: A_t, B_t generated in the kernel (no linearization buffers)
 static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const void *U, void *K, void *k,
-                               const int *active, const unsigned int *gate, cudaStream_t st)
+                               const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr)
 {
     constexpr int TPB = 16;
     auto go = [&](auto tz) -> int {
@@ -1363,7 +1419,7 @@ static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const 
         }
         backward_ltv_kernel<T, TPB><<<grid_for(h->p.B, TPB), TPB * 16, smem, st>>>(
             make_ltv<T>(h->p), make_cost<T, 12, 4>(h->p), h->p.N, h->p.B, (const T *)phi, (const T *)X, (const T *)U,
-            (T *)K, (T *)k, active, gate);
+            (T *)K, (T *)k, active, gate, (const T *)mu);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     };
@@ -1399,36 +1455,37 @@ static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const voi
 
 static int launch_select(Handle *h, int a_lo, int a_hi, int wave, const void *ca, void *cost, int *winner, int *active,
                          int *defer, int *iters, int *status, int it, Control *ctl, unsigned int *n2c, const SpecArgs &sp,
-                         cudaStream_t st)
+                         const RegArgs &rg, cudaStream_t st)
 {
     const int B = h->p.B, bs = 128;
     if (h->p.dtype == ILQR_F64)
         select_kernel<double><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, (const double *)ca, (double *)cost, winner,
                                                               active, defer, iters, status, h->p.tol, it, h->p.maxiter, ctl,
-                                                              n2c, h->tr_alpha, (double *)h->tr_cost, sp);
+                                                              n2c, h->tr_alpha, (double *)h->tr_cost, sp, rg);
     else
         select_kernel<float><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, (const float *)ca, (float *)cost, winner,
                                                              active, defer, iters, status, (float)h->p.tol, it, h->p.maxiter,
-                                                             ctl, n2c, h->tr_alpha, (float *)h->tr_cost, sp);
+                                                             ctl, n2c, h->tr_alpha, (float *)h->tr_cost, sp, rg);
     ILQR_CHECK_LAUNCH(h);
     return ILQR_OK;
 }
 
 static int launch_select_lazy(Handle *h, int a_lo, int a_hi, int wave, int last, const void *ca, void *cost, int *winner,
                               int *active, int *iters, int *status, int it, Control *ctl, const int *list_in,
-                              const unsigned int *cnt_in, int *list_out, unsigned int *cnt_out, int *wslot, cudaStream_t st)
+                              const unsigned int *cnt_in, int *list_out, unsigned int *cnt_out, int *wslot, const RegArgs &rg,
+                              cudaStream_t st)
 {
     const int B = h->p.B, bs = 128;
     if (h->p.dtype == ILQR_F64)
         select_lazy_kernel<double><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, last, (const double *)ca,
                                                                    (double *)cost, winner, active, iters, status, h->p.tol,
                                                                    it, h->p.maxiter, ctl, list_in, cnt_in, list_out, cnt_out,
-                                                                   wslot, h->tr_alpha, (double *)h->tr_cost);
+                                                                   wslot, h->tr_alpha, (double *)h->tr_cost, rg);
     else
         select_lazy_kernel<float><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, last, (const float *)ca,
                                                                   (float *)cost, winner, active, iters, status,
                                                                   (float)h->p.tol, it, h->p.maxiter, ctl, list_in, cnt_in,
-                                                                  list_out, cnt_out, wslot, h->tr_alpha, (float *)h->tr_cost);
+                                                                  list_out, cnt_out, wslot, h->tr_alpha, (float *)h->tr_cost, rg);
     ILQR_CHECK_LAUNCH(h);
     return ILQR_OK;
 }
@@ -1574,6 +1631,7 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
     if (p->n != n || p->m != m) return ILQR_E_INVALID;
     if (p->N < 1 || p->B < 1 || p->n_alpha < 1 || p->n_alpha > ILQR_MAX_ALPHAS || p->maxiter < 0) return ILQR_E_INVALID;
     if (!(p->dt > 0.0)) return ILQR_E_INVALID;
+    if (p->reg_factor > 1.0 && !(p->reg_init >= 0.0 && p->reg_min > 0.0 && p->reg_max >= p->reg_min)) return ILQR_E_INVALID;
     Handle *h = new (std::nothrow) Handle;
     if (!h) return ILQR_E_INVALID;
     std::memset(h, 0, sizeof(Handle));
@@ -1748,6 +1806,14 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     int *winner = (int *)(w + L.winner), *active = (int *)(w + L.active), *defer = (int *)(w + L.defer);
     int *mark = (int *)(w + L.mark), *lists = (int *)(w + L.lists);
     int *wslot = h->lazy ? (int *)(w + L.wslot) : nullptr;      // only the lazy schedule stores candidates by list position
+    RegArgs rg;
+    std::memset(&rg, 0, sizeof rg);
+    if (p.reg_factor > 1.0) {
+        rg.mu = h->mu_user ? h->mu_user : (void *)(w + L.mu);
+        rg.factor = p.reg_factor;
+        rg.mu_min = p.reg_min;
+        rg.mu_max = p.reg_max;
+    }
     const int B = p.B, bsB = 128;
     int rc;
     // two-wave line search (see select_kernel): n1 eager step sizes, n2 deferred ones
@@ -1770,10 +1836,12 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     prof_mark(h, ILQR_KC_INIT_ROLLOUT, st);
     if (p.dtype == ILQR_F64)
         init_kernel<double><<<grid_for(B, bsB), bsB, 0, st>>>(B, (const double *)ca, (double *)cost, winner, active,
-                                                                iters, status, p.maxiter, ctl, (double *)h->tr_cost);
+                                                                iters, status, p.maxiter, ctl, (double *)h->tr_cost,
+                                                                (double *)rg.mu, p.reg_init);
     else
         init_kernel<float><<<grid_for(B, bsB), bsB, 0, st>>>(B, (const float *)ca, (float *)cost, winner, active, iters,
-                                                               status, p.maxiter, ctl, (float *)h->tr_cost);
+                                                               status, p.maxiter, ctl, (float *)h->tr_cost, (float *)rg.mu,
+                                                               (float)p.reg_init);
     ILQR_CHECK_LAUNCH(h);
     // iterations are enqueued in blocks of CHK; the active count after each block is copied to pinned
     // memory and inspected one block later, so the device never idles waiting for the host.
@@ -1792,8 +1860,8 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
             if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, it > 0 ? wslot : nullptr, active,
                                               ltv ? 0 : 1, g, gprev, st))) return rc;
             prof_mark(h, ILQR_KC_LINEARIZE, st);
-            if ((rc = ltv ? launch_backward_ltv(h, phi, X, U, K, k, active, g, st)
-                          : launch_backward(h, X, U, A, Bd, K, k, active, g, st))) return rc;
+            if ((rc = ltv ? launch_backward_ltv(h, phi, X, U, K, k, active, g, st, rg.mu)
+                          : launch_backward(h, X, U, A, Bd, K, k, active, g, st, rg.mu))) return rc;
             prof_mark(h, ILQR_KC_BACKWARD, st);
             if (h->lazy) {
                 // lazy line search: wave v rolls out step sizes [wave_lo[v], wave_lo[v+1]) for the trajectories
@@ -1813,7 +1881,7 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
                                              v ? nullptr : active, v ? cin : g, nullptr, st, nullptr, lin, cin))) return rc;
                     prof_mark(h, ILQR_KC_ROLLOUT, st);
                     if ((rc = launch_select_lazy(h, lo, hi, v, v == h->n_waves - 1, ca, cost, winner, active, iters, status,
-                                                 it, ctl, lin, cin, lout, wcnt + v, wslot, st))) return rc;
+                                                 it, ctl, lin, cin, lout, wcnt + v, wslot, rg, st))) return rc;
                 }
                 continue;
             }
@@ -1835,13 +1903,13 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
             if ((rc = launch_rollout(h, n1, h->alphas, phi, x0, X, U, k, K, Xc, Uc, ca, active, g, nullptr, st, &sp))) return rc;
             prof_mark(h, ILQR_KC_ROLLOUT, st);
             unsigned int *n2c = &ctl->n_active[p.maxiter + 2 + it];
-            if ((rc = launch_select(h, 0, n1, 0, ca, cost, winner, active, n2 > 0 ? defer : nullptr, iters, status, it, ctl, n2c, sp, st))) return rc;
+            if ((rc = launch_select(h, 0, n1, 0, ca, cost, winner, active, n2 > 0 ? defer : nullptr, iters, status, it, ctl, n2c, sp, rg, st))) return rc;
             if (n2 > 0) {
                 // wave 2: the remaining step sizes, only for trajectories that accepted none so far; both
                 // launches return at once while the deferred counter of this iteration is zero
                 if ((rc = launch_rollout(h, n2, al2, phi, x0, X, U, k, K, (char *)Xc + xc_slab * n1, (char *)Uc + uc_slab * n1,
                                          (char *)ca + wbytes * (size_t)n1 * B, defer, n2c, nullptr, st))) return rc;
-                if ((rc = launch_select(h, n1, n1 + n2, 1, ca, cost, winner, active, defer, iters, status, it, ctl, n2c, sp, st))) return rc;
+                if ((rc = launch_select(h, n1, n1 + n2, 1, ca, cost, winner, active, defer, iters, status, it, ctl, n2c, sp, rg, st))) return rc;
             }
         }
         if (pending >= 0) {
@@ -1874,6 +1942,14 @@ int ilqr_set_linesearch_waves(ilqr_handle_t hh, int n_waves, const int32_t *size
     Handle *h = (Handle *)hh;
     if (!h || n_waves < 0 || n_waves > ILQR_MAX_WAVES || (n_waves > 0 && !sizes)) return ILQR_E_INVALID;
     set_waves(h, n_waves, sizes);
+    return ILQR_OK;
+}
+
+int ilqr_set_mu_buffer(ilqr_handle_t hh, void *mu)
+{
+    Handle *h = (Handle *)hh;
+    if (!h) return ILQR_E_INVALID;
+    h->mu_user = mu;
     return ILQR_OK;
 }
 

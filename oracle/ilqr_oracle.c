@@ -422,6 +422,12 @@ void orc_lf_derivs(const orc_problem *p, const double *x, double *lfx, double *l
 /* iLQR_class.py:79-119 (body), :122-161 (scan, reverse) */
 void orc_backward_pass(const orc_problem *p, double phi, const double *X, const double *U, double *U_ff, double *K)
 {
+    orc_backward_pass_mu(p, phi, 0.0, X, U, U_ff, K);
+}
+
+void orc_backward_pass_mu(const orc_problem *p, double phi, double mu, const double *X, const double *U, double *U_ff,
+                          double *K)
+{
     const int n = p->n, m = p->m, N = p->N;
     double Vx[NX], Vxx[NX * NX], x[NX], u[MX];
     for (int i = 0; i < n; ++i) x[i] = X[i * (N + 1) + N];
@@ -445,6 +451,7 @@ void orc_backward_pass(const orc_problem *p, double phi, const double *X, const 
         for (int i = 0; i < m * n; ++i) Qux[i] = lux[i] + Qux[i];
         matmul(m, n, m, T2, fu, Quu);                                    /* :104 */
         for (int i = 0; i < m * m; ++i) Quu[i] = luu[i] + Quu[i];
+        for (int j = 0; j < m; ++j) Quu[j * m + j] += mu;                /* extension; mu = 0 in the reference */
         /* :109-110  K = -solve(Q_uu, Q_ux), k = -solve(Q_uu, Q_u); LU, no regularisation */
         double lu_m[MX * MX], rhs[MX * (NX + 1)];
         int piv[MX];
@@ -511,6 +518,19 @@ double orc_optimize(const orc_problem *p, double phi, const double *x0,
                     int *iters, int *status, double *cost0,
                     int *trace_alpha_idx, double *trace_cost)
 {
+    return orc_optimize_ex(p, phi, x0, X, U, K, U_ff, iters, status, cost0, trace_alpha_idx, trace_cost, NULL);
+}
+
+/* The regularisation branches (reg != 0) restate the schedule documented in include/ilqr_b200.h; with
+ * reg_factor <= 1 this is the reference loop line by line. */
+double orc_optimize_ex(const orc_problem *p, double phi, const double *x0,
+                       double *X, double *U, double *K, double *U_ff,
+                       int *iters, int *status, double *cost0,
+                       int *trace_alpha_idx, double *trace_cost, double *mu_out)
+{
+    const int reg = p->reg_factor > 1.0;
+    double mu = reg ? p->reg_init : 0.0;
+    int retry = 0;
     const int n = p->n, m = p->m, N = p->N;
     const size_t sx = (size_t)n * (N + 1), su = (size_t)m * N;
     double *Xn = (double *)malloc(sizeof(double) * (sx + su));
@@ -523,9 +543,9 @@ double orc_optimize(const orc_problem *p, double phi, const double *x0,
     double cost_prev = cost;
     int it = 0, st = ORC_MAXITER;
     for (int i = 0; i < p->maxiter; ++i) {
-        if (i > 0 && fabs(cost - cost_prev) <= p->tol) { st = ORC_CONVERGED; break; }       /* :267 */
+        if (i > 0 && !retry && fabs(cost - cost_prev) <= p->tol) { st = ORC_CONVERGED; break; }       /* :267 */
         cost_prev = cost;
-        orc_backward_pass(p, phi, X, U, U_ff, K);                                            /* :275 */
+        orc_backward_pass_mu(p, phi, mu, X, U, U_ff, K);                                     /* :275 */
         ++it;
         double alpha = 1.0;
         int accepted = -1;
@@ -543,11 +563,20 @@ double orc_optimize(const orc_problem *p, double phi, const double *x0,
         }
         if (trace_alpha_idx) trace_alpha_idx[i] = accepted;
         if (trace_cost) trace_cost[i] = cost;
-        if (accepted < 0) { st = ORC_LS_FAILED; break; }                                     /* :304-307 */
+        if (accepted < 0) {
+            double next = mu * p->reg_factor > p->reg_min ? mu * p->reg_factor : p->reg_min;
+            if (!reg || next > p->reg_max) { st = ORC_LS_FAILED; break; }                    /* :304-307 */
+            mu = next;                                                                       /* retry the iteration */
+            retry = 1;
+        } else {
+            retry = 0;
+            if (reg) { mu = mu / p->reg_factor; if (mu < p->reg_min) mu = 0.0; }
+        }
     }
     free(Xn);
     *iters = it;
     *status = st;
+    if (mu_out) *mu_out = mu;
     return cost;
 }
 

@@ -40,6 +40,9 @@ typedef struct {
     /* synthetic LTV (BASELINE config 4): x+ = x + dt*((Ac + amp*sin(2*pi*t/N + phi)*E) x + Bc u) */
     double Ac[ORC_NMAX * ORC_NMAX], E[ORC_NMAX * ORC_NMAX], Bc[ORC_NMAX * ORC_MMAX];
     double ltv_amp;
+    /* EXTENSION restated from include/ilqr_b200.h (the reference has no regularisation): Levenberg-Marquardt
+     * schedule of Q_uu + mu I; reg_factor <= 1 disables it. */
+    double reg_init, reg_factor, reg_min, reg_max;
 } orc_problem;
 
 /* point functions; t and phi only matter for ORC_LTV */
@@ -58,6 +61,9 @@ void orc_lf_derivs(const orc_problem *p, const double *x, double *lfx, double *l
 /* X (n,N+1), U (m,N), U_ff (m,N) row-major (dim,time); K (N,m,n) */
 void orc_backward_pass(const orc_problem *p, double phi, const double *X, const double *U,
                        double *U_ff, double *K);
+/* same with Q_uu + mu I (extension; mu = 0 is the reference) */
+void orc_backward_pass_mu(const orc_problem *p, double phi, double mu, const double *X, const double *U,
+                          double *U_ff, double *K);
 double orc_forward_pass(const orc_problem *p, double phi, const double *x0, double alpha,
                         const double *X_old, const double *U_old, const double *U_ff,
                         const double *K, double *X_new, double *U_new);
@@ -69,6 +75,12 @@ double orc_optimize(const orc_problem *p, double phi, const double *x0,
                     double *X, double *U, double *K, double *U_ff,
                     int *iters, int *status, double *cost0,
                     int *trace_alpha_idx, double *trace_cost);
+
+/* orc_optimize with the regularisation state returned: *mu_out = mu after the last iteration */
+double orc_optimize_ex(const orc_problem *p, double phi, const double *x0,
+                       double *X, double *U, double *K, double *U_ff,
+                       int *iters, int *status, double *cost0,
+                       int *trace_alpha_idx, double *trace_cost, double *mu_out);
 
 /* B independent solves in batch-major layout (X[b] is (n,N+1) etc.), fresh solver state
  * (X=K=U_ff=0) per trajectory, fanned out over nthreads POSIX threads. */

@@ -31,6 +31,7 @@ class Problem(C.Structure):
         ("Qf", C.c_double * (NMAX * NMAX)), ("x_target", C.c_double * NMAX),
         ("Ac", C.c_double * (NMAX * NMAX)), ("E", C.c_double * (NMAX * NMAX)),
         ("Bc", C.c_double * (NMAX * MMAX)), ("ltv_amp", C.c_double),
+        ("reg_init", C.c_double), ("reg_factor", C.c_double), ("reg_min", C.c_double), ("reg_max", C.c_double),
     ]
 
 
@@ -85,6 +86,9 @@ def lib():
         L.orc_forward_pass.restype = C.c_double
         L.orc_optimize.argtypes = [P, C.c_double, D, D, D, D, D, I, I, D, I, D]
         L.orc_optimize.restype = C.c_double
+        L.orc_optimize_ex.argtypes = [P, C.c_double, D, D, D, D, D, I, I, D, I, D, D]
+        L.orc_optimize_ex.restype = C.c_double
+        L.orc_backward_pass_mu.argtypes = [P, C.c_double, C.c_double, D, D, D, D]
         L.orc_optimize_batch.argtypes = [P, C.c_int, D, D, D, D, D, D, D, D, I, I, C.c_int]
         L.orc_mpc.argtypes = [P, P, C.c_double, D, C.c_int, D, D, D, I, D, D, D, D, D, D]
         L.orc_max_threads.restype = C.c_int
@@ -118,7 +122,8 @@ def horizon(T, dt):
 
 
 def make_problem(kind, integrator, N, dt, Q, R, Q_f, x_target, phys=None, tol=1e-5, maxiter=100,
-                 alpha_factor=0.5, min_alpha=1e-8, n_alpha=10, ltv=None):
+                 alpha_factor=0.5, min_alpha=1e-8, n_alpha=10, ltv=None, reg_init=0.0, reg_factor=0.0, reg_min=1e-6,
+                 reg_max=1e10):
     """kind in MODELS; phys = dict of the system's physical parameters; Q/R/Q_f diag vectors or full."""
     p = Problem()
     if kind == "ltv":
@@ -128,6 +133,7 @@ def make_problem(kind, integrator, N, dt, Q, R, Q_f, x_target, phys=None, tol=1e
     p.model, p.integrator, p.n, p.m, p.N = MODELS[kind], INTEGRATORS[integrator], n, m, int(N)
     p.n_alpha, p.maxiter = int(n_alpha), int(maxiter)
     p.dt, p.tol, p.alpha_factor, p.min_alpha = float(dt), float(tol), float(alpha_factor), float(min_alpha)
+    p.reg_init, p.reg_factor, p.reg_min, p.reg_max = float(reg_init), float(reg_factor), float(reg_min), float(reg_max)
     phys = dict(phys or {})
     if kind == "pendulum":
         vals = [phys.get("g", 9.81), phys.get("l", 1.0), phys.get("d", 0.01)]
@@ -240,9 +246,10 @@ def optimize(p, x0, U_init, state=None, phi=0.0):
     cost0 = C.c_double(0.0)
     tr_a = np.full(max(p.maxiter, 1), -2, dtype=np.int32)
     tr_c = np.full(max(p.maxiter, 1), np.nan)
-    cost = lib().orc_optimize(C.byref(p), phi, _d(x0), _d(X), _d(U), _d(K), _d(U_ff), C.byref(iters),
-                              C.byref(status), C.byref(cost0), _i(tr_a), _d(tr_c))
-    return dict(X=X, U=U, K=K, U_ff=U_ff, cost=cost, cost0=cost0.value, iters=iters.value,
+    mu = C.c_double(0.0)
+    cost = lib().orc_optimize_ex(C.byref(p), phi, _d(x0), _d(X), _d(U), _d(K), _d(U_ff), C.byref(iters),
+                                 C.byref(status), C.byref(cost0), _i(tr_a), _d(tr_c), C.byref(mu))
+    return dict(X=X, U=U, K=K, U_ff=U_ff, cost=cost, cost0=cost0.value, iters=iters.value, mu=mu.value,
                 status=STATUS[status.value], alpha_idx=tr_a[: iters.value], cost_trace=tr_c[: iters.value])
 
 

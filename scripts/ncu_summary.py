@@ -28,7 +28,35 @@ KEYS = [
 ]
 
 
+def traffic(rep, key, out):
+    """average dram read+write bytes per launch of each kernel class -> out[key] (JSON, merged)"""
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = {}
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        cls = "rollout" if "rollout" in name else "linearize" if "linearize" in name else "backward" if "backward" in name else None
+        if cls is None:
+            continue
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[idx[k]].replace(",", "")) * scale[units[idx[k]]]
+        acc.setdefault(cls, []).append(tot)
+    d = json.load(open(out)) if os.path.exists(out) else {}
+    d[key] = {c: sum(v) / len(v) for c, v in acc.items()}
+    d[key]["source"] = os.path.basename(rep) + " (ncu --set full, average over the captured launches of each kernel)"
+    json.dump(d, open(out, "w"), indent=1)
+    print(d[key])
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[2] == "--traffic":
+        return traffic(sys.argv[1], sys.argv[3], sys.argv[4])
     rep = sys.argv[1]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))

@@ -77,6 +77,8 @@ def main():
 
 
 def profiled_solves(sol, iters):
+    if os.environ.get("QG_NO_REPS"):
+        return
     for rep in range(4):
         if rep == 3:
             sol.set_profiling(True)

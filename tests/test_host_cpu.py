@@ -32,11 +32,21 @@ def test_library_exports_every_declared_symbol():
     assert lib.ilqr_strerror(-3).decode().startswith("workspace")
 
 
-def test_problem_struct_matches_header_layout():
+def test_problem_struct_matches_header_layout(tmp_path):
+    """sizeof/offsetof of ilqr_problem_t as gcc sees include/ilqr_b200.h == the ctypes mirror"""
+    import subprocess
     from class_files import _cabi
-    # 10 int32 + 4 double + 16 + 144 + 16 + 144 + 12 + 144 + 144 + 48 + 1 doubles
-    assert C.sizeof(_cabi.Problem) == 10 * 4 + 8 * (4 + 16 + 144 + 16 + 144 + 12 + 144 + 144 + 48 + 1)
-    assert _cabi.Problem.dt.offset == 40 and _cabi.Problem.phys.offset == 72
+    fields = [f[0] for f in _cabi.Problem._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ilqr_b200.h"\nint main(void){\n'
+                   'printf("%zu\\n", sizeof(ilqr_problem_t));\n' +
+                   "".join(f'printf("%zu\\n", offsetof(ilqr_problem_t, {f}));\n' for f in fields) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    vals = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert vals[0] == C.sizeof(_cabi.Problem)
+    for f, off in zip(fields, vals[1:]):
+        assert getattr(_cabi.Problem, f).offset == off, f
 
 
 def test_create_rejects_bad_problems_without_touching_cuda():
