@@ -35,7 +35,9 @@ extern "C" {
 #define ILQR_MAX_ALPHAS 16
 #define ILQR_MAX_WAVES 8
 
-enum { ILQR_PENDULUM = 0, ILQR_DOUBLE_PENDULUM = 1, ILQR_UA_DOUBLE_PENDULUM = 2, ILQR_LTV = 3 };
+enum { ILQR_PENDULUM = 0, ILQR_DOUBLE_PENDULUM = 1, ILQR_UA_DOUBLE_PENDULUM = 2, ILQR_LTV = 3,
+       /* a user-defined System subclass: valid only in a library generated for it (class_files/codegen.py) */
+       ILQR_USER = 4 };
 enum { ILQR_EULER = 0, ILQR_MIDPOINT = 1, ILQR_RK4 = 2, ILQR_BACKWARD_EULER = 3 };
 enum { ILQR_F64 = 0, ILQR_F32 = 1 };
 /* per-trajectory exit status written by ilqr_solve (iLQR_class.py:265-311) */

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 NMAX, MMAX, MAX_ALPHAS = 12, 4, 16
-MODELS = {"pendulum": 0, "double_pendulum": 1, "ua_double_pendulum": 2, "ltv": 3}
+MODELS = {"pendulum": 0, "double_pendulum": 1, "ua_double_pendulum": 2, "ltv": 3, "user": 4}
 INTEGRATORS = {"euler": 0, "midpoint": 1, "rk4": 2, "backward_euler": 3}
 DTYPES = {"float64": 0, "float32": 1}
 KERNEL_CLASSES = ("linearize", "backward", "rollout", "init_rollout", "other")

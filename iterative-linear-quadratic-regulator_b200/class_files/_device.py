@@ -89,9 +89,9 @@ def ptr(t):
 class Handle:
     """Owns one ilqr_handle_t (problem constants + launch bookkeeping)."""
 
-    def __init__(self, problem):
+    def __init__(self, problem, lib=None):
         require_cuda()
-        self.lib = _cabi.load()
+        self.lib = lib if lib is not None else _cabi.load()     # lib: the generated library of a user-defined system
         self.problem = problem
         self._h = C.c_void_p()
         rc = self.lib.ilqr_create(C.byref(problem), C.byref(self._h))

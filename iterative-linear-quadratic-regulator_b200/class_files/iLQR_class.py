@@ -70,7 +70,7 @@ class iLQR:
         self._handle = D.Handle(system.make_problem(self.N, self.B, tol=tol, maxiter=maxiter,
                                                     alpha_factor=alpha_factor, min_alpha=min_alpha, n_alpha=n_alpha,
                                                     reg_init=reg_init, reg_factor=reg_factor, reg_min=reg_min,
-                                                    reg_max=reg_max))
+                                                    reg_max=reg_max), lib=system._library())
         n, m, N, B = self.n_x, self.n_u, self.N, self.B
         dev = dict(dtype=self._tdt, device="cuda")
         # device state, batch-innermost (include/ilqr_b200.h)

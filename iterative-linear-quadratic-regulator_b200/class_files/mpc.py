@@ -37,7 +37,7 @@ def run_mpc(ilqr_solver, plant_system, x_0, N_sim, U_init=None, record_plans=Fal
         raise ValueError("plant and optimizer systems must have the same dimensions")
     torch_out = D.is_torch(x_0) and x_0.is_cuda
     tdt = sol._tdt
-    plant = D.Handle(plant_system.make_problem(N=1, B=B))
+    plant = D.Handle(plant_system.make_problem(N=1, B=B), lib=plant_system._library())
     lib = plant.lib
     dev = dict(dtype=tdt, device="cuda")
     X_sim = torch.empty((N_sim + 1, n, B), **dev)

@@ -8,9 +8,12 @@ l_f_x_fcn, l_f_xx_fcn`, system_base.py:223-251) evaluate on the GPU with analyti
 for one point (x (n,), u (m,)) exactly as in the reference, or for a batch of points
 (x (P,n), u (P,m)).
 
-A subclass describes itself to the kernels through `_device_model()`; arbitrary Python
-`_f_cont_fcn` bodies cannot run inside a CUDA kernel (NVRTC codegen, is
-future work), so a subclass without a device model raises NotImplementedError when used.
+The shipped subclasses describe themselves to the kernels through `_device_model()`.  A USER-DEFINED
+subclass keeps the reference's contract -- implement `_f_cont_fcn`, `_l_fcn`, `_l_f_fcn`
+(system_base.py:255-275) -- written against `class_files.symbolic` instead of `jax.numpy`: the three
+methods are traced once symbolically, differentiated analytically and compiled into a device model of
+their own (class_files/codegen.py), the counterpart of the reference's jit + autodiff factory
+(system_base.py:203-251).
 """
 import ctypes as C
 from abc import ABC
@@ -66,12 +69,30 @@ class System(ABC):
     # ---- what a subclass provides -----------------------------------------------------
     def _device_model(self):
         """-> (model name in _cabi.MODELS, list of physical parameters in ilqr_problem_t.phys order)"""
+        if self._is_user_defined():
+            return "user", []
         raise NotImplementedError(
-            f"{type(self).__name__} has no device model: only the shipped systems (MyPendulum, "
-            "MyDoublePendulum, MyUADoublePendulum) run on the GPU; user-defined _f_cont_fcn bodies "
-            "are not supported by this build.")
+            f"{type(self).__name__} has no device model: implement _f_cont_fcn, _l_fcn and _l_f_fcn "
+            "(written with class_files.symbolic) or use one of the shipped systems.")
+
+    def _is_user_defined(self):
+        cls = type(self)
+        return all(getattr(cls, name) is not getattr(System, name) for name in ("_f_cont_fcn", "_l_fcn", "_l_f_fcn"))
+
+    def _library(self):
+        """the shared library holding this system's kernels: libilqr_b200.so for the shipped systems, a
+        generated one (class_files/codegen.py) for a user-defined subclass"""
+        if type(self)._device_model is System._device_model and self._is_user_defined():
+            if getattr(self, "_user_lib", None) is None:
+                from .. import codegen
+                self._user_lib = codegen.build_library(self)
+            return self._user_lib
+        return _cabi.load()
 
     def _cost_weights(self):
+        if type(self)._device_model is System._device_model and self._is_user_defined():
+            n, m = self.n_x, self.n_u           # the generated cost carries its own weights
+            return np.zeros((n, n)), np.zeros((m, m)), np.zeros((n, n)), np.zeros(n)
         return self.Q, self.R, self.Q_f, self.x_target
 
     # ---- problem struct ---------------------------------------------------------------
@@ -117,7 +138,7 @@ class System(ABC):
     def _handle(self, P, N=1):
         h = self._point_handles.get((P, N))
         if h is None:
-            h = D.Handle(self.make_problem(N=N, B=P))
+            h = D.Handle(self.make_problem(N=N, B=P), lib=self._library())
             self._point_handles[(P, N)] = h
         return h
 

@@ -13,6 +13,13 @@
 // Paths in comments are relative to /root/reference/python/class_files/.
 #include "ilqr_b200.h"
 #include "ilqr_systems.cuh"
+// A library for ONE user-defined System subclass is this same file compiled with
+//   -DILQR_USER_SYS -DILQR_USER_HEADER="<generated>.cuh" -DILQR_USER_INTEG=<0..3> -DILQR_USER_F32=<0|1>
+// (class_files/codegen.py): the generated header defines ilqr::UserSys<T> / ilqr::UserCost<T>, and only that
+// model, integrator and element type are instantiated.
+#ifdef ILQR_USER_SYS
+#include ILQR_USER_HEADER
+#endif
 
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -207,8 +214,8 @@ ILQR_DEV void bwd_read(BwdIn<T, n, m> &d, const T *stage)
     for (int j = 0; j < m; ++j, ++row) d.u[j] = stage[row * bd + tid];
 }
 
-template <typename T, int n, int m, int DEPTH>
-__global__ void backward_kernel(const __grid_constant__ QuadCost<T, n, m> qc, int N, int B, const T *__restrict__ X,
+template <class Cost, typename T, int n, int m, int DEPTH>
+__global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, const T *__restrict__ X,
                                 const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
                                 T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
                                 const unsigned int *__restrict__ gate, const T *__restrict__ mu)
@@ -232,11 +239,15 @@ __global__ void backward_kernel(const __grid_constant__ QuadCost<T, n, m> qc, in
         T xN[n];
 #pragma unroll
         for (int i = 0; i < n; ++i) xN[i] = X[((size_t)N * n + i) * B + b];
-        qc.terminal_grad(xN, Vx);                                        // iLQR_class.py:136-138
+        if constexpr (Cost::QUADRATIC) {
+            qc.terminal_grad(xN, Vx);                                    // iLQR_class.py:136-138
 #pragma unroll
-        for (int i = 0; i < n; ++i)
+            for (int i = 0; i < n; ++i)
 #pragma unroll
-            for (int j = 0; j < n; ++j) Vxx[i][j] = qc.Qfs[i][j];
+                for (int j = 0; j < n; ++j) Vxx[i][j] = qc.Qfs[i][j];
+        } else {
+            qc.terminal_expand(xN, Vx, Vxx);
+        }
     }
     BwdIn<T, n, m> cur;
     int stage = 0;
@@ -244,7 +255,13 @@ __global__ void backward_kernel(const __grid_constant__ QuadCost<T, n, m> qc, in
         cp_async_wait<DEPTH - 1>();                                       // the group holding step t has landed
         bwd_read(cur, ring + stage * stage_elems);
         T lx[n], lu[m];
-        qc.grad(cur.x, cur.u, lx, lu);
+        // quadratic costs: l_xx = Q dt, l_uu = R dt, l_ux = 0 are constants folded into the sums below;
+        // generated user costs (ilqr_user.cuh) provide the full state-dependent expansion
+        [[maybe_unused]] T lxx[Cost::QUADRATIC ? 1 : n][Cost::QUADRATIC ? 1 : n];
+        [[maybe_unused]] T luu[Cost::QUADRATIC ? 1 : m][Cost::QUADRATIC ? 1 : m];
+        [[maybe_unused]] T lux[Cost::QUADRATIC ? 1 : m][Cost::QUADRATIC ? 1 : n];
+        if constexpr (Cost::QUADRATIC) qc.grad(cur.x, cur.u, lx, lu);
+        else qc.expand(cur.x, cur.u, lx, lu, lxx, luu, lux);
         // Q_x = l_x + f_x' V_x ; Q_u = l_u + f_u' V_x                    (:100-101)
         T Qx[n], Qu[m];
 #pragma unroll
@@ -288,7 +305,8 @@ __global__ void backward_kernel(const __grid_constant__ QuadCost<T, n, m> qc, in
                 T s = T(0);
 #pragma unroll
                 for (int l = 0; l < n; ++l) s += T1[i][l] * cur.A[l][j];
-                Qxx[i][j] = qc.Qs[i][j] * qc.dt + s;
+                if constexpr (Cost::QUADRATIC) Qxx[i][j] = qc.Qs[i][j] * qc.dt + s;
+                else Qxx[i][j] = lxx[i][j] + s;
             }
 #pragma unroll
         for (int i = 0; i < m; ++i) {
@@ -297,14 +315,16 @@ __global__ void backward_kernel(const __grid_constant__ QuadCost<T, n, m> qc, in
                 T s = T(0);
 #pragma unroll
                 for (int l = 0; l < n; ++l) s += T2[i][l] * cur.A[l][j];
-                Qux[i][j] = s;                                           // l_ux = 0 for the quadratic cost
+                if constexpr (Cost::QUADRATIC) Qux[i][j] = s;            // l_ux = 0 for the quadratic cost
+                else Qux[i][j] = lux[i][j] + s;
             }
 #pragma unroll
             for (int j = 0; j < m; ++j) {
                 T s = T(0);
 #pragma unroll
                 for (int l = 0; l < n; ++l) s += T2[i][l] * cur.Bd[l][j];
-                Quu[i][j] = qc.Rs[i][j] * qc.dt + s;
+                if constexpr (Cost::QUADRATIC) Quu[i][j] = qc.Rs[i][j] * qc.dt + s;
+                else Quu[i][j] = luu[i][j] + s;
                 if (i == j) Quu[i][j] += mu_b;
             }
         }
@@ -742,8 +762,8 @@ ILQR_DEV void fwd_load(FwdIn<T, n, m> &d, int t, int b, int B, const T *__restri
 }
 
 // one step of the forward pass: control law (iLQR_class.py:181-182), store, stage cost (:187), dynamics (:185)
-template <int INTEG, class Sys, typename T>
-ILQR_DEV void rollout_step(const Sys &sys, const QuadCost<T, Sys::N, Sys::M> &qc, const FwdIn<T, Sys::N, Sys::M> &in,
+template <int INTEG, class Sys, class Cost, typename T>
+ILQR_DEV void rollout_step(const Sys &sys, const Cost &qc, const FwdIn<T, Sys::N, Sys::M> &in,
                            T alpha, int t, int bw, int B, T phi, T *x, T &cost, T *__restrict__ Xw,
                            T *__restrict__ Uw)
 {
@@ -771,8 +791,8 @@ ILQR_DEV void rollout_step(const Sys &sys, const QuadCost<T, Sys::N, Sys::M> &qc
 #else
 #define ILQR_ROLLOUT_BOUNDS
 #endif
-template <class Sys, int INTEG, typename T>
-__global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys sys, const __grid_constant__ QuadCost<T, Sys::N, Sys::M> qc,
+template <class Sys, class Cost, int INTEG, typename T>
+__global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys sys, const __grid_constant__ Cost qc,
                                int N, int B, int n_alpha, const __grid_constant__ AlphaList alphas,
                                const T *__restrict__ phi,
                                const T *__restrict__ x0, const T *__restrict__ X_old, const T *__restrict__ U_old,
@@ -1081,8 +1101,8 @@ __global__ void winner_kernel(int B, int n_alpha, const T *__restrict__ cost_alp
 }
 
 // materialised cost expansion (system_base.py:212-219); one thread per (t,b), t in [0,N]
-template <typename T, int n, int m>
-__global__ void cost_expansion_kernel(const __grid_constant__ QuadCost<T, n, m> qc, int N, int B, const T *__restrict__ X,
+template <class Cost, typename T, int n, int m>
+__global__ void cost_expansion_kernel(const __grid_constant__ Cost qc, int N, int B, const T *__restrict__ X,
                                       const T *__restrict__ U, T *__restrict__ l, T *__restrict__ lx,
                                       T *__restrict__ lu, T *__restrict__ lxx, T *__restrict__ luu,
                                       T *__restrict__ lux, T *__restrict__ lf, T *__restrict__ lfx,
@@ -1096,38 +1116,61 @@ __global__ void cost_expansion_kernel(const __grid_constant__ QuadCost<T, n, m> 
     for (int i = 0; i < n; ++i) x[i] = X[((size_t)t * n + i) * B + b];
     if (t == N) {
         if (lf) lf[b] = qc.terminal(x);
-        T g[n];
-        qc.terminal_grad(x, g);
+        T g[n], H[n][n];
+        if constexpr (Cost::QUADRATIC) {
+            qc.terminal_grad(x, g);
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+#pragma unroll
+                for (int j = 0; j < n; ++j) H[i][j] = qc.Qfs[i][j];
+        } else {
+            qc.terminal_expand(x, g, H);
+        }
 #pragma unroll
         for (int i = 0; i < n; ++i) {
             if (lfx) lfx[(size_t)i * B + b] = g[i];
 #pragma unroll
             for (int j = 0; j < n; ++j)
-                if (lfxx) lfxx[((size_t)i * n + j) * B + b] = qc.Qfs[i][j];
+                if (lfxx) lfxx[((size_t)i * n + j) * B + b] = H[i][j];
         }
         return;
     }
 #pragma unroll
     for (int j = 0; j < m; ++j) u[j] = U[((size_t)t * m + j) * B + b];
-    T gx[n], gu[m];
-    qc.grad(x, u, gx, gu);
+    T gx[n], gu[m], hxx[n][n], huu[m][m], hux[m][n];
+    if constexpr (Cost::QUADRATIC) {
+        qc.grad(x, u, gx, gu);
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) hxx[i][j] = qc.Qs[i][j] * qc.dt;
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+#pragma unroll
+            for (int j = 0; j < m; ++j) huu[i][j] = qc.Rs[i][j] * qc.dt;
+#pragma unroll
+            for (int j = 0; j < n; ++j) hux[i][j] = T(0);
+        }
+    } else {
+        qc.expand(x, u, gx, gu, hxx, huu, hux);
+    }
     if (l) l[(size_t)t * B + b] = qc.stage(x, u);
 #pragma unroll
     for (int i = 0; i < n; ++i) {
         if (lx) lx[((size_t)t * n + i) * B + b] = gx[i];
 #pragma unroll
         for (int j = 0; j < n; ++j)
-            if (lxx) lxx[(((size_t)t * n + i) * n + j) * B + b] = qc.Qs[i][j] * qc.dt;
+            if (lxx) lxx[(((size_t)t * n + i) * n + j) * B + b] = hxx[i][j];
     }
 #pragma unroll
     for (int i = 0; i < m; ++i) {
         if (lu) lu[((size_t)t * m + i) * B + b] = gu[i];
 #pragma unroll
         for (int j = 0; j < m; ++j)
-            if (luu) luu[(((size_t)t * m + i) * m + j) * B + b] = qc.Rs[i][j] * qc.dt;
+            if (luu) luu[(((size_t)t * m + i) * m + j) * B + b] = huu[i][j];
 #pragma unroll
         for (int j = 0; j < n; ++j)
-            if (lux) lux[(((size_t)t * m + i) * n + j) * B + b] = T(0);
+            if (lux) lux[(((size_t)t * m + i) * n + j) * B + b] = hux[i][j];
     }
 }
 
@@ -1307,6 +1350,7 @@ template <typename T, class Sys, class F> static int dispatch_integ(const Handle
     return ILQR_E_INVALID;
 }
 
+#ifndef ILQR_USER_SYS
 template <typename T, class F> static int dispatch_model(const Handle *h, F &&f)
 {
     switch (h->p.model) {
@@ -1321,12 +1365,28 @@ template <typename T, class F> static int dispatch_model(const Handle *h, F &&f)
     }
     return ILQR_E_INVALID;
 }
+#endif
 
+#ifdef ILQR_USER_SYS
+#if ILQR_USER_F32
+typedef float user_t;
+#else
+typedef double user_t;
+#endif
+template <class F> static int dispatch(const Handle *h, F &&f)
+{
+    UserSys<user_t> sys;
+    UserCost<user_t> qc;
+    qc.dt = (user_t)h->p.dt;
+    return f(user_t(0), sys, qc, std::integral_constant<int, ILQR_USER_INTEG>{});
+}
+#else
 template <class F> static int dispatch(const Handle *h, F &&f)
 {
     if (h->p.dtype == ILQR_F64) return dispatch_model<double>(h, f);
     return dispatch_model<float>(h, f);
 }
+#endif
 
 // ---- launch helpers -----------------------------------------------------------------------
 
@@ -1348,8 +1408,8 @@ static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U,
     });
 }
 
-template <typename T, int n, int m, int DEPTH>
-static int launch_backward_depth(Handle *h, int bs, const QuadCost<T, n, m> &qc, const void *X, const void *U,
+template <typename T, int n, int m, int DEPTH, class Cost>
+static int launch_backward_depth(Handle *h, int bs, const Cost &qc, const void *X, const void *U,
                                  const void *A, const void *Bd, void *K, void *k, const int *active,
                                  const unsigned int *gate, const void *mu, cudaStream_t st)
 {
@@ -1357,12 +1417,12 @@ static int launch_backward_depth(Handle *h, int bs, const QuadCost<T, n, m> &qc,
     const size_t smem = (size_t)DEPTH * L * bs * sizeof(T);
     static size_t configured = 0;           // per instantiation: opt in to > 48 KB dynamic shared memory once
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(backward_kernel<T, n, m, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(backward_kernel<Cost, T, n, m, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) { h->last_cuda = (int)e; return ILQR_E_CUDA; }
         configured = smem;
     }
-    backward_kernel<T, n, m, DEPTH><<<grid_for(h->p.B, bs), bs, smem, st>>>(
+    backward_kernel<Cost, T, n, m, DEPTH><<<grid_for(h->p.B, bs), bs, smem, st>>>(
         qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active, gate,
         (const T *)mu);
     ILQR_CHECK_LAUNCH(h);
@@ -1377,7 +1437,7 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
         using Sys = decltype(sys);
         // small batches: one warp per block and a deep ring (latency bound); large batches: shallower
         // ring so that more warps fit per SM (HBM bound)
-        if constexpr (Sys::N == 4 && Sys::M == 1) {
+        if constexpr (Sys::N == 4 && Sys::M == 1 && decltype(qc)::QUADRATIC) {
             // small batches of the n=4, m=1 case: four lanes per trajectory (latency bound regime)
             const char *lanes_env = getenv("ILQR_BACKWARD_LANES");
             const bool lanes = lanes_env ? atoi(lanes_env) != 0 : h->p.B <= 32768;
@@ -1406,6 +1466,9 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
 static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const void *U, void *K, void *k,
                                const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr)
 {
+#ifdef ILQR_USER_SYS
+    return ILQR_E_INVALID;
+#else
     constexpr int TPB = 16;
     auto go = [&](auto tz) -> int {
         using T = decltype(tz);
@@ -1424,6 +1487,7 @@ static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const 
         return ILQR_OK;
     };
     return h->p.dtype == ILQR_F64 ? go(double(0)) : go(float(0));
+#endif
 }
 
 static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const void *phi, const void *x0, const void *X, const void *U,
@@ -1445,7 +1509,7 @@ static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const voi
         if (!bs_env && bs > 128) bs = 128;
         // lazy waves: the warps of one trajectory group (one per step size) share a block, hence an L1
         if (!bs_env && h->lazy && n_alpha <= 4 && threads >= (size_t)148 * 16 * 32 * n_alpha) bs = 32 * n_alpha;
-        rollout_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
+        rollout_kernel<Sys, decltype(qc), I, T><<<grid_for(threads, bs), bs, 0, st>>>(
             sys, qc, h->p.N, h->p.B, n_alpha, al, (const T *)phi, (const T *)x0, (const T *)X, (const T *)U, (const T *)k,
             (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref, sp, list, list_count);
         ILQR_CHECK_LAUNCH(h);
@@ -1601,7 +1665,11 @@ using namespace ilqr;
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
+#ifdef ILQR_USER_SYS
+const char *ilqr_version(void) { return "ilqr_b200 0.1 (sm_100a), user-defined system build"; }
+#else
 const char *ilqr_version(void) { return "ilqr_b200 0.1 (sm_100a)"; }
+#endif
 
 const char *ilqr_strerror(int code)
 {
@@ -1626,8 +1694,17 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
     case ILQR_DOUBLE_PENDULUM: n = 4; m = 2; break;
     case ILQR_UA_DOUBLE_PENDULUM: n = 4; m = 1; break;
     case ILQR_LTV: n = 12; m = 4; if (p->integrator != ILQR_EULER) return ILQR_E_INVALID; break;
+#ifdef ILQR_USER_SYS
+    case ILQR_USER:
+        n = UserSys<user_t>::N; m = UserSys<user_t>::M;
+        if (p->integrator != ILQR_USER_INTEG || p->dtype != (ILQR_USER_F32 ? ILQR_F32 : ILQR_F64)) return ILQR_E_INVALID;
+        break;
+#endif
     default: return ILQR_E_INVALID;
     }
+#ifdef ILQR_USER_SYS
+    if (p->model != ILQR_USER) return ILQR_E_INVALID;        // this library holds one generated model only
+#endif
     if (p->n != n || p->m != m) return ILQR_E_INVALID;
     if (p->N < 1 || p->B < 1 || p->n_alpha < 1 || p->n_alpha > ILQR_MAX_ALPHAS || p->maxiter < 0) return ILQR_E_INVALID;
     if (!(p->dt > 0.0)) return ILQR_E_INVALID;
@@ -1720,7 +1797,7 @@ int ilqr_cost_expansion(ilqr_handle_t hh, const void *X, const void *U, void *l,
         using Sys = decltype(sys);
         const size_t threads = (size_t)(h->p.N + 1) * h->p.B;
         const int bs = 128;
-        cost_expansion_kernel<T, Sys::N, Sys::M><<<grid_for(threads, bs), bs, 0, st>>>(
+        cost_expansion_kernel<decltype(qc), T, Sys::N, Sys::M><<<grid_for(threads, bs), bs, 0, st>>>(
             qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (T *)l, (T *)lx, (T *)lu, (T *)lxx, (T *)luu, (T *)lux,
             (T *)lf, (T *)lfx, (T *)lfxx);
         ILQR_CHECK_LAUNCH(h);

@@ -78,6 +78,21 @@ ILQR_DEV double sqrt_t(double x) { return sqrt(x); }
 ILQR_DEV float sqrt_t(float x) { return sqrtf(x); }
 ILQR_DEV double abs_t(double x) { return fabs(x); }
 ILQR_DEV float abs_t(float x) { return fabsf(x); }
+// used by generated user systems (class_files/codegen.py)
+ILQR_DEV double cos_t(double x) { double s, c; sincos_t(x, &s, &c); return c; }
+ILQR_DEV float cos_t(float x) { return cosf(x); }
+ILQR_DEV double tan_t(double x) { double s, c; sincos_t(x, &s, &c); return s / c; }
+ILQR_DEV float tan_t(float x) { return tanf(x); }
+ILQR_DEV double exp_t(double x) { return exp(x); }
+ILQR_DEV float exp_t(float x) { return expf(x); }
+ILQR_DEV double log_t(double x) { return log(x); }
+ILQR_DEV float log_t(float x) { return logf(x); }
+ILQR_DEV double tanh_t(double x) { return tanh(x); }
+ILQR_DEV float tanh_t(float x) { return tanhf(x); }
+ILQR_DEV double pow_t(double x, double y) { return pow(x, y); }
+ILQR_DEV float pow_t(float x, float y) { return powf(x, y); }
+ILQR_DEV double atan2_t(double y, double x) { return atan2(y, x); }
+ILQR_DEV float atan2_t(float y, float x) { return atan2f(y, x); }
 
 // ------------------------------------------------------------------------------------------
 // Second-order mechanical systems: x = [q, qd], xdot = [qd, qdd(x,u)].  A system provides
@@ -90,7 +105,7 @@ ILQR_DEV float abs_t(float x) { return fabsf(x); }
 template <typename T>
 struct PendulumSys {
     static constexpr int NQ = 1, N = 2, M = 1;
-    static constexpr bool FIRST_ORDER = false;
+    static constexpr bool FIRST_ORDER = false, GENERIC = false;
     T gl, d;   // g/l, damping
     ILQR_DEV T time_scalar(int, T) const { return T(0); }
     ILQR_DEV void acc(const T *x, const T *u, T *a) const
@@ -111,7 +126,7 @@ struct PendulumSys {
 template <typename T, int M_>
 struct DoublePendulumSys {
     static constexpr int NQ = 2, N = 4, M = M_;
-    static constexpr bool FIRST_ORDER = false;
+    static constexpr bool FIRST_ORDER = false, GENERIC = false;
     ILQR_DEV T time_scalar(int, T) const { return T(0); }
     // derived constants (host, double precision):
     //   c = m2 l1 l2, m11_0 = m1 l1^2/4 + m2 l1^2 + m2 l2^2/4 + th1 + th2, m12_0 = m22 = m2 l2^2/4 + th2,
@@ -182,7 +197,7 @@ struct DoublePendulumSys {
 template <typename T>
 struct LtvSys {
     static constexpr int NQ = 0, N = 12, M = 4;
-    static constexpr bool FIRST_ORDER = true;
+    static constexpr bool FIRST_ORDER = true, GENERIC = false;
     T Ac[N][N], E[N][N], Bc[N][M];
     T amp, two_pi_over_N;
     ILQR_DEV T time_scalar(int t, T phi) const { return amp * sin_t(two_pi_over_N * T(t) + phi); }
@@ -249,11 +264,166 @@ ILQR_DEV void lu_solve_inplace(T (*a)[n], T (*b)[nrhs])
 template <class Sys, typename T>
 ILQR_DEV void f_cont(const Sys &s, const T *x, const T *u, T *xd)
 {
-    constexpr int NQ = Sys::NQ;
-    T a[NQ];
-    s.acc(x, u, a);
+    if constexpr (Sys::GENERIC) {
+        s.f(x, u, xd);
+    } else {
+        constexpr int NQ = Sys::NQ;
+        T a[NQ];
+        s.acc(x, u, a);
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) { xd[i] = x[NQ + i]; xd[NQ + i] = a[i]; }
+        for (int i = 0; i < NQ; ++i) { xd[i] = x[NQ + i]; xd[NQ + i] = a[i]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic first-order systems x_dot = f(x,u) with dense continuous Jacobians -- the form generated
+// for user-defined System subclasses (class_files/codegen.py): the system provides
+//   f(x,u,xd)                 xd = f(x,u)
+//   f_jac(x,u,xd,Ac,Bc)       xd = f(x,u), Ac = df/dx (N x N), Bc = df/du (N x M)
+// ------------------------------------------------------------------------------------------
+
+// backward Euler quasi-Newton, system_base.py:101-140 (same scheme as backward_euler_step below)
+template <class Sys, typename T>
+ILQR_DEV void backward_euler_step_generic(const Sys &s, T dt, const T *x, const T *u, T *xn)
+{
+    constexpr int n = Sys::N, M = Sys::M;
+    T f[n], F[n], Ac[n][n], Bc[n][M], Jr[n][n], Inv[n][n];
+    s.f(x, u, f);
+#pragma unroll
+    for (int i = 0; i < n; ++i) xn[i] = x[i] + dt * f[i];                     // explicit-Euler guess (:124)
+    s.f_jac(xn, u, f, Ac, Bc);                                               // residual Jacobian frozen at the guess (:130-135)
+    T fn = T(0);
+#pragma unroll
+    for (int i = 0; i < n; ++i) { F[i] = xn[i] - x[i] - dt * f[i]; fn += F[i] * F[i]; }
+    fn = sqrt_t(fn);
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            Jr[i][j] = ((i == j) ? T(1) : T(0)) - dt * Ac[i][j];
+            Inv[i][j] = (i == j) ? T(1) : T(0);
+        }
+    lu_solve_inplace<n, n>(Jr, Inv);
+    int k = 0;
+    while (fn > T(1e-5) && k < 20) {                                         // (:105-120)
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T d = T(0);
+#pragma unroll
+            for (int j = 0; j < n; ++j) d -= Inv[i][j] * F[j];
+            xn[i] += d;
+        }
+        s.f(xn, u, f);
+        fn = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) { F[i] = xn[i] - x[i] - dt * f[i]; fn += F[i] * F[i]; }
+        fn = sqrt_t(fn);
+        ++k;
+    }
+}
+
+// discrete Jacobians of a generic system: chain rule through the integrator stages (what the reference
+// obtains with jacfwd of the step, system_base.py:203-205; implicit function theorem for backward Euler,
+// :146-188)
+template <int INTEG, class Sys, typename T>
+ILQR_DEV void step_jac_generic(const Sys &s, T dt, const T *x, const T *u, T (*A)[Sys::N], T (*Bd)[Sys::M])
+{
+    constexpr int n = Sys::N, M = Sys::M;
+    T k[n], Ac[n][n], Bc[n][M];
+    if (INTEG == EULER) {
+        s.f_jac(x, u, k, Ac, Bc);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) A[i][j] = ((i == j) ? T(1) : T(0)) + dt * Ac[i][j];
+#pragma unroll
+            for (int j = 0; j < M; ++j) Bd[i][j] = dt * Bc[i][j];
+        }
+    } else if (INTEG == BACKWARD_EULER) {
+        T xn[n], Jr[n][n], R[n][n + M];
+        backward_euler_step_generic(s, dt, x, u, xn);
+        s.f_jac(xn, u, k, Ac, Bc);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                Jr[i][j] = ((i == j) ? T(1) : T(0)) - dt * Ac[i][j];
+                R[i][j] = (i == j) ? T(1) : T(0);
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) R[i][n + j] = dt * Bc[i][j];
+        }
+        lu_solve_inplace<n, n + M>(Jr, R);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) A[i][j] = R[i][j];
+#pragma unroll
+            for (int j = 0; j < M; ++j) Bd[i][j] = R[i][n + j];
+        }
+    } else {
+        constexpr int S = (INTEG == MIDPOINT) ? 2 : 4;
+        const T cs[4] = { T(0), T(0.5), (INTEG == RK4) ? T(0.5) : T(0), T(1) };
+        const T ws[4] = { (INTEG == RK4) ? T(1) : T(0), (INTEG == RK4) ? T(2) : T(1), T(2), T(1) };
+        T Kx[n][n], Ku[n][M], Ax[n][n], Au[n][M], xs[n];
+#pragma unroll
+        for (int st = 0; st < S; ++st) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) xs[i] = st == 0 ? x[i] : x[i] + (cs[st] * dt) * k[i];
+            s.f_jac(xs, u, k, Ac, Bc);
+            if (st == 0) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+#pragma unroll
+                    for (int j = 0; j < n; ++j) Kx[i][j] = Ac[i][j];
+#pragma unroll
+                    for (int j = 0; j < M; ++j) Ku[i][j] = Bc[i][j];
+                }
+            } else {
+                // Kx <- Ac (I + c dt Kx), Ku <- Ac (c dt Ku) + Bc
+                T Sx[n][n], Su[n][M];
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+#pragma unroll
+                    for (int j = 0; j < n; ++j) Sx[i][j] = ((i == j) ? T(1) : T(0)) + (cs[st] * dt) * Kx[i][j];
+#pragma unroll
+                    for (int j = 0; j < M; ++j) Su[i][j] = (cs[st] * dt) * Ku[i][j];
+                }
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+#pragma unroll
+                    for (int j = 0; j < n; ++j) {
+                        T acc = T(0);
+#pragma unroll
+                        for (int l = 0; l < n; ++l) acc += Ac[i][l] * Sx[l][j];
+                        Kx[i][j] = acc;
+                    }
+#pragma unroll
+                    for (int j = 0; j < M; ++j) {
+                        T acc = T(0);
+#pragma unroll
+                        for (int l = 0; l < n; ++l) acc += Ac[i][l] * Su[l][j];
+                        Ku[i][j] = acc + Bc[i][j];
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+#pragma unroll
+                for (int j = 0; j < n; ++j) Ax[i][j] = st == 0 ? ws[0] * Kx[i][j] : Ax[i][j] + ws[st] * Kx[i][j];
+#pragma unroll
+                for (int j = 0; j < M; ++j) Au[i][j] = st == 0 ? ws[0] * Ku[i][j] : Au[i][j] + ws[st] * Ku[i][j];
+            }
+        }
+        const T h = (INTEG == RK4) ? dt / T(6) : dt;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) A[i][j] = ((i == j) ? T(1) : T(0)) + h * Ax[i][j];
+#pragma unroll
+            for (int j = 0; j < M; ++j) Bd[i][j] = h * Au[i][j];
+        }
+    }
 }
 
 // backward Euler quasi-Newton (system_base.py:101-140): explicit-Euler guess, Jacobian of the
@@ -348,7 +518,8 @@ ILQR_DEV void step(const Sys &s, T dt, const T *x, const T *u, T *xn, T w = T(0)
 #pragma unroll
         for (int i = 0; i < n; ++i) xn[i] = x[i] + (dt / T(6)) * (k1[i] + T(2) * k2[i] + T(2) * k3[i] + k4[i]);
     } else {
-        backward_euler_step(s, dt, x, u, xn);
+        if constexpr (Sys::GENERIC) backward_euler_step_generic(s, dt, x, u, xn);
+        else backward_euler_step(s, dt, x, u, xn);
     }
 }
 
@@ -375,7 +546,9 @@ template <int INTEG, class Sys, typename T>
 ILQR_DEV void step_jac(const Sys &s, T dt, const T *x, const T *u, T (*A)[Sys::N], T (*Bd)[Sys::M], T w = T(0))
 {
     constexpr int n = Sys::N, NQ = Sys::NQ, M = Sys::M;
-    if constexpr (Sys::FIRST_ORDER) {
+    if constexpr (Sys::GENERIC) {
+        step_jac_generic<INTEG>(s, dt, x, u, A, Bd);
+    } else if constexpr (Sys::FIRST_ORDER) {
 #pragma unroll
         for (int i = 0; i < n; ++i) {
 #pragma unroll
@@ -504,6 +677,7 @@ ILQR_DEV void step_jac(const Sys &s, T dt, const T *x, const T *u, T (*A)[Sys::N
 // ------------------------------------------------------------------------------------------
 template <typename T, int n, int m>
 struct QuadCost {
+    static constexpr bool QUADRATIC = true;
     T dt;
     T xt[n];
     T Qs[n][n], Rs[m][m], Qfs[n][n];

@@ -59,6 +59,26 @@ def cos(x):
     return torch.cos(_to_tensor(x))
 
 
+def exp(x):
+    return torch.exp(_to_tensor(x))
+
+
+def log(x):
+    return torch.log(_to_tensor(x))
+
+
+def sqrt(x):
+    return torch.sqrt(_to_tensor(x))
+
+
+def tanh(x):
+    return torch.tanh(_to_tensor(x))
+
+
+def tan(x):
+    return torch.tan(_to_tensor(x))
+
+
 def concatenate(seq, axis=0):
     return torch.cat([_to_tensor(s) for s in seq], dim=axis)
 

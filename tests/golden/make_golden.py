@@ -63,6 +63,14 @@ def make_system(p, integrator):
     diag = lambda v: jnp.diag(jnp.array(v))
     common = dict(dt=p["dt"], x_target=jnp.array(p["x_target"]), Q=diag(p["Q"]), R=diag(p["R"]),
                   Q_f=diag(p["Q_f"]), integrator=integrator, use_jit=True)
+    if p["kind"] == "user_cartpole":
+        # a USER-DEFINED subclass of the reference's System (tests/user_systems.py): the reference's own
+        # jit + autodiff factory (system_base.py:203-251) supplies every derivative
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from class_files.systems.system_base import System
+        from user_systems import make_cartpole_class
+        extra = {k: p[k] for k in ("mc", "mp", "l", "g", "b", "p_max", "w_bar")}
+        return make_cartpole_class(System, jnp)(**extra, **common)
     if p["kind"] == "pendulum":
         from class_files.systems.pendulum_sys import MyPendulum
         return MyPendulum(g=p["g"], l=p["l"], d=p["d"], **common)
@@ -242,6 +250,16 @@ def case_mpc(p, integ_opt, integ_plant, T_h, ticks, x0, maxiter, tol):
 def build_cases():
     cases = {}
     integs = ["euler", "midpoint", "rk4", "backward_euler"]
+    # user-defined System subclass (cart-pole with a non-quadratic barrier cost), tests/user_systems.py
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from user_systems import CARTPOLE
+    p_cp = dict(CARTPOLE, kind="user_cartpole")
+    for i, integ in enumerate(integs):
+        cases[f"user_cartpole_derivs_{integ}"] = (case_derivs, (p_cp, integ, 300 + i))
+    cases["user_cartpole_passes_rk4"] = (case_passes, (p_cp, "rk4", 0.6, 310))
+    cases["user_cartpole_solve_rk4_T1"] = (case_solve, (p_cp, "rk4", 1.0, [0.0, 0.3, 0.0, 0.0], 30, 1e-5))
+    cases["user_cartpole_solve_be_T1"] = (case_solve, (p_cp, "backward_euler", 1.0, [0.2, -0.2, 0.0, 0.5], 20, 1e-5))
+    cases["user_cartpole_mpc_T0p5"] = (case_mpc, (p_cp, "rk4", "midpoint", 0.5, 4, [0.1, 2.9, 0.0, 0.0], 20, 1e-5))
     for tag, p in (("pend", P_PEND_D), ("double", P_DP_OL), ("ua", P_UA_OL)):
         for i, integ in enumerate(integs):
             cases[f"derivs_{tag}_{integ}"] = (case_derivs, (p, integ, 100 + i))

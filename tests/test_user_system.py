@@ -1,0 +1,223 @@
+"""User-defined System subclasses: the reference's three-method contract
+(`_f_cont_fcn`, `_l_fcn`, `_l_f_fcn`, system_base.py:255-275) through class_files.symbolic -> analytic
+derivatives -> generated CUDA -> its own library with the same C ABI.
+
+Golden vectors `tests/golden/user_cartpole_*.npz` come from the UNMODIFIED reference running the same class
+body (tests/user_systems.py) with its own jit/autodiff factory (tests/golden/make_golden.py)."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, rel_err
+from helpers import UA_OL, cfg2_x0, golden_flow, ua_system
+from user_systems import CARTPOLE, make_cartpole_class, make_user_ua_class
+
+INTEGRATORS = ("euler", "midpoint", "rk4", "backward_euler")
+TOL = 1e-9
+
+
+def cartpole(integrator="rk4", dtype="float64"):
+    from class_files import symbolic as jnp
+    from class_files.systems.system_base import System
+    p = CARTPOLE
+    cls = make_cartpole_class(System, jnp)
+    return cls(dt=p["dt"], x_target=np.array(p["x_target"]), Q=np.diag(p["Q"]), R=np.diag(p["R"]), Q_f=np.diag(p["Q_f"]),
+               integrator=integrator, dtype=dtype, **{k: p[k] for k in ("mc", "mp", "l", "g", "b", "p_max", "w_bar")})
+
+
+def user_ua(integrator="rk4"):
+    from class_files import symbolic as jnp
+    from class_files.systems.system_base import System
+    p = UA_OL
+    return make_user_ua_class(System, jnp)(dt=p["dt"], x_target=np.array(p["x_target"]), Q=np.diag(p["Q"]),
+                                           R=np.diag(p["R"]), Q_f=np.diag(p["Q_f"]), integrator=integrator, **p["phys"])
+
+
+# ------------------------------------------------------------------------------------------ CPU
+def test_generated_header_derivatives_match_finite_differences():
+    import sympy as sp
+    from class_files import codegen
+    s = cartpole()
+    text, n, m = codegen.generate_header(s)
+    assert (n, m) == (4, 1) and "struct UserSys" in text and "struct UserCost" in text
+    assert "exp_t(" in text and "sin_t(" in text and "QUADRATIC = false" in text
+    # the analytic continuous Jacobian that went into the header vs central differences of the traced f
+    _, _, xs, us, f, l, lf = codegen._trace(s)
+    fn = sp.lambdify([xs, us], f, "math")
+    Ac = sp.lambdify([xs, us], [[sp.diff(fi, v) for v in xs] for fi in f], "math")
+    lxx = sp.lambdify([xs, us], [[sp.diff(sp.diff(l, a), b) for b in xs] for a in xs], "math")
+    lfn = sp.lambdify([xs, us], l, "math")
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        x, u = rng.uniform(-1, 1, 4), rng.uniform(-2, 2, 1)
+        A = np.array(Ac(x, u), dtype=float)
+        H = np.array(lxx(x, u), dtype=float)
+        for j in range(4):
+            e = np.zeros(4); e[j] = 1e-6
+            fd = (np.array(fn(x + e, u)) - np.array(fn(x - e, u))) / 2e-6
+            assert np.allclose(A[:, j], fd, rtol=1e-6, atol=1e-7)
+        e = np.zeros(4); e[0] = 1e-4
+        fd2 = (lfn(x + e, u) - 2 * lfn(x, u) + lfn(x - e, u)) / 1e-8
+        assert abs(H[0, 0] - fd2) < 1e-4 * max(1.0, abs(H[0, 0]))
+    assert abs(H[0, 0] - CARTPOLE["Q"][0] * CARTPOLE["dt"]) > 1e-6        # the barrier makes l_xx state dependent
+
+
+def test_user_library_builds_with_the_same_c_abi():
+    from class_files import _cabi
+    s = cartpole("midpoint")
+    lib = s._library()
+    hdr = open(f"{ROOT}/include/ilqr_b200.h").read()
+    for name in sorted(set(re.findall(r"\b(ilqr_[a-z0-9_]+)\s*\(", hdr))):
+        assert getattr(lib, name) is not None, name
+    assert b"user-defined system" in lib.ilqr_version()
+    # the generated library holds ONE model: anything else is rejected before any CUDA call
+    p = ua_system().make_problem(N=10, B=1)
+    h = C.c_void_p()
+    assert lib.ilqr_create(C.byref(p), C.byref(h)) == -1
+    p = s.make_problem(N=10, B=1)
+    p.integrator = _cabi.INTEGRATORS["rk4"]            # compiled for midpoint
+    assert lib.ilqr_create(C.byref(p), C.byref(h)) == -1
+    assert s._library() is lib                          # cached on the instance
+
+
+def test_shipped_systems_keep_their_device_models():
+    s = ua_system()
+    assert not s._is_user_defined() and s._device_model()[0] == "ua_double_pendulum"
+    from class_files.systems.system_base import System
+
+    class Incomplete(System):
+        def _f_cont_fcn(self, x, u):
+            return x
+    with pytest.raises(NotImplementedError, match="no device model"):
+        Incomplete(2, 1, 0.01)._device_model()
+
+
+# ------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("integ", INTEGRATORS)
+def test_user_cartpole_point_functions_vs_reference(integ):
+    g = load_golden(f"user_cartpole_derivs_{integ}")
+    s = cartpole(integ)
+    xs, us = g["xs"], g["us"]
+    got = dict(f=s.f_fcn(xs, us), f_x=s.f_x_fcn(xs, us), f_u=s.f_u_fcn(xs, us), l=s.l_fcn(xs, us),
+               l_x=s.l_x_fcn(xs, us), l_u=s.l_u_fcn(xs, us), l_xx=s.l_xx_fcn(xs, us), l_uu=s.l_uu_fcn(xs, us),
+               l_ux=s.l_ux_fcn(xs, us), l_f=s.l_f_fcn(xs), l_f_x=s.l_f_x_fcn(xs), l_f_xx=s.l_f_xx_fcn(xs))
+    for k, v in got.items():
+        ref = g[k].reshape(np.shape(v))
+        assert rel_err(v, ref, floor=1e-3) < 1e-11, (k, rel_err(v, ref, floor=1e-3))
+    one = s.f_x_fcn(xs[0], us[0])                         # single point, reference shapes
+    assert one.shape == (4, 4) and rel_err(one, g["f_x"][0]) < 1e-11
+
+
+@pytest.mark.gpu
+def test_user_cartpole_passes_vs_reference():
+    from class_files.iLQR_class import iLQR
+    g = load_golden("user_cartpole_passes_rk4")
+    s = cartpole("rk4")
+    N = int(g["N"])
+    sol = iLQR(s, float(g["T"]), g["x0"], np.zeros((1, N)), verbose=False)
+    X_nom, U_nom, c0 = sol.forward_pass(g["x0"], 0.0, sol.X, g["U_nom"], sol.U_ff, sol.K)
+    assert rel_err(X_nom, g["X_nom"]) < 1e-12 and rel_err(c0, g["cost0"]) < 1e-12
+    U_ff, K = sol.backward_pass(g["X_nom"], g["U_nom"])
+    assert rel_err(K, g["K"]) < TOL and rel_err(U_ff, g["U_ff"], floor=1e-6) < TOL
+    for a in (1.0, 0.5, 0.125):
+        tag = str(a).replace(".", "p")
+        Xn, Un, c = sol.forward_pass(g["x0_b"], a, g["X_nom"], g["U_nom"], g["U_ff"], g["K"])
+        assert rel_err(Xn, g[f"X_a{tag}"]) < TOL and rel_err(c, g[f"cost_a{tag}"]) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,integ", [("user_cartpole_solve_rk4_T1", "rk4"), ("user_cartpole_solve_be_T1", "backward_euler")])
+def test_user_cartpole_solve_vs_reference(name, integ):
+    """every iteration the reference executed, on identical inputs (1e-9), then the full solve's flow and result"""
+    from class_files.iLQR_class import iLQR
+    g = load_golden(name)
+    s = cartpole(integ)
+    N = int(g["N"])
+    sol = iLQR(s, float(g["T"]), g["x0"], np.zeros((1, N)), tol=float(g["tol"]), maxiter=int(g["maxiter"]), verbose=True)
+    ref_idx, ref_costs = golden_flow(g)
+    for i in range(len(ref_idx)):
+        U_ff, K = sol.backward_pass(g["it_X"][i], g["it_U"][i])
+        assert rel_err(K, g["it_K"][i]) < 1e-8, (i, rel_err(K, g["it_K"][i]))
+        assert rel_err(U_ff, g["it_U_ff"][i], floor=1e-6) < 1e-8, i
+        if ref_idx[i] < 0:
+            continue
+        Xn, Un, c = sol.forward_pass(g["x0"], 0.5 ** ref_idx[i], g["it_X"][i], g["it_U"][i], g["it_U_ff"][i], g["it_K"][i])
+        X_ref = g["it_X"][i + 1] if i + 1 < len(ref_idx) else g["X"]
+        assert rel_err(Xn, X_ref) < TOL and rel_err(c, ref_costs[i + 1]) < TOL, i
+    X, U, cost = sol.optimize_trajectory()
+    idx, alphas, costs = sol.trace(0)
+    k = min(6, len(ref_idx), len(idx))
+    assert np.array_equal(idx[:k], ref_idx[:k]), (idx, ref_idx)
+    assert np.all(np.abs(costs[:k + 1] - ref_costs[:k + 1]) <= 1e-8 * np.abs(ref_costs[:k + 1]))
+    if np.array_equal(idx, ref_idx):
+        assert rel_err(cost, g["cost"]) < 1e-6 and rel_err(X, g["X"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_user_cartpole_mpc_vs_reference():
+    """receding horizon with a user-defined optimizer model (rk4) and a user-defined plant (midpoint)"""
+    from class_files.iLQR_class import iLQR
+    from class_files.mpc import run_mpc
+    g = load_golden("user_cartpole_mpc_T0p5")
+    opt, plant = cartpole("rk4"), cartpole(str(g["p_integrator_plant"]))
+    N, ticks = int(g["N"]), int(g["ticks"])
+    sol = iLQR(opt, float(g["T"]), g["x0"], np.zeros((1, N)), tol=float(g["tol"]), maxiter=int(g["maxiter"]), verbose=False)
+    r = run_mpc(sol, plant, g["x0"], ticks)
+    assert list(r["iterations"]) == list(g["n_backward"])
+    assert rel_err(r["X_sim"], g["X_sim"]) < 1e-7 and rel_err(r["costs"], g["costs"]) < 1e-7
+    assert rel_err(r["U_sim"], g["U_sim"], floor=1e-3) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("integ", INTEGRATORS)
+def test_user_ua_matches_reference_goldens_and_shipped_model(integ):
+    """the UA double pendulum re-entered as a user system: generated code vs the reference's goldens for the
+    shipped system and vs the hand-written device model"""
+    g = load_golden(f"derivs_ua_{integ}")
+    s, b = user_ua(integ), ua_system(integ)
+    xs, us = g["xs"], g["us"]
+    for k, fn in (("f", s.f_fcn), ("f_x", s.f_x_fcn), ("f_u", s.f_u_fcn), ("l_x", s.l_x_fcn), ("l_xx", s.l_xx_fcn),
+                  ("l_uu", s.l_uu_fcn), ("l_ux", s.l_ux_fcn)):
+        v = fn(xs, us)
+        assert rel_err(v, g[k].reshape(np.shape(v)), floor=1e-3) < 1e-11, (k, integ)
+    assert rel_err(s.f_x_fcn(xs, us), b.f_x_fcn(xs, us)) < 1e-12
+
+
+@pytest.mark.gpu
+def test_user_ua_batched_solve_matches_shipped_model():
+    from class_files.iLQR_class import iLQR
+    B, N = 256, 100
+    x0 = cfg2_x0(B, seed=4)
+    res = {}
+    for name, s in (("user", user_ua()), ("shipped", ua_system())):
+        sol = iLQR(s, 1.0, x0, np.zeros((1, N)), maxiter=3, verbose=False)
+        X, U, cost = sol.optimize_trajectory()
+        res[name] = (X.copy(), cost.copy(), sol.iterations.copy())
+    same = res["user"][2] == res["shipped"][2]
+    assert same.mean() > 0.99
+    ec = np.abs(res["user"][1] - res["shipped"][1]) / np.abs(res["shipped"][1])
+    assert np.median(ec[same]) < 1e-12 and np.quantile(ec[same], 0.95) < TOL
+
+
+@pytest.mark.gpu
+def test_user_cartpole_batch_properties_and_fp32():
+    import torch
+    from class_files.iLQR_class import iLQR
+    B, N = 2048, 150
+    rng = np.random.default_rng(7)
+    x0 = rng.uniform(-0.5, 0.5, (B, 4))
+    sol = iLQR(cartpole(), 1.5, torch.as_tensor(x0).cuda(), torch.zeros((1, N), dtype=torch.float64, device="cuda"),
+               maxiter=15, verbose=False)
+    X, U, cost = sol.optimize_trajectory()
+    zX, zU = torch.zeros_like(X), torch.zeros_like(U)
+    c0 = sol.forward_pass(sol.x_0, 0.0, zX, zU, torch.zeros_like(sol.U_ff), torch.zeros_like(sol.K))[2]
+    assert bool((cost <= c0).all()) and float((cost < 0.9 * c0).double().mean()) > 0.9
+    Xr, Ur, cr = sol.forward_pass(sol.x_0, 0.0, X, U, torch.zeros_like(sol.U_ff), torch.zeros_like(sol.K))
+    assert torch.equal(Xr, X) and torch.equal(cr, cost)
+    # FP32 build of the same user system (1e-4 mode of BASELINE.json)
+    s32 = cartpole(dtype="float32")
+    g = load_golden("user_cartpole_derivs_rk4")
+    assert rel_err(s32.f_x_fcn(g["xs"], g["us"]), g["f_x"], floor=1e-2) < 1e-4

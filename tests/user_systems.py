@@ -1,0 +1,83 @@
+"""User-defined System subclasses used by the tests of the codegen path.
+
+Each factory takes the `System` base class and the array namespace, so that the SAME method bodies run
+  * under the UNMODIFIED reference (`/root/reference/python/class_files/systems/system_base.py` + jax.numpy,
+    via oracle/jaxshim in tests/golden/make_golden.py) to produce golden vectors, and
+  * under this package (`class_files.systems.system_base.System` + `class_files.symbolic`) on the GPU.
+"""
+import math
+
+CARTPOLE = dict(dt=0.01, x_target=[0.0, math.pi, 0.0, 0.0], Q=[1.0, 5.0, 0.1, 0.1], R=[0.1],
+                Q_f=[50.0, 200.0, 10.0, 10.0], mc=1.0, mp=0.2, l=0.5, g=9.81, b=0.1, p_max=1.5, w_bar=0.5)
+
+
+def make_cartpole_class(System, jnp):
+    class MyCartPole(System):
+        """Cart-pole, x = [p, theta, p_dot, theta_dot] (theta = 0 hanging down), u = [force].
+        Stage cost = quadratic + a smooth (exponential) barrier keeping the cart inside |p| < p_max, so
+        l_xx depends on the state -- a cost the shipped quadratic device cost cannot express (the kind
+        of term the reference leaves commented out at pendulum_sys.py:84-85)."""
+
+        def __init__(self, dt, x_target, Q, R, Q_f, mc=1.0, mp=0.2, l=0.5, g=9.81, b=0.1, p_max=1.5, w_bar=0.5,
+                     use_jit=True, integrator="rk4", **kw):
+            self.mc, self.mp, self.l, self.g, self.b = mc, mp, l, g, b
+            self.p_max, self.w_bar = p_max, w_bar
+            self.x_target, self.Q, self.R, self.Q_f = x_target, Q, R, Q_f
+            super().__init__(n_x=4, n_u=1, dt=dt, use_jit=use_jit, integrator=integrator, **kw)
+
+        def _f_cont_fcn(self, x, u):
+            p, th, pd, thd = x[0], x[1], x[2], x[3]
+            s, c = jnp.sin(th), jnp.cos(th)
+            den = self.mc + self.mp * s * s
+            pdd = (u[0] + self.mp * s * (self.l * thd * thd + self.g * c) - self.b * pd) / den
+            thdd = (-u[0] * c - self.mp * self.l * thd * thd * c * s - (self.mc + self.mp) * self.g * s
+                    + self.b * pd * c) / (self.l * den)
+            return jnp.array([pd, thd, pdd, thdd])
+
+        def _l_fcn(self, x, u):
+            dx = x - self.x_target
+            quad = 0.5 * dx.T @ self.Q @ dx + 0.5 * u.T @ self.R @ u
+            barrier = self.w_bar * jnp.exp(4.0 * (x[0] * x[0] - self.p_max * self.p_max))
+            return (quad + barrier) * self.dt
+
+        def _l_f_fcn(self, x):
+            dx = x - self.x_target
+            return 0.5 * dx.T @ self.Q_f @ dx
+
+    return MyCartPole
+
+
+def make_user_ua_class(System, jnp):
+    class UserUADoublePendulum(System):
+        """The under-actuated double pendulum written as a USER system (M(q) qdd = h solved in closed form),
+        to check the generated device code against the shipped device model and the reference's goldens."""
+
+        def __init__(self, dt, x_target, Q, R, Q_f, g=9.81, m1=1.0, m2=1.0, l1=1.0, l2=1.0, d1=0.01, d2=0.01,
+                     theta1=0.0, theta2=0.0, use_jit=True, integrator="rk4", **kw):
+            self.ph = (g, m1, m2, l1, l2, d1, d2, theta1, theta2)
+            self.x_target, self.Q, self.R, self.Q_f = x_target, Q, R, Q_f
+            super().__init__(n_x=4, n_u=1, dt=dt, use_jit=use_jit, integrator=integrator, **kw)
+
+        def _f_cont_fcn(self, x, u):
+            g, m1, m2, l1, l2, d1, d2, th1, th2 = self.ph
+            q1, q2, q1d, q2d = x[0], x[1], x[2], x[3]
+            c = m2 * l1 * l2
+            m11 = m1 * l1 * l1 / 4 + m2 * l1 * l1 + m2 * l2 * l2 / 4 + th1 + th2 + c * jnp.cos(q2)
+            m22 = m2 * l2 * l2 / 4 + th2
+            m12 = m22 + 0.5 * c * jnp.cos(q2)
+            s12 = jnp.sin(q1 + q2)
+            h1 = (u[0] + 0.5 * c * jnp.sin(q2) * (2 * q1d * q2d + q2d * q2d) - m2 * g * l2 / 2 * s12
+                  - (m2 * g * l1 + m1 * g * l1 / 2) * jnp.sin(q1) - d1 * q1d)
+            h2 = -0.5 * c * jnp.sin(q2) * q1d * q1d - m2 * g * l2 / 2 * s12 - d2 * q2d
+            det = m11 * m22 - m12 * m12
+            return jnp.array([q1d, q2d, (m22 * h1 - m12 * h2) / det, (m11 * h2 - m12 * h1) / det])
+
+        def _l_fcn(self, x, u):
+            dx = x - self.x_target
+            return (0.5 * dx.T @ self.Q @ dx + 0.5 * u.T @ self.R @ u) * self.dt
+
+        def _l_f_fcn(self, x):
+            dx = x - self.x_target
+            return 0.5 * dx.T @ self.Q_f @ dx
+
+    return UserUADoublePendulum
