@@ -243,3 +243,43 @@ def test_lazy_wave_line_search_is_exact():
     for name in ("2224", "ones", "37", "big"):
         for a, b in zip(out["eager"], out[name]):
             assert np.array_equal(a, b), name
+
+
+@pytest.mark.parametrize("B,N,maxiter", [(1, 1, 3), (33, 2, 4), (31, 7, 0), (97, 60, 6), (1, 60, 6)])
+def test_edge_shapes_vs_oracle(oracle, B, N, maxiter):
+    """ragged batches (not a multiple of the warp size), a single trajectory with a batch axis, horizons of one and
+    two steps, and maxiter = 0 (optimize_trajectory returns the alpha = 0 rollout, iLQR_class.py:257-263)"""
+    from class_files.iLQR_class import iLQR
+    x0 = cfg2_x0(B, seed=11)
+    rng = np.random.default_rng(12)
+    U0 = 0.5 * rng.standard_normal((B, 1, N))
+    sol = iLQR(ua_system(), N * 0.01, x0, U0, maxiter=maxiter, verbose=False)
+    assert sol.N == N
+    X, U, cost = sol.optimize_trajectory()
+    assert X.shape == (B, 4, N + 1) and U.shape == (B, 1, N) and cost.shape == (B,)
+    ref = oracle.optimize_batch(ua_oracle_problem(oracle, N, maxiter=maxiter), x0, U0)
+    assert np.array_equal(sol.iterations, ref["iters"])
+    assert np.array_equal(sol.status, ref["status"])
+    assert rel_err(cost, ref["cost"]) < TOL and rel_err(X, ref["X"]) < TOL and rel_err(U, ref["U"], floor=1e-3) < TOL
+    if maxiter == 0:
+        assert np.all(sol.iterations == 0) and np.array_equal(U, U0)
+    else:
+        assert rel_err(sol.K, ref["K"]) < 1e-8
+
+
+def test_nan_initial_state_fails_line_search_like_python():
+    """NaN costs compare false in `cost_new <= cost` (iLQR_class.py:289): the trajectory ends with a failed line
+    search after one backward pass, and its neighbours in the batch are unaffected"""
+    from class_files.iLQR_class import iLQR
+    B, N = 40, 30
+    x0 = cfg2_x0(B, seed=13)
+    clean = iLQR(ua_system(), 0.3, x0, np.zeros((1, N)), maxiter=5, verbose=False)
+    Xc, Uc, cc = clean.optimize_trajectory()
+    x0n = x0.copy()
+    x0n[17, 2] = np.nan
+    sol = iLQR(ua_system(), 0.3, x0n, np.zeros((1, N)), maxiter=5, verbose=False)
+    X, U, cost = sol.optimize_trajectory()
+    assert sol.status[17] == 1 and sol.iterations[17] == 1 and np.isnan(cost[17])
+    keep = np.arange(B) != 17
+    assert np.array_equal(X[keep], Xc[keep]) and np.array_equal(cost[keep], cc[keep])
+    assert np.array_equal(sol.status[keep], clean.status[keep])
