@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="trajectories per GPU")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="trajectories per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true",
+                    help="secondary runs only (e.g. --batch 131072 on 8 GPUs = config 5): skip the host-in/host-out arm")
     ap.add_argument("--large-batch", type=int, default=131072,
                     help="N=1 only: also time a few steps at this batch (config 5's per-GPU shard at 8 GPUs), where "
                          "the passes are throughput bound; reported under 'large_batch'.  0 disables.")
@@ -209,16 +211,18 @@ def main():
     x0_dev = torch.as_tensor(x0_host).cuda()
     U_dev = torch.zeros((1, N_H), dtype=torch.float64, device="cuda")
     sol = iLQR(sysm, T_H, x0_dev, U_dev, tol=0.0, maxiter=ITERS, verbose=False, n_alpha=N_ALPHA)
-    gathered = [torch.empty(B, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
-    flags = [torch.empty(B, dtype=torch.int32, device="cuda") for _ in range(world)] if world > 1 else None
+    # the path's only exchange: per-shard cost and exit status, packed into ONE NCCL all-gather per step
+    pack = torch.empty((2, B), dtype=torch.float64, device="cuda") if world > 1 else None
+    gathered = torch.empty((world, 2, B), dtype=torch.float64, device="cuda") if world > 1 else None
 
     def step_device():
         sol.reset_state()
         sol._U.zero_()
         units = sol.solve_device(sync=True)
-        if world > 1:      # the path's only exchange: per-shard cost and convergence flags
-            dist.all_gather(gathered, sol._cost)
-            dist.all_gather(flags, sol._status)
+        if world > 1:
+            pack[0].copy_(sol._cost)
+            pack[1].copy_(sol._status)
+            dist.all_gather_into_tensor(gathered, pack)
         return units
 
     def barrier():
@@ -257,38 +261,31 @@ def main():
     sol.set_profiling(False)
 
     # ---- end-to-end arm: host numpy in, host numpy out through the public API -----------------------
-    sol_h = iLQR(sysm, T_H, x0_host, U_host, tol=0.0, maxiter=ITERS, verbose=False, n_alpha=N_ALPHA)
+    te, units_e, h2d, d2h = float("nan"), 0, 0, 0
+    sol_h = None
+    if not args.skip_e2e:
+        sol_h = iLQR(sysm, T_H, x0_host, U_host, tol=0.0, maxiter=ITERS, verbose=False, n_alpha=N_ALPHA)
 
-    def step_e2e():
-        sol_h.x_0 = x0_host                   # H2D
-        sol_h.U = U_host                      # H2D
-        sol_h.reset_state()
-        X, U, cost = sol_h.optimize_trajectory()   # D2H of X, U, cost
-        return sol_h.total_iterations, X, U, cost
+        def step_e2e():
+            sol_h.x_0 = x0_host                   # H2D
+            sol_h.U = U_host                      # H2D
+            sol_h.reset_state()
+            X, U, cost = sol_h.optimize_trajectory()   # D2H of X, U, cost
+            return sol_h.total_iterations, X, U, cost
 
-    for _ in range(max(3, args.warmup)):
-        # keep the results alive across steps exactly as the timed loop does, so that the pinned staging
-        # buffers of the steady state (two per output) exist before the clock starts
-        u, X, U, cost = step_e2e()
-    barrier()
-    prof = None
-    if os.environ.get("BENCH_PROFILE_E2E"):
-        import cProfile
-        prof = cProfile.Profile()
-        prof.enable()
-    te0 = time.perf_counter()
-    units_e = 0
-    for _ in range(args.steps):
-        u, X, U, cost = step_e2e()
-        units_e += u
-    barrier()
-    te = time.perf_counter() - te0
-    if prof:
-        import pstats
-        prof.disable()
-        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(12)
-    h2d = x0_host.nbytes + U_host.nbytes
-    d2h = X.nbytes + U.nbytes + cost.nbytes
+        for _ in range(max(3, args.warmup)):
+            # keep the results alive across steps exactly as the timed loop does, so that the pinned staging
+            # buffers of the steady state (two per output) exist before the clock starts
+            u, X, U, cost = step_e2e()
+        barrier()
+        te0 = time.perf_counter()
+        for _ in range(args.steps):
+            u, X, U, cost = step_e2e()
+            units_e += u
+        barrier()
+        te = time.perf_counter() - te0
+        h2d = x0_host.nbytes + U_host.nbytes
+        d2h = X.nbytes + U.nbytes + cost.nbytes
 
     # ---- N=1 only: the same solve at config 5's per-GPU shard size (HBM/FP64-throughput-bound regime) ------
     large = None
@@ -363,8 +360,8 @@ def main():
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
            "traj_iterations_per_step": units / args.steps,
-           "e2e": {"value": units_e / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": te / args.steps * 1e3},
+           "e2e": None if args.skip_e2e else {"value": units_e / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                                              "d2h_bytes_per_step": int(d2h), "ms_per_step": te / args.steps * 1e3},
            "gpu_launches": int(launches), "roofline": roof, "roofline_backward": roof_b, "kernels": kern,
            "large_batch": large, "cpu_baseline": cpu, "clocks": clocks}
     if large:

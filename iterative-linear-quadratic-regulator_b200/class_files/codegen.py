@@ -154,8 +154,10 @@ struct UserCost {{
 
 def _sources_digest():
     h = hashlib.sha1()
-    for rel in ("csrc/ilqr_b200.cu", "csrc/ilqr_systems.cuh"):
-        h.update(open(os.path.join(_PKG, rel), "rb").read())
+    csrc = os.path.join(_PKG, "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(csrc, name), "rb").read())
     h.update(open(os.path.join(_ROOT, "include", "ilqr_b200.h"), "rb").read())
     return h.hexdigest()
 

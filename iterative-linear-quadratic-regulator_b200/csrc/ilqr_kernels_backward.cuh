@@ -1,0 +1,590 @@
+// ilqr_kernels_backward.cuh -- K2, the reverse Riccati scan: thread-per-trajectory kernel with a cp.async ring, four-lane
+// kernel for small batches of n=4/m=1, sixteen-lane kernel for the n=12/m=4 LTV model
+// Part of libilqr_b200.so; included by ilqr_b200.cu only (see the file map at its top).
+#pragma once
+#include "ilqr_systems.cuh"
+#include "ilqr_kernels_common.cuh"
+
+namespace ilqr {
+
+// K2.  One thread per trajectory; V_x, V_xx live in registers for the whole scan.  The scan is
+// sequential in t, so at small batches a warp cannot hide HBM latency by occupancy: each thread
+// streams its own A_t, B_t, x_t, u_t through a DEPTH-deep shared-memory ring with cp.async
+// (LDGSTS), DEPTH-1 timesteps ahead of the arithmetic.  A thread only ever reads the ring slots it
+// filled itself, so cp.async.wait_group is the only synchronisation needed (no block barrier).
+template <typename T, int n, int m>
+struct BwdIn { T A[n][n], Bd[n][m], x[n], u[m]; };
+
+template <int BYTES>
+ILQR_DEV void cp_async(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+ILQR_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING> ILQR_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+// rows of one ring stage: A (n*n), Bd (n*m), x (n), u (m); element [row][tid]
+template <typename T, int n, int m>
+ILQR_DEV void bwd_issue(T *stage, int t, int b, int B, const T *__restrict__ X, const T *__restrict__ U,
+                        const T *__restrict__ A, const T *__restrict__ Bd)
+{
+    const int bd = blockDim.x, tid = threadIdx.x;
+    int row = 0;
+#pragma unroll
+    for (int i = 0; i < n * n; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, A + ((size_t)t * n * n + i) * B + b);
+#pragma unroll
+    for (int i = 0; i < n * m; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, Bd + ((size_t)t * n * m + i) * B + b);
+#pragma unroll
+    for (int i = 0; i < n; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, X + ((size_t)t * n + i) * B + b);
+#pragma unroll
+    for (int i = 0; i < m; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, U + ((size_t)t * m + i) * B + b);
+}
+
+template <typename T, int n, int m>
+ILQR_DEV void bwd_read(BwdIn<T, n, m> &d, const T *stage)
+{
+    const int bd = blockDim.x, tid = threadIdx.x;
+    int row = 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < n; ++j, ++row) d.A[i][j] = stage[row * bd + tid];
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < m; ++j, ++row) d.Bd[i][j] = stage[row * bd + tid];
+#pragma unroll
+    for (int i = 0; i < n; ++i, ++row) d.x[i] = stage[row * bd + tid];
+#pragma unroll
+    for (int j = 0; j < m; ++j, ++row) d.u[j] = stage[row * bd + tid];
+}
+
+template <class Cost, typename T, int n, int m, int DEPTH>
+__global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, const T *__restrict__ X,
+                                const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
+                                T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
+                                const unsigned int *__restrict__ gate, const T *__restrict__ mu)
+{
+    constexpr int L = n * n + n * m + n + m;
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    T *ring = reinterpret_cast<T *>(ring_raw);
+    if (gate && *gate == 0u) return;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (active && !active[b]) return;
+    const int stage_elems = L * blockDim.x;
+#pragma unroll
+    for (int s = 0; s < DEPTH; ++s) {
+        if (N - 1 - s >= 0) bwd_issue<T, n, m>(ring + s * stage_elems, N - 1 - s, b, B, X, U, A, Bd);
+        cp_async_commit();
+    }
+    const T mu_b = mu ? mu[b] : T(0);                                    // regularisation (RegArgs), 0 in the reference
+    T Vx[n], Vxx[n][n];
+    {
+        T xN[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) xN[i] = X[((size_t)N * n + i) * B + b];
+        if constexpr (Cost::QUADRATIC) {
+            qc.terminal_grad(xN, Vx);                                    // iLQR_class.py:136-138
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+#pragma unroll
+                for (int j = 0; j < n; ++j) Vxx[i][j] = qc.Qfs[i][j];
+        } else {
+            qc.terminal_expand(xN, Vx, Vxx);
+        }
+    }
+    BwdIn<T, n, m> cur;
+    int stage = 0;
+    for (int t = N - 1; t >= 0; --t) {
+        cp_async_wait<DEPTH - 1>();                                       // the group holding step t has landed
+        bwd_read(cur, ring + stage * stage_elems);
+        T lx[n], lu[m];
+        // quadratic costs: l_xx = Q dt, l_uu = R dt, l_ux = 0 are constants folded into the sums below;
+        // generated user costs (ilqr_user.cuh) provide the full state-dependent expansion
+        [[maybe_unused]] T lxx[Cost::QUADRATIC ? 1 : n][Cost::QUADRATIC ? 1 : n];
+        [[maybe_unused]] T luu[Cost::QUADRATIC ? 1 : m][Cost::QUADRATIC ? 1 : m];
+        [[maybe_unused]] T lux[Cost::QUADRATIC ? 1 : m][Cost::QUADRATIC ? 1 : n];
+        if constexpr (Cost::QUADRATIC) qc.grad(cur.x, cur.u, lx, lu);
+        else qc.expand(cur.x, cur.u, lx, lu, lxx, luu, lux);
+        // Q_x = l_x + f_x' V_x ; Q_u = l_u + f_u' V_x                    (:100-101)
+        T Qx[n], Qu[m];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T s = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) s += cur.A[l][i] * Vx[l];
+            Qx[i] = lx[i] + s;
+        }
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+            T s = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) s += cur.Bd[l][j] * Vx[l];
+            Qu[j] = lu[j] + s;
+        }
+        // T1 = f_x' V_xx, T2 = f_u' V_xx ; Q_xx = l_xx + T1 f_x ; Q_ux = T2 f_x ; Q_uu = l_uu + T2 f_u   (:102-104)
+        T T1[n][n], T2[m][n], Qxx[n][n], Qux[m][n], Quu[m][m];
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int l = 0; l < n; ++l) s += cur.A[l][i] * Vxx[l][j];
+                T1[i][j] = s;
+            }
+#pragma unroll
+        for (int i = 0; i < m; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int l = 0; l < n; ++l) s += cur.Bd[l][i] * Vxx[l][j];
+                T2[i][j] = s;
+            }
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int l = 0; l < n; ++l) s += T1[i][l] * cur.A[l][j];
+                if constexpr (Cost::QUADRATIC) Qxx[i][j] = qc.Qs[i][j] * qc.dt + s;
+                else Qxx[i][j] = lxx[i][j] + s;
+            }
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int l = 0; l < n; ++l) s += T2[i][l] * cur.A[l][j];
+                if constexpr (Cost::QUADRATIC) Qux[i][j] = s;            // l_ux = 0 for the quadratic cost
+                else Qux[i][j] = lux[i][j] + s;
+            }
+#pragma unroll
+            for (int j = 0; j < m; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int l = 0; l < n; ++l) s += T2[i][l] * cur.Bd[l][j];
+                if constexpr (Cost::QUADRATIC) Quu[i][j] = qc.Rs[i][j] * qc.dt + s;
+                else Quu[i][j] = luu[i][j] + s;
+                if (i == j) Quu[i][j] += mu_b;
+            }
+        }
+        // K = -Q_uu^-1 Q_ux, k = -Q_uu^-1 Q_u                            (:109-110; no regularisation)
+        T Kt[m][n], kt[m];
+        if (m == 1) {
+            const T r = -rcp_t(Quu[0][0]);
+#pragma unroll
+            for (int j = 0; j < n; ++j) Kt[0][j] = Qux[0][j] * r;
+            kt[0] = Qu[0] * r;
+        } else {
+            T rhs[m][n + 1];
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+#pragma unroll
+                for (int j = 0; j < n; ++j) rhs[i][j] = Qux[i][j];
+                rhs[i][n] = Qu[i];
+            }
+            T Lm[m][m];
+#pragma unroll
+            for (int i = 0; i < m; ++i)
+#pragma unroll
+                for (int j = 0; j < m; ++j) Lm[i][j] = Quu[i][j];
+            lu_solve_inplace<m, n + 1>(Lm, rhs);
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+#pragma unroll
+                for (int j = 0; j < n; ++j) Kt[i][j] = -rhs[i][j];
+                kt[i] = -rhs[i][n];
+            }
+        }
+        // V_x = Q_x + K' Q_u ; V_xx = Q_xx + Q_ux' K                      (:113-114; not symmetrised)
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T s = T(0);
+#pragma unroll
+            for (int j = 0; j < m; ++j) s += Kt[j][i] * Qu[j];
+            Vx[i] = Qx[i] + s;
+#pragma unroll
+            for (int c = 0; c < n; ++c) {
+                T s2 = T(0);
+#pragma unroll
+                for (int j = 0; j < m; ++j) s2 += Qux[j][i] * Kt[j][c];
+                Vxx[i][c] = Qxx[i][c] + s2;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) K[(((size_t)t * m + j) * n + i) * B + b] = Kt[j][i];
+            k[((size_t)t * m + j) * B + b] = kt[j];
+        }
+        if (t - DEPTH >= 0) bwd_issue<T, n, m>(ring + stage * stage_elems, t - DEPTH, b, B, X, U, A, Bd);
+        cp_async_commit();
+        stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
+    }
+}
+
+// K2, small-batch variant for n = 4, m = 1 (the double-pendulum headline case): FOUR lanes per
+// trajectory.  With a few thousand trajectories the one-thread-per-trajectory scan runs one warp per
+// SM and is bound by dependent-instruction issue (~490 instructions per step in one thread).  Here
+// lane j of a 4-lane group owns column j: it computes Y[:,j] = V_xx A[:,j], Q_xx[:,j] = l_xx[:,j] +
+// A' Y[:,j], Q_ux[j] = B' Y[:,j], Q_x[j], K[j] and the new V_xx[:,j], V_x[j]; Q_uu, Q_u, k are cheap and
+// computed redundantly.  Every lane keeps a full copy of V_xx, V_x, re-assembled each step through a
+// shared-memory exchange (two __syncwarp per step).  A warp holds 8 trajectories; their A_t,B_t,x_t,u_t
+// (25 values each) arrive through a DEPTH-deep cp.async ring filled cooperatively (7 LDGSTS per step
+// per warp, 64-byte global segments).  ~115 instructions per lane per step.
+template <typename T, int DEPTH>
+__global__ void __launch_bounds__(32)
+backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, int B, const T *__restrict__ X,
+                           const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
+                           T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
+                           const unsigned int *__restrict__ gate, const T *__restrict__ mu)
+{
+    constexpr int n = 4, L = 25, LP = 26, SLOTS = 8;       // LP: padded slot stride (bank-conflict free LDS.128)
+    extern __shared__ __align__(16) unsigned char lanes_raw[];
+    T *ring = reinterpret_cast<T *>(lanes_raw);             // [DEPTH][SLOTS][LP]
+    T *exQ = ring + DEPTH * SLOTS * LP;                     // [SLOTS][4]   Q_ux exchange
+    T *exV = exQ + SLOTS * 4;                               // [SLOTS][20]  V_xx (row-major 16) + V_x (4)
+    if (gate && *gate == 0u) return;
+    const int lane = threadIdx.x, s = lane >> 2, j = lane & 3;
+    const int b_raw = blockIdx.x * SLOTS + s;
+    const bool valid = b_raw < B && (!active || active[b_raw < B ? b_raw : B - 1] != 0);
+    if (__ballot_sync(0xffffffffu, valid) == 0u) return;
+    const int b = b_raw < B ? b_raw : B - 1;                // clamped: out-of-range slots compute on a copy, never store
+
+    // cooperative fill of one ring stage: element e = row * 8 + slot, 32 elements per LDGSTS
+    const int f_slot = lane & 7, f_row0 = lane >> 3;
+    const int f_b = min(blockIdx.x * SLOTS + f_slot, B - 1);
+    auto issue = [&](int stage, int t) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int row = f_row0 + 4 * i;
+            if (row < L) {
+                const T *src = row < 16 ? A + ((size_t)t * 16 + row) * B + f_b
+                             : row < 20 ? Bd + ((size_t)t * 4 + (row - 16)) * B + f_b
+                             : row < 24 ? X + ((size_t)t * 4 + (row - 20)) * B + f_b
+                                        : U + (size_t)t * B + f_b;
+                cp_async<sizeof(T)>(ring + (stage * SLOTS + f_slot) * LP + row, src);
+            }
+        }
+    };
+#pragma unroll
+    for (int st = 0; st < DEPTH; ++st) {
+        if (N - 1 - st >= 0) issue(st, N - 1 - st);
+        cp_async_commit();
+    }
+    // per-lane constants: row j of dt*Qs (for l_x[j]) and column j of dt*Qs (for l_xx[:,j])
+    T qrow[n], qcol[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) { qrow[i] = qc.Qs[j][i] * qc.dt; qcol[i] = qc.Qs[i][j] * qc.dt; }
+    const T xtj[n] = { qc.xt[0], qc.xt[1], qc.xt[2], qc.xt[3] };
+    const T luu = qc.Rs[0][0] * qc.dt;
+    const T mu_b = mu ? mu[b] : T(0);                                    // regularisation (RegArgs), 0 in the reference
+    T Vx[n], Vxx[n][n];
+    {
+        T xN[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) xN[i] = X[((size_t)N * n + i) * B + b];
+        qc.terminal_grad(xN, Vx);                                        // iLQR_class.py:136-138
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int c = 0; c < n; ++c) Vxx[i][c] = qc.Qfs[i][c];
+    }
+    int stage = 0;
+    for (int t = N - 1; t >= 0; --t) {
+        cp_async_wait<DEPTH - 1>();
+        __syncwarp();                                                    // other lanes' copies are visible
+        const T *in = ring + (stage * SLOTS + s) * LP;
+        T Am[n][n], Bv[n], x[n], Acol[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int c = 0; c < n; ++c) Am[i][c] = in[i * 4 + c];
+            Bv[i] = in[16 + i];
+            x[i] = in[20 + i];
+            Acol[i] = in[i * 4 + j];
+        }
+        const T u = in[24];
+        // Y = V_xx A[:,j] ; Q_xx[:,j] = l_xx[:,j] + A' Y ; Q_ux[j] = B' Y          (iLQR_class.py:102-103)
+        T Y[n], Qxxc[n], Quxj = T(0), Qxj = T(0), Qu = T(0), Quu = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T sum = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) sum += Vxx[i][l] * Acol[l];
+            Y[i] = sum;
+        }
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T sum = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) sum += Am[l][i] * Y[l];
+            Qxxc[i] = qcol[i] + sum;
+            Quxj += Bv[i] * Y[i];
+        }
+        // Q_uu = l_uu + B' V_xx B, Q_u = l_u + B' V_x (redundant in the 4 lanes) ; Q_x[j]   (:100-101,104)
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T vb = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) vb += Vxx[i][l] * Bv[l];
+            Quu += Bv[i] * vb;
+            Qu += Bv[i] * Vx[i];
+            Qxj += Acol[i] * Vx[i];
+        }
+        Quu += luu;
+        Quu += mu_b;
+        Qu += luu * u;
+        T lxj = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) lxj += qrow[i] * (x[i] - xtj[i]);
+        Qxj += lxj;
+        const T r = -rcp_t(Quu);                                         // (:109-110)
+        const T Kj = Quxj * r, kk = Qu * r;
+        const T Vxj = Qxj + Kj * Qu;                                     // (:113)
+        exQ[s * 4 + j] = Quxj;
+        __syncwarp();
+        T Quxa[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) Quxa[i] = exQ[s * 4 + i];
+#pragma unroll
+        for (int i = 0; i < n; ++i) exV[s * 20 + i * 4 + j] = Qxxc[i] + Quxa[i] * Kj;     // V_xx[:,j]   (:114)
+        exV[s * 20 + 16 + j] = Vxj;
+        if (valid) {
+            K[((size_t)t * n + j) * B + b] = Kj;
+            if (j == 0) k[(size_t)t * B + b] = kk;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int c = 0; c < n; ++c) Vxx[i][c] = exV[s * 20 + i * 4 + c];
+            Vx[i] = exV[s * 20 + 16 + i];
+        }
+        if (t - DEPTH >= 0) issue(stage, t - DEPTH);                     // every lane is past its reads of this stage
+        cp_async_commit();
+        stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
+    }
+}
+
+// K2 for the synthetic LTV system (n = 12, m = 4; BASELINE.json config 4).  One thread per trajectory
+// would need V_xx alone in 288 registers, so SIXTEEN lanes share a trajectory: lane c owns column c of
+// [A_t | B_t] (12 + 4 columns).  A_t = I + dt (Ac + w_t E) is generated in the kernel from the constants and
+// the trajectory's phase -- it is never read from (or written to) HBM -- and B_t = dt Bc is constant.
+// Per step lane c computes
+//     W[:,c]  = V_xx [A|B][:,c]                    (V_xx read from shared memory, 16-byte broadcasts)
+//     G[:,c]  = [A|B]' W[:,c]                       (A' from shared memory, B' constant)
+//               -> c < 12: Q_xx[:,c], Q_ux[:,c]      c >= 12: Q_uu[:,c-12]          (iLQR_class.py:102-104)
+//     Q_x[c] / Q_u[c-12]                                                             (:100-101)
+// then every lane factors the 4x4 Q_uu (LU, partial pivoting, as the reference's solve) and solves for its
+// own right-hand side: K[:,c] (c < 12) or k (:109-110), and writes its column of the new V_xx and V_x[c]
+// (:113-114).  TPB trajectories per block; the 52 gain values of a step go through a shared-memory stage so
+// that every global store is a row of TPB consecutive trajectories (full 128-byte lines for TPB = 16); x_t,
+// u_t arrive the same way, prefetched one step ahead.  One block barrier per step.
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+#ifndef ILQR_LTV_MINBLOCKS
+#define ILQR_LTV_MINBLOCKS 2
+#endif
+template <typename T, int TPB>
+__global__ void __launch_bounds__(TPB * 16, ILQR_LTV_MINBLOCKS)
+backward_ltv_kernel(const __grid_constant__ LtvSys<T> sys, const __grid_constant__ QuadCost<T, 12, 4> qc, int N, int B,
+                    const T *__restrict__ phi, const T *__restrict__ X, const T *__restrict__ U, T *__restrict__ K,
+                    T *__restrict__ k, const int *__restrict__ active, const unsigned int *__restrict__ gate,
+                    const T *__restrict__ mu)
+{
+    constexpr int n = 12, m = 4, NT = TPB * 16, ROWS = n * m + m;   // 52 gain rows per step
+    using V2 = typename Vec2<T>::type;
+    extern __shared__ __align__(16) unsigned char ltv_raw[];
+    T *sm = reinterpret_cast<T *>(ltv_raw);
+    T *VxxS = sm;                       // [TPB][12][12]  row-major V_xx
+    T *ATS = VxxS + TPB * 144;          // [TPB][12][12]  ATS[i][l] = A[l][i]
+    T *VxS = ATS + TPB * 144;           // [TPB][12]
+    T *QuxS = VxS + TPB * 12;           // [TPB][4][12]
+    T *QuuS = QuxS + TPB * 48;          // [TPB][4][4]
+    T *QuS = QuuS + TPB * 16;           // [TPB][4]
+    T *xsS = QuS + TPB * 4;             // [2][TPB][16]   x_t (12), u_t (4), double buffered
+    T *KS = xsS + 2 * TPB * 16;         // [2][52][TPB]   gain stage, double buffered
+    T *BdT = KS + 2 * ROWS * TPB;       // [4][12]        BdT[j][l] = dt Bc[l][j]
+    T *QsS = BdT + 48;                  // [12][12]       symmetrised Q
+    T *RsS = QsS + 144;                 // [4][4]
+    T *AcT = RsS + 16;                  // [12][12]       AcT[c][l] = Ac[l][c]
+    T *ET = AcT + 144;                  // [12][12]       ET[c][l]  = E[l][c]
+    __shared__ int vflag[TPB];
+    if (gate && *gate == 0u) return;
+    const int tid = threadIdx.x, s = tid >> 4, c = tid & 15;
+    const int b0 = blockIdx.x * TPB;
+    const int b_raw = b0 + s;
+    const bool valid = b_raw < B && (!active || active[b_raw] != 0);
+    if (__syncthreads_or(valid) == 0) return;
+    const int b = b_raw < B ? b_raw : B - 1;        // out-of-range / inactive slots compute on a copy, never store
+    if (c == 0) vflag[s] = valid;
+    for (int e = tid; e < 48; e += NT) BdT[e] = qc.dt * sys.Bc[e % 12][e / 12];
+    for (int e = tid; e < 144; e += NT) {
+        QsS[e] = qc.Qs[e / 12][e % 12];
+        AcT[e] = sys.Ac[e % 12][e / 12];
+        ET[e] = sys.E[e % 12][e / 12];
+    }
+    if (tid < 16) RsS[tid] = qc.Rs[tid >> 2][tid & 3];
+    // staged loads: thread (r, bb) fetches row r (x_0..x_11, u_0..u_3) of trajectory b0 + bb
+    const int ld_r = tid / TPB, ld_bb = tid % TPB;
+    const int ld_b = min(b0 + ld_bb, B - 1);
+    auto fetch = [&](int t) -> T {
+        if (ld_r < n) return X[((size_t)t * n + ld_r) * B + ld_b];
+        return t < N ? U[((size_t)t * m + (ld_r - n)) * B + ld_b] : T(0);
+    };
+    // column c of [A_t | B_t]: rebuilt every step from AcT/ET (c < 12), constant dt Bc[:,c-12] otherwise
+    T M[n];
+#pragma unroll
+    for (int l = 0; l < n; ++l) M[l] = c < n ? T(0) : qc.dt * sys.Bc[l][c - n];
+    const T ph = phi ? phi[b] : T(0);
+    const T mu_b = mu ? mu[b] : T(0);                                    // regularisation (RegArgs), 0 in the reference
+    T w = sys.time_scalar(N - 1, ph);
+    T *Vxx = VxxS + s * 144, *AT = ATS + s * 144, *Vx = VxS + s * 12, *Qux = QuxS + s * 48, *Quu = QuuS + s * 16,
+      *Qu = QuS + s * 4;
+    // terminal condition (iLQR_class.py:136-138): V_x = Q_f (x_N - x_target), V_xx = Q_f
+    xsS[ld_bb * 16 + ld_r] = fetch(N);
+    __syncthreads();
+    if (c < n) {
+        T g = T(0);
+#pragma unroll
+        for (int j = 0; j < n; ++j) g += qc.Qfs[c][j] * (xsS[s * 16 + j] - qc.xt[j]);
+        Vx[c] = g;
+#pragma unroll
+        for (int i = 0; i < n; ++i) Vxx[i * 12 + c] = qc.Qfs[i][c];
+    }
+    T pre = fetch(N - 1);
+    __syncthreads();
+    xsS[TPB * 16 + ld_bb * 16 + ld_r] = pre;        // buffer 1 holds step N-1 (buffer index = (N - t) & 1)
+    __syncthreads();
+    for (int t = N - 1; t >= 0; --t) {
+        const int buf = (N - t) & 1;
+        const T *xs = xsS + buf * TPB * 16 + s * 16;
+        if (t > 0) pre = fetch(t - 1);
+        if (c < n) {
+#pragma unroll
+            for (int l = 0; l < n; l += 2) {
+                const V2 a = *reinterpret_cast<const V2 *>(AcT + c * 12 + l), e = *reinterpret_cast<const V2 *>(ET + c * 12 + l);
+                M[l] = ((l == c) ? T(1) : T(0)) + qc.dt * (a.x + w * e.x);
+                M[l + 1] = ((l + 1 == c) ? T(1) : T(0)) + qc.dt * (a.y + w * e.y);
+                *reinterpret_cast<V2 *>(AT + c * 12 + l) = V2{M[l], M[l + 1]};
+            }
+        }
+        __syncwarp();
+        if (t > 0) w = sys.time_scalar(t - 1, ph);      // next step's scalar: independent work for the solve's latency
+        // W[:,c] = V_xx [A|B][:,c]
+        T W[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            T acc = T(0);
+#pragma unroll
+            for (int l = 0; l < n; l += 2) {
+                const V2 v = *reinterpret_cast<const V2 *>(Vxx + i * 12 + l);
+                acc += v.x * M[l];
+                acc += v.y * M[l + 1];
+            }
+            W[i] = acc;
+        }
+        // G = [A|B]' W[:,c]
+        T G[n + m];
+#pragma unroll
+        for (int r = 0; r < n + m; ++r) {
+            const T *row = r < n ? AT + r * 12 : BdT + (r - n) * 12;
+            T acc = T(0);
+#pragma unroll
+            for (int l = 0; l < n; l += 2) {
+                const V2 v = *reinterpret_cast<const V2 *>(row + l);
+                acc += v.x * W[l];
+                acc += v.y * W[l + 1];
+            }
+            G[r] = acc;
+        }
+        // q = [A|B][:,c]' V_x ; cost gradient entry of this lane
+        T q = T(0);
+#pragma unroll
+        for (int l = 0; l < n; ++l) q += M[l] * Vx[l];
+        T rhs[m][1], Qc;
+        if (c < n) {
+            T g = T(0);
+            if (qc.diag) g = QsS[c * 12 + c] * (xs[c] - qc.xt[c]);
+            else {
+#pragma unroll
+                for (int j = 0; j < n; ++j) g += QsS[c * 12 + j] * (xs[j] - qc.xt[j]);
+            }
+            Qc = g * qc.dt + q;                                          // Q_x[c]
+#pragma unroll
+            for (int i = 0; i < n; ++i) G[i] = QsS[i * 12 + c] * qc.dt + G[i];          // Q_xx[:,c]
+#pragma unroll
+            for (int j = 0; j < m; ++j) { Qux[j * 12 + c] = G[n + j]; rhs[j][0] = G[n + j]; }
+        } else {
+            const int jj = c - n;
+            T g = T(0);
+            if (qc.diag) g = RsS[jj * 4 + jj] * xs[n + jj];
+            else {
+#pragma unroll
+                for (int i = 0; i < m; ++i) g += RsS[jj * 4 + i] * xs[n + i];
+            }
+            Qc = g * qc.dt + q;                                          // Q_u[c-12]
+            Qu[jj] = Qc;
+#pragma unroll
+            for (int i = 0; i < m; ++i)
+                Quu[i * 4 + jj] = (RsS[i * 4 + jj] * qc.dt + G[n + i]) + (i == jj ? mu_b : T(0));            // Q_uu[:,c-12]
+        }
+        __syncwarp();
+        // K[:,c] = -Q_uu^-1 Q_ux[:,c] (c < 12) ; k = -Q_uu^-1 Q_u (lanes 12..15, lane 12+j keeps k[j])
+        T Lm[m][m], Quv[m];
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+#pragma unroll
+            for (int j = 0; j < m; ++j) Lm[i][j] = Quu[i * 4 + j];
+            Quv[i] = Qu[i];
+            if (c >= n) rhs[i][0] = Quv[i];
+        }
+        lu_solve_inplace<m, 1, T, true>(Lm, rhs);
+        T *ks = KS + ((N - t) & 1) * ROWS * TPB;
+        if (c < n) {
+            // V_xx[:,c] = Q_xx[:,c] + Q_ux' K[:,c] ; V_x[c] = Q_x[c] + K[:,c]' Q_u
+            T Kc[m];
+#pragma unroll
+            for (int j = 0; j < m; ++j) Kc[j] = -rhs[j][0];
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                T acc = T(0);
+#pragma unroll
+                for (int j = 0; j < m; ++j) acc += Qux[j * 12 + i] * Kc[j];
+                G[i] += acc;
+            }
+            T vx = T(0);
+#pragma unroll
+            for (int j = 0; j < m; ++j) vx += Kc[j] * Quv[j];
+            vx = Qc + vx;
+#pragma unroll
+            for (int i = 0; i < n; ++i) Vxx[i * 12 + c] = G[i];
+            Vx[c] = vx;
+#pragma unroll
+            for (int j = 0; j < m; ++j) ks[(j * n + c) * TPB + s] = Kc[j];
+        } else {
+            ks[(n * m + (c - n)) * TPB + s] = -rhs[c - n][0];
+        }
+        if (t > 0) xsS[(buf ^ 1) * TPB * 16 + ld_bb * 16 + ld_r] = pre;
+        __syncthreads();
+        // coalesced store of the step's gains: rows of TPB consecutive trajectories
+        for (int e = tid; e < ROWS * TPB; e += NT) {
+            const int row = e / TPB, bb = e % TPB;
+            if (vflag[bb]) {
+                if (row < n * m) K[((size_t)t * n * m + row) * B + b0 + bb] = ks[e];
+                else k[((size_t)t * m + (row - n * m)) * B + b0 + bb] = ks[e];
+            }
+        }
+    }
+}
+
+}  // namespace ilqr

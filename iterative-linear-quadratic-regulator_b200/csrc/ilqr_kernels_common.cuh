@@ -1,0 +1,69 @@
+// ilqr_kernels_common.cuh -- structures shared by the kernels: step-size list, iteration control block, speculation and
+// regularisation arguments
+// Part of libilqr_b200.so; included by ilqr_b200.cu only (see the file map at its top).
+#pragma once
+#include "ilqr_systems.cuh"
+#include "ilqr_b200.h"
+
+namespace ilqr {
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+
+struct AlphaList { double a[ILQR_MAX_ALPHAS]; };
+
+// iteration-control block living at the head of the workspace
+struct Control {
+    unsigned long long total_iters;          // sum over trajectories of backward passes executed
+    unsigned int n_active[1];                 // [maxiter + 2], n_active[it] = trajectories entering iteration it
+};
+
+// Speculative evaluation of the deferred (second-wave) step sizes.  Trajectories that needed a small
+// step in the previous iteration are put on a list by select_kernel; the first-wave rollout launch
+// carries `cap * n2` extra threads (the warp slots left over when the wave is sized to the SM
+// sub-partitions) that roll out the deferred step sizes for the listed trajectories, so that the
+// separate, latency-bound second wave is almost never needed.  Which rollouts are evaluated never
+// changes which one is accepted.
+struct SpecArgs {
+    int cap;                              // list capacity; 0 switches speculation off
+    int n2;                               // deferred step sizes per trajectory
+    int threshold;                        // accepted try index from which a trajectory is listed
+    int *list_cur, *list_next;            // [cap]
+    unsigned int *count_cur, *count_next; // entries appended this / next iteration (may exceed cap)
+    int *mark;                            // [B]: mark[b] == it + 1 <=> b is on the list of iteration it
+};
+
+// Levenberg-Marquardt regularisation of Q_uu, kept per trajectory on the device (an EXTENSION: the
+// reference has none, iLQR_class.py:109-110, and with factor <= 1 nothing here changes its behaviour).
+// The backward pass solves with Q_uu + mu I.  When the line search of an iteration accepts no step size,
+// the reference stops the solve (:304-307); with the schedule enabled the trajectory instead retries the
+// iteration with mu <- max(mu * factor, mu_min), and fails only once mu exceeds mu_max.  After an accepted
+// step mu <- mu / factor (snapped to 0 below mu_min).  All of it runs in the select kernels.
+struct RegArgs {
+    void *mu;                 // [B], T; nullptr <=> schedule disabled
+    double factor, mu_min, mu_max;
+};
+
+template <typename T>
+ILQR_DEV bool reg_on_failure(const RegArgs &rg, int b)
+{
+    // true: retry with a larger mu; false: give up (reference behaviour)
+    if (!rg.mu) return false;
+    T *mu = (T *)rg.mu;
+    const T next = mu[b] * (T)rg.factor > (T)rg.mu_min ? mu[b] * (T)rg.factor : (T)rg.mu_min;
+    if (next > (T)rg.mu_max) return false;
+    mu[b] = next;
+    return true;
+}
+
+template <typename T>
+ILQR_DEV void reg_on_success(const RegArgs &rg, int b)
+{
+    if (!rg.mu) return;
+    T *mu = (T *)rg.mu;
+    const T next = mu[b] / (T)rg.factor;
+    mu[b] = next < (T)rg.mu_min ? T(0) : next;
+}
+
+}  // namespace ilqr

@@ -59,7 +59,28 @@ ILQR_DEV void sincos_t(double x, double *s, double *c)
     *s = (k & 2) ? -a : a;
     *c = ((k + 1) & 2) ? -b : b;
 }
-ILQR_DEV void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
+// FP32 counterpart (optional 1e-4 mode): three-constant Cody-Waite reduction and the cephes sinf/cosf
+// polynomials on [-pi/4, pi/4]; ~2e-7 absolute error for |x| up to ~1e5, no slow path.
+ILQR_DEV void sincos_t(float x, float *s, float *c)
+{
+    const float magic = 12582912.0f;                         // 1.5 * 2^23: rounds to nearest integer
+    const float t = fmaf(x, 0.636619772f, magic);
+    const int k = __float_as_int(t);                         // the low mantissa bits hold the integer
+    const float kd = t - magic;
+    float r = fmaf(-kd, 1.5703125f, x);                      // pi/2 split in three parts (cephes DP1..DP3 * 2)
+    r = fmaf(-kd, 4.837512969970703125e-4f, r);
+    r = fmaf(-kd, 7.54978995489188216e-8f, r);
+    const float z = r * r;
+    float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(z, ps, -1.6666654611e-1f);
+    const float sn = fmaf(z * r, ps, r);
+    float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(z, pc, 4.166664568298827e-2f);
+    const float cs = fmaf(z * z, pc, fmaf(-0.5f, z, 1.0f));
+    const float a = (k & 1) ? cs : sn, b = (k & 1) ? sn : cs;
+    *s = (k & 2) ? -a : a;
+    *c = ((k + 1) & 2) ? -b : b;
+}
 ILQR_DEV double sin_t(double x) { double s, c; sincos_t(x, &s, &c); return s; }
 ILQR_DEV float sin_t(float x) { return sinf(x); }
 // reciprocal to ~1 ulp: MUFU seed + two Newton steps, no special-case path (the callers' arguments
@@ -73,7 +94,12 @@ ILQR_DEV double rcp_t(double d)
     e = fma(-d, y, 1.0);
     return fma(y, e, y);
 }
-ILQR_DEV float rcp_t(float d) { return 1.0f / d; }
+ILQR_DEV float rcp_t(float d)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
+    return fmaf(y, fmaf(-d, y, 1.0f), y);                    // one Newton step: ~1 ulp
+}
 ILQR_DEV double sqrt_t(double x) { return sqrt(x); }
 ILQR_DEV float sqrt_t(float x) { return sqrtf(x); }
 ILQR_DEV double abs_t(double x) { return fabs(x); }
