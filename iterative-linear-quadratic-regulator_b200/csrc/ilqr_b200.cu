@@ -122,6 +122,7 @@ struct Handle {
     int env_rollout_bs;       // ILQR_ROLLOUT_BS: 0 [auto] or a block size
     int env_check_every;      // ILQR_CHECK_EVERY: iterations enqueued between host polls of the active count [8]
     void *mu_user;            // optional caller buffer for the per-trajectory regularisation (ilqr_set_mu_buffer)
+    int sparse;               // lazy schedule: late iterations index the batch through the active list (SparseArgs)
     int lazy;                 // large batches: lazy multi-wave line search over compacted lists (select_lazy_kernel)
     int n_waves;
     int wave_lo[ILQR_MAX_WAVES + 1];
@@ -151,7 +152,7 @@ static inline int block_for(size_t threads)
 }
 
 struct WsLayout {
-    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, wslot, active, defer, mark, lists, mu, total;
+    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, wslot, active, defer, mark, lists, alists, mu, total;
 };
 
 static size_t ctl_bytes(int maxiter)
@@ -183,6 +184,7 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
     L.defer = off; off = al(off + 4 * B);
     L.mark = off; off = al(off + 4 * B);
     L.lists = off; off = al(off + 4 * 2 * B);     // two speculation lists (capacity <= B each)
+    L.alists = off; off = al(off + 4 * 2 * B);    // active lists of the current / next iteration (SparseArgs)
     L.mu = off; off = al(off + w * B);
     L.total = off;
     return L;
@@ -250,8 +252,12 @@ template <class F> static int dispatch(const Handle *h, F &&f)
 
 static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U, void *A, void *Bd, const void *Xc, const void *Uc,
                                    const int *winner, const int *wslot, const int *active, int do_lin, const unsigned int *g0,
-                                   const unsigned int *g1, cudaStream_t st)
+                                   const unsigned int *g1, cudaStream_t st, const int *iters = nullptr, int it = 0,
+                                   const SparseArgs *sparse = nullptr)
 {
+    SparseArgs sa;
+    std::memset(&sa, 0, sizeof sa);
+    if (sparse) sa = *sparse;
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
         using T = decltype(tz);
         using Sys = decltype(sys);
@@ -260,7 +266,7 @@ static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U,
         const int bs = 128;
         commit_linearize_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
             sys, qc.dt, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (T *)A, (T *)Bd, (const T *)Xc, (const T *)Uc, winner, wslot,
-            active, do_lin, g0, g1);
+            active, iters, it, do_lin, g0, g1, sa);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });
@@ -269,7 +275,7 @@ static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U,
 template <typename T, int n, int m, int DEPTH, class Cost>
 static int launch_backward_depth(Handle *h, int bs, const Cost &qc, const void *X, const void *U,
                                  const void *A, const void *Bd, void *K, void *k, const int *active,
-                                 const unsigned int *gate, const void *mu, cudaStream_t st)
+                                 const unsigned int *gate, const void *mu, cudaStream_t st, const SparseArgs &sa)
 {
     constexpr int L = n * n + n * m + n + m;
     const size_t smem = (size_t)DEPTH * L * bs * sizeof(T);
@@ -282,39 +288,50 @@ static int launch_backward_depth(Handle *h, int bs, const Cost &qc, const void *
     }
     backward_kernel<Cost, T, n, m, DEPTH><<<grid_for(h->p.B, bs), bs, smem, st>>>(
         qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active, gate,
-        (const T *)mu);
+        (const T *)mu, sa);
     ILQR_CHECK_LAUNCH(h);
     return ILQR_OK;
 }
 
 static int launch_backward(Handle *h, const void *X, const void *U, const void *A, const void *Bd, void *K, void *k,
-                           const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr)
+                           const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr,
+                           const SparseArgs *sparse = nullptr)
 {
+    SparseArgs sa;
+    std::memset(&sa, 0, sizeof sa);
+    if (sparse) sa = *sparse;
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto) -> int {
         using T = decltype(tz);
         using Sys = decltype(sys);
         // small batches: one warp per block and a deep ring (latency bound); large batches: shallower
         // ring so that more warps fit per SM (HBM bound)
         if constexpr (Sys::N == 4 && Sys::M == 1 && decltype(qc)::QUADRATIC) {
-            // small batches of the n=4, m=1 case: four lanes per trajectory (latency bound regime)
+            // four lanes per trajectory: small batches (latency bound regime), and the sparse iterations of large
+            // ones, where it runs next to the thread-per-trajectory kernel and each returns at once when the
+            // iteration is not its kind (SparseArgs::only)
             const bool lanes = h->env_lanes >= 0 ? h->env_lanes != 0 : h->p.B <= 32768;
-            if (lanes) {
+            const bool both = !lanes && sa.cur != nullptr && h->env_lanes < 0;
+            if (lanes || both) {
                 constexpr int DEPTH = 8, SLOTS = 8, LP = 26;
                 const size_t smem = sizeof(T) * (size_t)(DEPTH * SLOTS * LP + SLOTS * 4 + SLOTS * 20);
-                backward_n4m1_lanes_kernel<T, DEPTH><<<grid_for(h->p.B, SLOTS), 32, smem, st>>>(
+                SparseArgs sl = sa;
+                sl.only = both ? 2 : 0;
+                const int items = both ? (int)sa.thresh : h->p.B;
+                backward_n4m1_lanes_kernel<T, DEPTH><<<grid_for(items, SLOTS), 32, smem, st>>>(
                     qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active,
-                    gate, (const T *)mu);
+                    gate, (const T *)mu, sl);
                 ILQR_CHECK_LAUNCH(h);
-                return ILQR_OK;
+                if (!both) return ILQR_OK;
+                sa.only = 1;
             }
         }
         if constexpr (Sys::N > 4) {
             // n = 12, m = 4: a ring stage is 208 rows; two stages of one warp fit the 227 KB limit
-            return launch_backward_depth<T, Sys::N, Sys::M, 2>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st);
+            return launch_backward_depth<T, Sys::N, Sys::M, 2>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa);
         } else {
             if (h->p.B <= 32768)
-                return launch_backward_depth<T, Sys::N, Sys::M, 8>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st);
-            return launch_backward_depth<T, Sys::N, Sys::M, 4>(h, 64, qc, X, U, A, Bd, K, k, active, gate, mu, st);
+                return launch_backward_depth<T, Sys::N, Sys::M, 8>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa);
+            return launch_backward_depth<T, Sys::N, Sys::M, 4>(h, 64, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa);
         }
     });
 }
@@ -350,11 +367,15 @@ static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const 
 static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const void *phi, const void *x0, const void *X, const void *U,
                           const void *k, const void *K, void *Xc, void *Uc, void *cost_alpha, const int *active,
                           const unsigned int *gate, const void *cost_ref, cudaStream_t st, const SpecArgs *spec = nullptr,
-                          const int *list = nullptr, const unsigned int *list_count = nullptr)
+                          const int *list = nullptr, const unsigned int *list_count = nullptr,
+                          const SparseArgs *sparse = nullptr)
 {
     SpecArgs sp;
     std::memset(&sp, 0, sizeof sp);
     if (spec) sp = *spec;
+    SparseArgs sa;
+    std::memset(&sa, 0, sizeof sa);
+    if (sparse) sa = *sparse;
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
         using T = decltype(tz);
         using Sys = decltype(sys);
@@ -368,7 +389,7 @@ static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const voi
         if (!bs_env && h->lazy && n_alpha <= 4 && threads >= (size_t)148 * 16 * 32 * n_alpha) bs = 32 * n_alpha;
         rollout_kernel<Sys, decltype(qc), I, T><<<grid_for(threads, bs), bs, 0, st>>>(
             sys, qc, h->p.N, h->p.B, n_alpha, al, (const T *)phi, (const T *)x0, (const T *)X, (const T *)U, (const T *)k,
-            (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref, sp, list, list_count);
+            (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref, sp, list, list_count, sa);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });
@@ -394,19 +415,19 @@ static int launch_select(Handle *h, int a_lo, int a_hi, int wave, const void *ca
 static int launch_select_lazy(Handle *h, int a_lo, int a_hi, int wave, int last, const void *ca, void *cost, int *winner,
                               int *active, int *iters, int *status, int it, Control *ctl, const int *list_in,
                               const unsigned int *cnt_in, int *list_out, unsigned int *cnt_out, int *wslot, const RegArgs &rg,
-                              cudaStream_t st)
+                              const SparseArgs &sa, cudaStream_t st)
 {
     const int B = h->p.B, bs = 128;
     if (h->p.dtype == ILQR_F64)
         select_lazy_kernel<double><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, last, (const double *)ca,
                                                                    (double *)cost, winner, active, iters, status, h->p.tol,
                                                                    it, h->p.maxiter, ctl, list_in, cnt_in, list_out, cnt_out,
-                                                                   wslot, h->tr_alpha, (double *)h->tr_cost, rg);
+                                                                   wslot, h->tr_alpha, (double *)h->tr_cost, rg, sa);
     else
         select_lazy_kernel<float><<<grid_for(B, bs), bs, 0, st>>>(B, a_lo, a_hi, wave, last, (const float *)ca,
                                                                   (float *)cost, winner, active, iters, status,
                                                                   (float)h->p.tol, it, h->p.maxiter, ctl, list_in, cnt_in,
-                                                                  list_out, cnt_out, wslot, h->tr_alpha, (float *)h->tr_cost, rg);
+                                                                  list_out, cnt_out, wslot, h->tr_alpha, (float *)h->tr_cost, rg, sa);
     ILQR_CHECK_LAUNCH(h);
     return ILQR_OK;
 }
@@ -581,12 +602,13 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
         if (a < p->min_alpha) break;
     }
     h->n_alpha_eff = cnt;
+    const char *e;
     {
-        const char *e;
         h->env_lanes = (e = getenv("ILQR_BACKWARD_LANES")) ? (atoi(e) != 0) : -1;
         h->env_rollout_bs = (e = getenv("ILQR_ROLLOUT_BS")) && atoi(e) >= 32 ? atoi(e) / 32 * 32 : 0;
         h->env_check_every = (e = getenv("ILQR_CHECK_EVERY")) && atoi(e) > 0 ? atoi(e) : 8;
     }
+    h->sparse = (e = getenv("ILQR_SPARSE")) ? atoi(e) != 0 : 1;
     h->n_first = first_wave_size(p->B, cnt);
     h->spec_cap = spec_capacity(p->B, h->n_first, cnt);
     default_waves(h);
@@ -746,6 +768,22 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     int *winner = (int *)(w + L.winner), *active = (int *)(w + L.active), *defer = (int *)(w + L.defer);
     int *mark = (int *)(w + L.mark), *lists = (int *)(w + L.lists);
     int *wslot = h->lazy ? (int *)(w + L.wslot) : nullptr;      // only the lazy schedule stores candidates by list position
+    // sparse mode (SparseArgs): at or below `sparse_thresh` active trajectories an iteration walks the active list;
+    // at or below `sparse_all` its first rollout wave tries every step size -- by then that wave is latency bound
+    // (about two warps per SM sub-partition), and n_alpha * sparse_all must fit the threads of the dense first wave
+    int *alists = (int *)(w + L.alists);
+    unsigned int sparse_thresh = 0, sparse_all = 0;
+    if (h->lazy && h->sparse && p.model != ILQR_LTV) {
+        const long w0 = h->wave_lo[1];
+        long t = p.B / 4, ta = 2L * 148 * 4 * 32 / h->n_alpha_eff;
+        if (ta > (long)w0 * p.B / h->n_alpha_eff) ta = (long)w0 * p.B / h->n_alpha_eff;
+        if (const char *e = getenv("ILQR_SPARSE_THRESH")) t = atol(e);
+        if (const char *e = getenv("ILQR_SPARSE_ALL")) ta = atol(e);
+        if (ta > t) ta = t;
+        t &= ~31L;
+        ta &= ~31L;
+        if (t >= 32) { sparse_thresh = (unsigned int)t; sparse_all = (unsigned int)ta; }
+    }
     RegArgs rg;
     std::memset(&rg, 0, sizeof rg);
     if (p.reg_factor > 1.0) {
@@ -796,11 +834,24 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
             const unsigned int *gprev = it > 0 ? &ctl->n_active[it - 1] : g;
             prof_mark(h, ILQR_KC_OTHER, st);
             const bool ltv = p.model == ILQR_LTV;      // commit only: A_t, B_t are generated inside the LTV kernels
+            // sparse mode (SparseArgs): active lists of this / the previous / the next iteration
+            SparseArgs sa;
+            std::memset(&sa, 0, sizeof sa);
+            if (sparse_thresh > 0) {
+                sa.cur = alists + (size_t)(it & 1) * B;
+                sa.n_cur = g;
+                sa.prev = it > 0 ? alists + (size_t)((it - 1) & 1) * B : nullptr;
+                sa.n_prev = it > 0 ? gprev : nullptr;
+                sa.next = alists + (size_t)((it + 1) & 1) * B;
+                sa.thresh = sparse_thresh;
+                sa.thresh_all = sparse_all;
+                sa.n_alpha_all = h->n_alpha_eff;
+            }
             if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, it > 0 ? wslot : nullptr, active,
-                                              ltv ? 0 : 1, g, gprev, st))) return rc;
+                                              ltv ? 0 : 1, g, gprev, st, iters, it, &sa))) return rc;
             prof_mark(h, ILQR_KC_LINEARIZE, st);
             if ((rc = ltv ? launch_backward_ltv(h, phi, X, U, K, k, active, g, st, rg.mu)
-                          : launch_backward(h, X, U, A, Bd, K, k, active, g, st, rg.mu))) return rc;
+                          : launch_backward(h, X, U, A, Bd, K, k, active, g, st, rg.mu, &sa))) return rc;
             prof_mark(h, ILQR_KC_BACKWARD, st);
             if (h->lazy) {
                 // lazy line search: wave v rolls out step sizes [wave_lo[v], wave_lo[v+1]) for the trajectories
@@ -812,15 +863,17 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
                     AlphaList alv;
                     std::memset(&alv, 0, sizeof alv);
                     for (int i = lo; i < hi; ++i) alv.a[i - lo] = h->alphas.a[i];
+                    if (v == 0) alv = h->alphas;           // a sparse iteration tries every step size in wave 0
                     const int *lin = v ? lists + (size_t)((v - 1) & 1) * B : nullptr;
                     int *lout = lists + (size_t)(v & 1) * B;
                     const unsigned int *cin = v ? wcnt + v - 1 : nullptr;
                     if ((rc = launch_rollout(h, hi - lo, alv, phi, x0, X, U, k, K, (char *)Xc + xc_slab * lo,
                                              (char *)Uc + uc_slab * lo, (char *)ca + wbytes * (size_t)lo * B,
-                                             v ? nullptr : active, v ? cin : g, nullptr, st, nullptr, lin, cin))) return rc;
+                                             v ? nullptr : active, v ? cin : g, nullptr, st, nullptr, lin, cin,
+                                             v ? nullptr : &sa))) return rc;
                     prof_mark(h, ILQR_KC_ROLLOUT, st);
                     if ((rc = launch_select_lazy(h, lo, hi, v, v == h->n_waves - 1, ca, cost, winner, active, iters, status,
-                                                 it, ctl, lin, cin, lout, wcnt + v, wslot, rg, st))) return rc;
+                                                 it, ctl, lin, cin, lout, wcnt + v, wslot, rg, sa, st))) return rc;
                 }
                 continue;
             }
@@ -864,7 +917,7 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     }
     // commit the candidates accepted in the last executed iteration (no linearization)
     if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, it > 0 ? wslot : nullptr, nullptr, 0, nullptr,
-                                      nullptr, st))) return rc;
+                                      nullptr, st, iters, it))) return rc;
     if (total_iters) {
         unsigned long long tot = 0;
         CU(cudaMemcpyAsync(&tot, &ctl->total_iters, sizeof tot, cudaMemcpyDeviceToHost, st));

@@ -64,13 +64,19 @@ template <class Cost, typename T, int n, int m, int DEPTH>
 __global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, const T *__restrict__ X,
                                 const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
                                 T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
-                                const unsigned int *__restrict__ gate, const T *__restrict__ mu)
+                                const unsigned int *__restrict__ gate, const T *__restrict__ mu,
+                                const __grid_constant__ SparseArgs sa)
 {
     constexpr int L = n * n + n * m + n + m;
     extern __shared__ __align__(16) unsigned char ring_raw[];
     T *ring = reinterpret_cast<T *>(ring_raw);
     if (gate && *gate == 0u) return;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sparse_now(sa)) {                                                // few active trajectories: walk their list
+        if (sa.only == 1) return;                                        // ... which the four-lane kernel does better
+        if ((unsigned int)b >= *sa.n_cur) return;
+        b = sa.cur[b];
+    }
     if (b >= B) return;
     if (active && !active[b]) return;
     const int stage_elems = L * blockDim.x;
@@ -243,7 +249,8 @@ __global__ void __launch_bounds__(32)
 backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, int B, const T *__restrict__ X,
                            const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
                            T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
-                           const unsigned int *__restrict__ gate, const T *__restrict__ mu)
+                           const unsigned int *__restrict__ gate, const T *__restrict__ mu,
+                           const __grid_constant__ SparseArgs sa)
 {
     constexpr int n = 4, L = 25, LP = 26, SLOTS = 8;       // LP: padded slot stride (bank-conflict free LDS.128)
     extern __shared__ __align__(16) unsigned char lanes_raw[];
@@ -252,14 +259,21 @@ backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, 
     T *exV = exQ + SLOTS * 4;                               // [SLOTS][20]  V_xx (row-major 16) + V_x (4)
     if (gate && *gate == 0u) return;
     const int lane = threadIdx.x, s = lane >> 2, j = lane & 3;
-    const int b_raw = blockIdx.x * SLOTS + s;
-    const bool valid = b_raw < B && (!active || active[b_raw < B ? b_raw : B - 1] != 0);
+    // slot -> trajectory: the batch index itself, or an entry of the active list when few trajectories are left
+    const bool sparse = sparse_now(sa);
+    if (sa.only == 2 && !sparse) return;                    // large batch: dense iterations belong to backward_kernel
+    const int n_items = sparse ? (int)*sa.n_cur : B;
+    auto item = [&](int slot) -> int {
+        const int i = min(blockIdx.x * SLOTS + slot, n_items - 1);      // clamped: spare slots compute on a copy
+        return sparse ? sa.cur[i] : i;
+    };
+    const int b = item(s);
+    const bool valid = blockIdx.x * SLOTS + s < n_items && (!active || active[b] != 0);
     if (__ballot_sync(0xffffffffu, valid) == 0u) return;
-    const int b = b_raw < B ? b_raw : B - 1;                // clamped: out-of-range slots compute on a copy, never store
 
     // cooperative fill of one ring stage: element e = row * 8 + slot, 32 elements per LDGSTS
     const int f_slot = lane & 7, f_row0 = lane >> 3;
-    const int f_b = min(blockIdx.x * SLOTS + f_slot, B - 1);
+    const int f_b = item(f_slot);
     auto issue = [&](int stage, int t) {
 #pragma unroll
         for (int i = 0; i < 7; ++i) {

@@ -45,6 +45,30 @@ struct RegArgs {
     double factor, mu_min, mu_max;
 };
 
+// Solver mode (tol > 0): trajectories converge at different iterations, and the late iterations of a solve
+// serve a small, scattered fraction of the batch.  The select kernels therefore keep a compacted list of the
+// trajectories entering the next iteration (its length is the n_active counter they maintain anyway), and
+// when that count drops to `thresh` or below, K1, K2 and the rollouts index the batch through the list instead
+// of scanning it: the cost of an iteration follows the number of active trajectories.  Dense or sparse is
+// decided on the device, per iteration, from the same counter in every kernel.  cur == nullptr disables.
+struct SparseArgs {
+    const int *cur;               // list of the trajectories active in this iteration     [*n_cur entries]
+    const unsigned int *n_cur;    // = &ctl->n_active[it]
+    const int *prev;              // list of the previous iteration (K1: pending commits)    [*n_prev entries]
+    const unsigned int *n_prev;   // = &ctl->n_active[it - 1]; nullptr in iteration 0
+    int *next;                    // list being built for the next iteration (select kernels)
+    int only;                     // K2 comes in two kernels at large batches: 1 = run in dense iterations only,
+                                  // 2 = in sparse iterations only, 0 = always
+    unsigned int thresh;          // at or below this many active trajectories the kernels walk the list
+    unsigned int thresh_all;      // at or below this many the first rollout wave tries EVERY step size (the wave
+                                  // is latency bound by then: extra rollouts are free, extra waves are not)
+    int n_alpha_all;
+};
+
+ILQR_DEV bool sparse_now(const SparseArgs &sa) { return sa.cur != nullptr && *sa.n_cur <= sa.thresh; }
+ILQR_DEV bool sparse_all(const SparseArgs &sa) { return sa.cur != nullptr && *sa.n_cur <= sa.thresh_all; }
+ILQR_DEV bool sparse_prev(const SparseArgs &sa) { return sa.prev != nullptr && sa.n_prev != nullptr && *sa.n_prev <= sa.thresh; }
+
 template <typename T>
 ILQR_DEV bool reg_on_failure(const RegArgs &rg, int b)
 {

@@ -24,23 +24,19 @@ __global__ void step_kernel(const __grid_constant__ Sys sys, T dt, int B, int t,
     for (int i = 0; i < n; ++i) xn[(size_t)i * B + b] = out[i];
 }
 
-// K1.  One thread per (t,b), t in [0,N].  If winner != nullptr and winner[b] >= 0 the thread first
-// copies the accepted candidate (Xc/Uc slab winner[b]) into the nominal X/U; if the trajectory is
-// active it then writes the discrete Jacobians about that nominal point.
+// K1.  One thread per (t,b), t in [0,N].  If the trajectory ran the previous iteration (iters[b] == it) and
+// accepted a candidate (winner[b] >= 0) the thread first copies it (Xc/Uc slab winner[b]) into the nominal X/U; if
+// the trajectory is active it then writes the discrete Jacobians about that nominal point.
 template <class Sys, int INTEG, typename T>
-__global__ void commit_linearize_kernel(const __grid_constant__ Sys sys, T dt, int N, int B,
-                                        const T *__restrict__ phi, T *__restrict__ X, T *__restrict__ U,
-                                        T *__restrict__ A, T *__restrict__ Bd, const T *__restrict__ Xc,
-                                        const T *__restrict__ Uc, const int *__restrict__ winner,
-                                        const int *__restrict__ wslot, const int *__restrict__ active, int do_linearize,
-                                        const unsigned int *__restrict__ gate0, const unsigned int *__restrict__ gate1)
+ILQR_DEV void commit_linearize_point(const Sys &sys, T dt, int N, int B, int t, int b, const T *__restrict__ phi,
+                                     T *__restrict__ X, T *__restrict__ U, T *__restrict__ A, T *__restrict__ Bd,
+                                     const T *__restrict__ Xc, const T *__restrict__ Uc, const int *__restrict__ winner,
+                                     const int *__restrict__ wslot, const int *__restrict__ active,
+                                     const int *__restrict__ iters, int it, int do_linearize)
 {
     constexpr int n = Sys::N, m = Sys::M;
-    if (gate0 && *gate0 == 0u && *gate1 == 0u) return;   // nobody active now or in the previous iteration
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)(N + 1) * B) return;
-    const int t = (int)(gid / B), b = (int)(gid % B);
-    const int w = winner ? winner[b] : -1;
+    int w = winner ? winner[b] : -1;
+    if (iters && iters[b] != it) w = -1;                 // nothing pending: committed earlier, or never ran
     const bool act = do_linearize && (active ? active[b] != 0 : true) && t < N;
     if (w < 0 && !act) return;
     T x[n], u[m];
@@ -76,6 +72,35 @@ __global__ void commit_linearize_kernel(const __grid_constant__ Sys sys, T dt, i
 #pragma unroll
         for (int j = 0; j < m; ++j) Bd[(((size_t)t * n + i) * m + j) * B + b] = Bj[i][j];
     }
+}
+
+template <class Sys, int INTEG, typename T>
+__global__ void __launch_bounds__(128, Sys::N <= 4 ? 4 : 1) commit_linearize_kernel(const __grid_constant__ Sys sys, T dt, int N, int B,
+                                        const T *__restrict__ phi, T *__restrict__ X, T *__restrict__ U,
+                                        T *__restrict__ A, T *__restrict__ Bd, const T *__restrict__ Xc,
+                                        const T *__restrict__ Uc, const int *__restrict__ winner,
+                                        const int *__restrict__ wslot, const int *__restrict__ active,
+                                        const int *__restrict__ iters, int it, int do_linearize,
+                                        const unsigned int *__restrict__ gate0, const unsigned int *__restrict__ gate1,
+                                        const __grid_constant__ SparseArgs sa)
+{
+    if (gate0 && *gate0 == 0u && *gate1 == 0u) return;   // nobody active now or in the previous iteration
+    if (sparse_prev(sa)) {
+        // few trajectories ran the previous iteration: the first blocks stride over (t, list entry) pairs, the
+        // rest of the grid (sized for the whole batch) leaves at once
+        const unsigned int cnt = *sa.n_prev;
+        const unsigned int nblk = min(gridDim.x, 148u * 8u);
+        if (blockIdx.x >= nblk) return;
+        const size_t total = (size_t)(N + 1) * cnt, stride = (size_t)nblk * blockDim.x;
+        for (size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride)
+            commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, (int)(item / cnt), sa.prev[item % cnt], phi, X, U, A, Bd, Xc,
+                                                  Uc, winner, wslot, active, iters, it, do_linearize);
+        return;
+    }
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)(N + 1) * B) return;
+    commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, (int)(gid / B), (int)(gid % B), phi, X, U, A, Bd, Xc, Uc, winner,
+                                          wslot, active, iters, it, do_linearize);
 }
 
 // materialised cost expansion (system_base.py:212-219); one thread per (t,b), t in [0,N]

@@ -66,7 +66,7 @@ __global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys s
                                T *__restrict__ Uc, T *__restrict__ cost_alpha, const int *__restrict__ active,
                                const unsigned int *__restrict__ gate, const T *__restrict__ cost_ref,
                                const __grid_constant__ SpecArgs sp, const int *__restrict__ list,
-                               const unsigned int *__restrict__ list_count)
+                               const unsigned int *__restrict__ list_count, const __grid_constant__ SparseArgs sa)
 {
     constexpr int n = Sys::N, m = Sys::M;
     if (gate && *gate == 0u) return;
@@ -75,6 +75,13 @@ __global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys s
     // reads come from L1/L2 instead of once per step size from HBM.
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t wg = gid >> 5, ngrp = ((size_t)B + 31) >> 5;
+    // sparse iteration (SparseArgs; first wave of the lazy schedule only): the wave walks the compacted active
+    // list, and once very few trajectories are left it tries every step size at once
+    if (sparse_now(sa)) {
+        list = sa.cur;
+        list_count = sa.n_cur;
+        if (sparse_all(sa)) n_alpha = sa.n_alpha_all;
+    }
     int ai, b, bw;        // bw: column of the candidate slabs / cost_alpha this thread writes
     if (wg < ngrp * n_alpha) {
         ai = (int)(wg % n_alpha);
@@ -285,14 +292,25 @@ __global__ void select_lazy_kernel(int B, int a_lo, int a_hi, int wave, int last
                                    int *__restrict__ iters, int *__restrict__ status, T tol, int it, int maxiter,
                                    Control *ctl, const int *__restrict__ list_in, const unsigned int *cnt_in,
                                    int *__restrict__ list_out, unsigned int *cnt_out, int *__restrict__ wslot,
-                                   int *__restrict__ tr_alpha, T *__restrict__ tr_cost, const __grid_constant__ RegArgs rg)
+                                   int *__restrict__ tr_alpha, T *__restrict__ tr_cost, const __grid_constant__ RegArgs rg,
+                                   const __grid_constant__ SparseArgs sa)
 {
     if (ctl->n_active[it] == 0u) return;
     if (wave > 0 && *cnt_in == 0u) return;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int b = gid;
     bool mine = false;
-    if (wave == 0) {
+    if (wave == 0 && sparse_now(sa)) {
+        // sparse iteration: the first wave ran over the active list (and, with very few left, tried every step size)
+        if ((unsigned int)gid < *sa.n_cur) {
+            b = sa.cur[gid];
+            mine = active[b] != 0;
+        }
+        if (sparse_all(sa)) {
+            a_hi = sa.n_alpha_all;
+            last = 1;
+        }
+    } else if (wave == 0) {
         if (gid < B) {
             mine = active[gid] != 0;
             if (!mine) winner[gid] = -1;
@@ -344,12 +362,18 @@ __global__ void select_lazy_kernel(int B, int a_lo, int a_hi, int wave, int last
         base = __shfl_sync(full, base, leader);
         if (app) list_out[base + __popc(ma & ((1u << lane) - 1u))] = b;
     }
-    const unsigned ns = __popc(__ballot_sync(full, still));
-    const unsigned nr = __popc(__ballot_sync(full, mine && wave == 0));
-    if (lane == 0) {
-        if (ns) atomicAdd(&ctl->n_active[it + 1], ns);
-        if (nr) atomicAdd(&ctl->total_iters, (unsigned long long)nr);
+    // trajectories entering the next iteration: count them and, for the sparse mode, list them (the counter's
+    // old value is the warp's position in the list)
+    const unsigned ms = __ballot_sync(full, still);
+    if (ms) {
+        const int leader = __ffs(ms) - 1;
+        unsigned int base = 0;
+        if ((int)lane == leader) base = atomicAdd(&ctl->n_active[it + 1], (unsigned int)__popc(ms));
+        base = __shfl_sync(full, base, leader);
+        if (still && sa.next) sa.next[base + __popc(ms & ((1u << lane) - 1u))] = b;
     }
+    const unsigned nr = __popc(__ballot_sync(full, mine && wave == 0));
+    if (lane == 0 && nr) atomicAdd(&ctl->total_iters, (unsigned long long)nr);
 }
 
 // winner only (ilqr_forward_linesearch)

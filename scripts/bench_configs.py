@@ -76,6 +76,9 @@ def cfg4(B=262144, N=1000, chunk=32768):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg3":
+        print(json.dumps(cfg3(ticks=int(sys.argv[2]) if len(sys.argv) > 2 else 20)))
+        return
     out = {"gpu": torch.cuda.get_device_name(0)}
     out["cfg2_f64_B4096"] = cfg2(4096, "float64")
     out["cfg2_f32_B4096"] = cfg2(4096, "float32")

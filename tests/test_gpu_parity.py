@@ -283,3 +283,30 @@ def test_nan_initial_state_fails_line_search_like_python():
     keep = np.arange(B) != 17
     assert np.array_equal(X[keep], Xc[keep]) and np.array_equal(cost[keep], cc[keep])
     assert np.array_equal(sol.status[keep], clean.status[keep])
+
+
+def test_sparse_active_list_iterations_are_exact(monkeypatch):
+    """Solver mode (tol > 0): trajectories converge at different iterations; once few are left the lazy schedule
+    walks a compacted active list (SparseArgs) instead of the whole batch and tries every step size in one wave.
+    Scheduling only: results must be bit-identical with the sparse mode off and with the eager schedule."""
+    from class_files.iLQR_class import iLQR
+    B, N = 1000, 80
+    x0 = cfg2_x0(B, seed=5)
+    out = {}
+    for name, waves, sparse in (("eager", (), "1"), ("lazy", (2, 2, 2, 4), "0"), ("lazy_sparse", (2, 2, 2, 4), "1"),
+                                ("lazy_sparse_37", (3, 7), "1")):
+        monkeypatch.setenv("ILQR_SPARSE", sparse)
+        sol = iLQR(ua_system(), 0.8, x0, np.zeros((1, N)), tol=1e-2, maxiter=80, verbose=False, reg_factor=10.0)
+        sol.set_linesearch_waves(waves)
+        res = []
+        for rep in range(2):                                  # second solve warm-started from the first (MPC style)
+            X, U, cost = sol.optimize_trajectory()
+            res += [X.copy(), U.copy(), cost.copy(), sol.K.copy(), sol.U_ff.copy(), sol.iterations.copy(), sol.status.copy()]
+            sol.x_0 = x0 + 0.02
+        out[name] = res
+    it = out["eager"][5]
+    tail = np.array([(it > k).sum() for k in range(int(it.max()))])
+    assert ((tail > 0) & (tail <= 192)).sum() >= 3          # several iterations ran below the sparse threshold of 192
+    for name in ("lazy", "lazy_sparse", "lazy_sparse_37"):
+        for a, b in zip(out["eager"], out[name]):
+            assert np.array_equal(a, b), name
