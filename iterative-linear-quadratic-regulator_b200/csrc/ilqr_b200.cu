@@ -152,7 +152,7 @@ static inline int block_for(size_t threads)
 }
 
 struct WsLayout {
-    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, wslot, active, defer, mark, lists, alists, mu, total;
+    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, wslot, active, defer, mark, lists, alists, apos, mu, total;
 };
 
 static size_t ctl_bytes(int maxiter)
@@ -185,6 +185,7 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
     L.mark = off; off = al(off + 4 * B);
     L.lists = off; off = al(off + 4 * 2 * B);     // two speculation lists (capacity <= B each)
     L.alists = off; off = al(off + 4 * 2 * B);    // active lists of the current / next iteration (SparseArgs)
+    L.apos = off; off = al(off + 4 * B);          // position of each trajectory in its active list
     L.mu = off; off = al(off + w * B);
     L.total = off;
     return L;
@@ -843,6 +844,7 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
                 sa.prev = it > 0 ? alists + (size_t)((it - 1) & 1) * B : nullptr;
                 sa.n_prev = it > 0 ? gprev : nullptr;
                 sa.next = alists + (size_t)((it + 1) & 1) * B;
+                sa.pos = (int *)(w + L.apos);
                 sa.thresh = sparse_thresh;
                 sa.thresh_all = sparse_all;
                 sa.n_alpha_all = h->n_alpha_eff;

@@ -26,15 +26,15 @@ template <int PENDING> ILQR_DEV void cp_async_wait() { asm volatile("cp.async.wa
 
 // rows of one ring stage: A (n*n), Bd (n*m), x (n), u (m); element [row][tid]
 template <typename T, int n, int m>
-ILQR_DEV void bwd_issue(T *stage, int t, int b, int B, const T *__restrict__ X, const T *__restrict__ U,
+ILQR_DEV void bwd_issue(T *stage, int t, int b, int c, int B, const T *__restrict__ X, const T *__restrict__ U,
                         const T *__restrict__ A, const T *__restrict__ Bd)
-{
+{   // b: trajectory (columns of X, U); c: column of A, Bd (= b, or the list position in a sparse iteration)
     const int bd = blockDim.x, tid = threadIdx.x;
     int row = 0;
 #pragma unroll
-    for (int i = 0; i < n * n; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, A + ((size_t)t * n * n + i) * B + b);
+    for (int i = 0; i < n * n; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, A + ((size_t)t * n * n + i) * B + c);
 #pragma unroll
-    for (int i = 0; i < n * m; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, Bd + ((size_t)t * n * m + i) * B + b);
+    for (int i = 0; i < n * m; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, Bd + ((size_t)t * n * m + i) * B + c);
 #pragma unroll
     for (int i = 0; i < n; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, X + ((size_t)t * n + i) * B + b);
 #pragma unroll
@@ -72,17 +72,18 @@ __global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, c
     T *ring = reinterpret_cast<T *>(ring_raw);
     if (gate && *gate == 0u) return;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int cAB = b;                                                         // column of A, Bd
     if (sparse_now(sa)) {                                                // few active trajectories: walk their list
         if (sa.only == 1) return;                                        // ... which the four-lane kernel does better
         if ((unsigned int)b >= *sa.n_cur) return;
-        b = sa.cur[b];
+        b = sa.cur[b];                                                   // A_t, B_t stay at the list position (K1)
     }
     if (b >= B) return;
     if (active && !active[b]) return;
     const int stage_elems = L * blockDim.x;
 #pragma unroll
     for (int s = 0; s < DEPTH; ++s) {
-        if (N - 1 - s >= 0) bwd_issue<T, n, m>(ring + s * stage_elems, N - 1 - s, b, B, X, U, A, Bd);
+        if (N - 1 - s >= 0) bwd_issue<T, n, m>(ring + s * stage_elems, N - 1 - s, b, cAB, B, X, U, A, Bd);
         cp_async_commit();
     }
     const T mu_b = mu ? mu[b] : T(0);                                    // regularisation (RegArgs), 0 in the reference
@@ -229,7 +230,7 @@ __global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, c
             for (int i = 0; i < n; ++i) K[(((size_t)t * m + j) * n + i) * B + b] = Kt[j][i];
             k[((size_t)t * m + j) * B + b] = kt[j];
         }
-        if (t - DEPTH >= 0) bwd_issue<T, n, m>(ring + stage * stage_elems, t - DEPTH, b, B, X, U, A, Bd);
+        if (t - DEPTH >= 0) bwd_issue<T, n, m>(ring + stage * stage_elems, t - DEPTH, b, cAB, B, X, U, A, Bd);
         cp_async_commit();
         stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
     }
@@ -274,13 +275,15 @@ backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, 
     // cooperative fill of one ring stage: element e = row * 8 + slot, 32 elements per LDGSTS
     const int f_slot = lane & 7, f_row0 = lane >> 3;
     const int f_b = item(f_slot);
+    // column of A, Bd: the trajectory, or in a sparse iteration its list position (where K1 wrote them, coalesced)
+    const int f_c = sparse ? min(blockIdx.x * SLOTS + f_slot, n_items - 1) : f_b;
     auto issue = [&](int stage, int t) {
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
             const int row = f_row0 + 4 * i;
             if (row < L) {
-                const T *src = row < 16 ? A + ((size_t)t * 16 + row) * B + f_b
-                             : row < 20 ? Bd + ((size_t)t * 4 + (row - 16)) * B + f_b
+                const T *src = row < 16 ? A + ((size_t)t * 16 + row) * B + f_c
+                             : row < 20 ? Bd + ((size_t)t * 4 + (row - 16)) * B + f_c
                              : row < 24 ? X + ((size_t)t * 4 + (row - 20)) * B + f_b
                                         : U + (size_t)t * B + f_b;
                 cp_async<sizeof(T)>(ring + (stage * SLOTS + f_slot) * LP + row, src);

@@ -57,6 +57,8 @@ struct SparseArgs {
     const int *prev;              // list of the previous iteration (K1: pending commits)    [*n_prev entries]
     const unsigned int *n_prev;   // = &ctl->n_active[it - 1]; nullptr in iteration 0
     int *next;                    // list being built for the next iteration (select kernels)
+    int *pos;                     // [B] position of a trajectory in the list it was last put on: in a sparse iteration
+                                  // K1 writes A_t, B_t at that column and K2 reads them back coalesced
     int only;                     // K2 comes in two kernels at large batches: 1 = run in dense iterations only,
                                   // 2 = in sparse iterations only, 0 = always
     unsigned int thresh;          // at or below this many active trajectories the kernels walk the list

@@ -32,7 +32,8 @@ ILQR_DEV void commit_linearize_point(const Sys &sys, T dt, int N, int B, int t, 
                                      T *__restrict__ X, T *__restrict__ U, T *__restrict__ A, T *__restrict__ Bd,
                                      const T *__restrict__ Xc, const T *__restrict__ Uc, const int *__restrict__ winner,
                                      const int *__restrict__ wslot, const int *__restrict__ active,
-                                     const int *__restrict__ iters, int it, int do_linearize)
+                                     const int *__restrict__ iters, int it, int do_linearize,
+                                     const int *__restrict__ pos)
 {
     constexpr int n = Sys::N, m = Sys::M;
     int w = winner ? winner[b] : -1;
@@ -65,12 +66,13 @@ ILQR_DEV void commit_linearize_point(const Sys &sys, T dt, int N, int B, int t, 
     if (!act) return;
     T Aj[n][n], Bj[n][m];
     step_jac<INTEG>(sys, dt, x, u, Aj, Bj, sys.time_scalar(t, phi ? phi[b] : T(0)));
+    const int c = pos ? pos[b] : b;          // sparse iteration: compact column = position in the active list
 #pragma unroll
     for (int i = 0; i < n; ++i) {
 #pragma unroll
-        for (int j = 0; j < n; ++j) A[(((size_t)t * n + i) * n + j) * B + b] = Aj[i][j];
+        for (int j = 0; j < n; ++j) A[(((size_t)t * n + i) * n + j) * B + c] = Aj[i][j];
 #pragma unroll
-        for (int j = 0; j < m; ++j) Bd[(((size_t)t * n + i) * m + j) * B + b] = Bj[i][j];
+        for (int j = 0; j < m; ++j) Bd[(((size_t)t * n + i) * m + j) * B + c] = Bj[i][j];
     }
 }
 
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(128, Sys::N <= 4 ? 4 : 1) commit_linearize_ker
                                         const __grid_constant__ SparseArgs sa)
 {
     if (gate0 && *gate0 == 0u && *gate1 == 0u) return;   // nobody active now or in the previous iteration
+    const int *pos = sparse_now(sa) ? sa.pos : nullptr;  // where K2 will look for A_t, B_t in this iteration
     if (sparse_prev(sa)) {
         // few trajectories ran the previous iteration: the first blocks stride over (t, list entry) pairs, the
         // rest of the grid (sized for the whole batch) leaves at once
@@ -94,13 +97,13 @@ __global__ void __launch_bounds__(128, Sys::N <= 4 ? 4 : 1) commit_linearize_ker
         const size_t total = (size_t)(N + 1) * cnt, stride = (size_t)nblk * blockDim.x;
         for (size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride)
             commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, (int)(item / cnt), sa.prev[item % cnt], phi, X, U, A, Bd, Xc,
-                                                  Uc, winner, wslot, active, iters, it, do_linearize);
+                                                  Uc, winner, wslot, active, iters, it, do_linearize, pos);
         return;
     }
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)(N + 1) * B) return;
     commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, (int)(gid / B), (int)(gid % B), phi, X, U, A, Bd, Xc, Uc, winner,
-                                          wslot, active, iters, it, do_linearize);
+                                          wslot, active, iters, it, do_linearize, pos);
 }
 
 // materialised cost expansion (system_base.py:212-219); one thread per (t,b), t in [0,N]

@@ -370,7 +370,11 @@ __global__ void select_lazy_kernel(int B, int a_lo, int a_hi, int wave, int last
         unsigned int base = 0;
         if ((int)lane == leader) base = atomicAdd(&ctl->n_active[it + 1], (unsigned int)__popc(ms));
         base = __shfl_sync(full, base, leader);
-        if (still && sa.next) sa.next[base + __popc(ms & ((1u << lane) - 1u))] = b;
+        if (still && sa.next) {
+            const unsigned int at = base + __popc(ms & ((1u << lane) - 1u));
+            sa.next[at] = b;
+            sa.pos[b] = (int)at;
+        }
     }
     const unsigned nr = __popc(__ballot_sync(full, mine && wave == 0));
     if (lane == 0 && nr) atomicAdd(&ctl->total_iters, (unsigned long long)nr);
