@@ -327,9 +327,10 @@ def main():
     kern["other_ms_per_iteration"] = ktimes["other"][0] / max(1, ktimes["other"][1])
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
     # command (profiles/traffic.json, written by scripts/ncu_summary.py --traffic); null when absent
-    traffic = {}
+    traffic, traffic_all = {}, {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"B{B}", {})
+        traffic_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = traffic_all.get(f"B{B}", {})
     except Exception:
         pass
     dom = max(("linearize", "backward", "rollout"), key=lambda k: ktimes[k][0])
@@ -367,6 +368,8 @@ def main():
     if large:
         large["roofline_backward"]["peak"] = peak
         large["roofline_backward"]["frac"] = large["roofline_backward"]["achieved"] / peak
+        large["roofline_backward"]["algorithmic_bytes"] = BYTES["backward"] * N_H * large["batch"]
+        large["roofline_backward"]["traffic"] = traffic_all.get(f"B{large['batch']}", {}).get("backward")
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -37,7 +37,9 @@ def traffic(rep, key, out):
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    acc = {}
+    # one bucket per iLQR iteration: K1 (linearize) opens it; the rollout waves (and the two K2 kernels of a large
+    # batch) of an iteration are summed, matching bench.py's per-iteration kernel times
+    buckets = []
     for r in rows[2:]:
         name = r[idx["Kernel Name"]]
         cls = "rollout" if "rollout" in name else "linearize" if "linearize" in name else "backward" if "backward" in name else None
@@ -46,10 +48,15 @@ def traffic(rep, key, out):
         tot = 0.0
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(r[idx[k]].replace(",", "")) * scale[units[idx[k]]]
-        acc.setdefault(cls, []).append(tot)
+        if cls == "linearize":
+            buckets.append({})
+        if buckets:
+            buckets[-1][cls] = buckets[-1].get(cls, 0.0) + tot
+    full = [b for b in buckets if {"linearize", "backward", "rollout"} <= set(b)]
+    acc = {c: [b[c] for b in full] for c in ("linearize", "backward", "rollout")} if full else {}
     d = json.load(open(out)) if os.path.exists(out) else {}
     d[key] = {c: sum(v) / len(v) for c, v in acc.items()}
-    d[key]["source"] = os.path.basename(rep) + " (ncu --set full, average over the captured launches of each kernel)"
+    d[key]["source"] = os.path.basename(rep) + " (ncu --set full; per iLQR iteration: sum over the launches of a kernel class, averaged over the captured iterations)"
     json.dump(d, open(out, "w"), indent=1)
     print(d[key])
 
