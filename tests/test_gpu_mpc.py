@@ -107,3 +107,20 @@ def test_batched_mpc_vs_oracle(oracle):
     ex, same = np.array(ex), np.array(same)
     assert same.mean() > 0.95
     assert np.median(ex[same]) < 1e-12 and np.quantile(ex[same], 0.9) < TOL
+
+
+def test_examples_run(capsys):
+    """the example scripts (the reference's run scripts without plots) run end to end"""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    ex = os.path.join(ROOT, "examples")
+    import sys
+    sys.path.insert(0, ex)
+    for name, kw in (("open_loop_pendulum", {}), ("ua_mpc", dict(N_sim=3, B=256)), ("batched_swing_up", dict(B=256))):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ex, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.main(**kw)
+    out = capsys.readouterr().out
+    assert "Initial cost:" in out and "run_mpc, 256 instances" in out and "256 trajectories" in out

