@@ -122,6 +122,7 @@ struct Handle {
     int env_rollout_bs;       // ILQR_ROLLOUT_BS: 0 [auto] or a block size
     int env_check_every;      // ILQR_CHECK_EVERY: iterations enqueued between host polls of the active count [8]
     void *mu_user;            // optional caller buffer for the per-trajectory regularisation (ilqr_set_mu_buffer)
+    int ab_blocked;           // ilqr_solve stores the linearization blocked by groups of 32 trajectories (ab_off)
     int sparse;               // lazy schedule: late iterations index the batch through the active list (SparseArgs)
     int lazy;                 // large batches: lazy multi-wave line search over compacted lists (select_lazy_kernel)
     int n_waves;
@@ -173,8 +174,11 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
     L.ctl = off; off = al(off + ctl_bytes(p.maxiter));
     // the LTV model generates A_t, B_t inside its kernels: no per-trajectory linearization is stored
     const size_t lin = p.model == ILQR_LTV ? 0 : 1;
-    L.A = off; off = al(off + lin * w * N * n * n * B);
-    L.Bd = off; off = al(off + lin * w * N * n * m * B);
+    // sized for the batch padded to whole groups of 32 columns: ilqr_solve keeps A and Bd as ONE blocked array
+    // starting at L.A (ab_off); the two sizes are multiples of 256 bytes, so the regions are contiguous
+    const size_t Bpad = (B + 31) / 32 * 32;
+    L.A = off; off = al(off + lin * w * N * n * n * Bpad);
+    L.Bd = off; off = al(off + lin * w * N * n * m * Bpad);
     L.Xc = off; off = al(off + w * (size_t)n_alpha * (N + 1) * n * B);
     L.Uc = off; off = al(off + w * (size_t)n_alpha * N * m * B);
     L.cost_alpha = off; off = al(off + w * (size_t)n_alpha * B);
@@ -254,7 +258,7 @@ template <class F> static int dispatch(const Handle *h, F &&f)
 static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U, void *A, void *Bd, const void *Xc, const void *Uc,
                                    const int *winner, const int *wslot, const int *active, int do_lin, const unsigned int *g0,
                                    const unsigned int *g1, cudaStream_t st, const int *iters = nullptr, int it = 0,
-                                   const SparseArgs *sparse = nullptr)
+                                   const SparseArgs *sparse = nullptr, int ab_blocked = 0)
 {
     SparseArgs sa;
     std::memset(&sa, 0, sizeof sa);
@@ -267,7 +271,7 @@ static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U,
         const int bs = 128;
         commit_linearize_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
             sys, qc.dt, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (T *)A, (T *)Bd, (const T *)Xc, (const T *)Uc, winner, wslot,
-            active, iters, it, do_lin, g0, g1, sa);
+            active, iters, it, do_lin, g0, g1, sa, ab_blocked);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });
@@ -276,7 +280,8 @@ static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U,
 template <typename T, int n, int m, int DEPTH, class Cost>
 static int launch_backward_depth(Handle *h, int bs, const Cost &qc, const void *X, const void *U,
                                  const void *A, const void *Bd, void *K, void *k, const int *active,
-                                 const unsigned int *gate, const void *mu, cudaStream_t st, const SparseArgs &sa)
+                                 const unsigned int *gate, const void *mu, cudaStream_t st, const SparseArgs &sa,
+                                 int ab_blocked)
 {
     constexpr int L = n * n + n * m + n + m;
     const size_t smem = (size_t)DEPTH * L * bs * sizeof(T);
@@ -289,14 +294,14 @@ static int launch_backward_depth(Handle *h, int bs, const Cost &qc, const void *
     }
     backward_kernel<Cost, T, n, m, DEPTH><<<grid_for(h->p.B, bs), bs, smem, st>>>(
         qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active, gate,
-        (const T *)mu, sa);
+        (const T *)mu, sa, ab_blocked);
     ILQR_CHECK_LAUNCH(h);
     return ILQR_OK;
 }
 
 static int launch_backward(Handle *h, const void *X, const void *U, const void *A, const void *Bd, void *K, void *k,
                            const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr,
-                           const SparseArgs *sparse = nullptr)
+                           const SparseArgs *sparse = nullptr, int ab_blocked = 0)
 {
     SparseArgs sa;
     std::memset(&sa, 0, sizeof sa);
@@ -320,7 +325,7 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
                 const int items = both ? (int)sa.thresh : h->p.B;
                 backward_n4m1_lanes_kernel<T, DEPTH><<<grid_for(items, SLOTS), 32, smem, st>>>(
                     qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active,
-                    gate, (const T *)mu, sl);
+                    gate, (const T *)mu, sl, ab_blocked);
                 ILQR_CHECK_LAUNCH(h);
                 if (!both) return ILQR_OK;
                 sa.only = 1;
@@ -328,11 +333,11 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
         }
         if constexpr (Sys::N > 4) {
             // n = 12, m = 4: a ring stage is 208 rows; two stages of one warp fit the 227 KB limit
-            return launch_backward_depth<T, Sys::N, Sys::M, 2>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa);
+            return launch_backward_depth<T, Sys::N, Sys::M, 2>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa, ab_blocked);
         } else {
             if (h->p.B <= 32768)
-                return launch_backward_depth<T, Sys::N, Sys::M, 8>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa);
-            return launch_backward_depth<T, Sys::N, Sys::M, 4>(h, 64, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa);
+                return launch_backward_depth<T, Sys::N, Sys::M, 8>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa, ab_blocked);
+            return launch_backward_depth<T, Sys::N, Sys::M, 4>(h, 64, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa, ab_blocked);
         }
     });
 }
@@ -610,6 +615,7 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
         h->env_check_every = (e = getenv("ILQR_CHECK_EVERY")) && atoi(e) > 0 ? atoi(e) : 8;
     }
     h->sparse = (e = getenv("ILQR_SPARSE")) ? atoi(e) != 0 : 1;
+    h->ab_blocked = (e = getenv("ILQR_AB_BLOCKED")) ? atoi(e) != 0 : 1;
     h->n_first = first_wave_size(p->B, cnt);
     h->spec_cap = spec_capacity(p->B, h->n_first, cnt);
     default_waves(h);
@@ -850,10 +856,10 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
                 sa.n_alpha_all = h->n_alpha_eff;
             }
             if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, it > 0 ? wslot : nullptr, active,
-                                              ltv ? 0 : 1, g, gprev, st, iters, it, &sa))) return rc;
+                                              ltv ? 0 : 1, g, gprev, st, iters, it, &sa, h->ab_blocked))) return rc;
             prof_mark(h, ILQR_KC_LINEARIZE, st);
             if ((rc = ltv ? launch_backward_ltv(h, phi, X, U, K, k, active, g, st, rg.mu)
-                          : launch_backward(h, X, U, A, Bd, K, k, active, g, st, rg.mu, &sa))) return rc;
+                          : launch_backward(h, X, U, A, Bd, K, k, active, g, st, rg.mu, &sa, h->ab_blocked))) return rc;
             prof_mark(h, ILQR_KC_BACKWARD, st);
             if (h->lazy) {
                 // lazy line search: wave v rolls out step sizes [wave_lo[v], wave_lo[v+1]) for the trajectories

@@ -27,14 +27,17 @@ template <int PENDING> ILQR_DEV void cp_async_wait() { asm volatile("cp.async.wa
 // rows of one ring stage: A (n*n), Bd (n*m), x (n), u (m); element [row][tid]
 template <typename T, int n, int m>
 ILQR_DEV void bwd_issue(T *stage, int t, int b, int c, int B, const T *__restrict__ X, const T *__restrict__ U,
-                        const T *__restrict__ A, const T *__restrict__ Bd)
+                        const T *__restrict__ A, const T *__restrict__ Bd, int ab_blocked)
 {   // b: trajectory (columns of X, U); c: column of A, Bd (= b, or the list position in a sparse iteration)
     const int bd = blockDim.x, tid = threadIdx.x;
     int row = 0;
 #pragma unroll
-    for (int i = 0; i < n * n; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, A + ((size_t)t * n * n + i) * B + c);
+    for (int i = 0; i < n * n; ++i, ++row)
+        cp_async<sizeof(T)>(stage + row * bd + tid, ab_blocked ? A + ab_off(n * n + n * m, t, i, c, B) : A + ((size_t)t * n * n + i) * B + c);
 #pragma unroll
-    for (int i = 0; i < n * m; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, Bd + ((size_t)t * n * m + i) * B + c);
+    for (int i = 0; i < n * m; ++i, ++row)
+        cp_async<sizeof(T)>(stage + row * bd + tid,
+                            ab_blocked ? A + ab_off(n * n + n * m, t, n * n + i, c, B) : Bd + ((size_t)t * n * m + i) * B + c);
 #pragma unroll
     for (int i = 0; i < n; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, X + ((size_t)t * n + i) * B + b);
 #pragma unroll
@@ -65,7 +68,7 @@ __global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, c
                                 const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
                                 T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
                                 const unsigned int *__restrict__ gate, const T *__restrict__ mu,
-                                const __grid_constant__ SparseArgs sa)
+                                const __grid_constant__ SparseArgs sa, int ab_blocked)
 {
     constexpr int L = n * n + n * m + n + m;
     extern __shared__ __align__(16) unsigned char ring_raw[];
@@ -83,7 +86,7 @@ __global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, c
     const int stage_elems = L * blockDim.x;
 #pragma unroll
     for (int s = 0; s < DEPTH; ++s) {
-        if (N - 1 - s >= 0) bwd_issue<T, n, m>(ring + s * stage_elems, N - 1 - s, b, cAB, B, X, U, A, Bd);
+        if (N - 1 - s >= 0) bwd_issue<T, n, m>(ring + s * stage_elems, N - 1 - s, b, cAB, B, X, U, A, Bd, ab_blocked);
         cp_async_commit();
     }
     const T mu_b = mu ? mu[b] : T(0);                                    // regularisation (RegArgs), 0 in the reference
@@ -230,7 +233,7 @@ __global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, c
             for (int i = 0; i < n; ++i) K[(((size_t)t * m + j) * n + i) * B + b] = Kt[j][i];
             k[((size_t)t * m + j) * B + b] = kt[j];
         }
-        if (t - DEPTH >= 0) bwd_issue<T, n, m>(ring + stage * stage_elems, t - DEPTH, b, cAB, B, X, U, A, Bd);
+        if (t - DEPTH >= 0) bwd_issue<T, n, m>(ring + stage * stage_elems, t - DEPTH, b, cAB, B, X, U, A, Bd, ab_blocked);
         cp_async_commit();
         stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
     }
@@ -251,7 +254,7 @@ backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, 
                            const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
                            T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
                            const unsigned int *__restrict__ gate, const T *__restrict__ mu,
-                           const __grid_constant__ SparseArgs sa)
+                           const __grid_constant__ SparseArgs sa, int ab_blocked)
 {
     constexpr int n = 4, L = 25, LP = 26, SLOTS = 8;       // LP: padded slot stride (bank-conflict free LDS.128)
     extern __shared__ __align__(16) unsigned char lanes_raw[];
@@ -272,23 +275,28 @@ backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, 
     const bool valid = blockIdx.x * SLOTS + s < n_items && (!active || active[b] != 0);
     if (__ballot_sync(0xffffffffu, valid) == 0u) return;
 
-    // cooperative fill of one ring stage: element e = row * 8 + slot, 32 elements per LDGSTS
+    // cooperative fill of one ring stage: element e = row * 8 + slot, 32 elements per LDGSTS.  Lane (f_row0, f_slot)
+    // copies rows f_row0 + 4 i of slot f_slot: i < 4 are rows of A, i = 4 of B, i = 5 of x, i = 6 is u (f_row0 == 0
+    // only) -- so every source is a base pointer fixed before the scan plus t times a fixed stride.
     const int f_slot = lane & 7, f_row0 = lane >> 3;
     const int f_b = item(f_slot);
     // column of A, Bd: the trajectory, or in a sparse iteration its list position (where K1 wrote them, coalesced)
     const int f_c = sparse ? min(blockIdx.x * SLOTS + f_slot, n_items - 1) : f_b;
+    const T *pA = ab_blocked ? A + ab_off(20, 0, f_row0, f_c, B) : A + (size_t)f_row0 * B + f_c;
+    const T *pB = ab_blocked ? A + ab_off(20, 0, 16 + f_row0, f_c, B) : Bd + (size_t)f_row0 * B + f_c;
+    const T *pX = X + (size_t)f_row0 * B + f_b, *pU = U + f_b;
+    const size_t ab_step = (((size_t)B + 31) >> 5) * 20 * 32;           // blocked: elements per timestep
+    const size_t tsA = ab_blocked ? ab_step : (size_t)16 * B, tsB = ab_blocked ? ab_step : (size_t)4 * B;
+    const size_t rsA = ab_blocked ? (size_t)4 * 32 : (size_t)4 * B;     // four rows further
+    T *const f_dst = ring + f_slot * LP + f_row0;
     auto issue = [&](int stage, int t) {
+        T *dst = f_dst + stage * SLOTS * LP;
+        const T *a = pA + (size_t)t * tsA;
 #pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const int row = f_row0 + 4 * i;
-            if (row < L) {
-                const T *src = row < 16 ? A + ((size_t)t * 16 + row) * B + f_c
-                             : row < 20 ? Bd + ((size_t)t * 4 + (row - 16)) * B + f_c
-                             : row < 24 ? X + ((size_t)t * 4 + (row - 20)) * B + f_b
-                                        : U + (size_t)t * B + f_b;
-                cp_async<sizeof(T)>(ring + (stage * SLOTS + f_slot) * LP + row, src);
-            }
-        }
+        for (int i = 0; i < 4; ++i) cp_async<sizeof(T)>(dst + 4 * i, a + i * rsA);
+        cp_async<sizeof(T)>(dst + 16, pB + (size_t)t * tsB);
+        cp_async<sizeof(T)>(dst + 20, pX + (size_t)t * 4 * B);
+        if (f_row0 == 0) cp_async<sizeof(T)>(dst + 24, pU + (size_t)t * B);
     };
 #pragma unroll
     for (int st = 0; st < DEPTH; ++st) {

@@ -45,6 +45,17 @@ struct RegArgs {
     double factor, mu_min, mu_max;
 };
 
+// Blocked layout of the linearization inside ilqr_solve's workspace: AB[t][group of 32 columns][row][lane], rows =
+// the n*n entries of A_t followed by the n*m entries of B_t.  Everything a warp reads or writes for one timestep
+// (n(n+m) rows of 32 values) is ONE contiguous chunk (5 KB for n=4, m=1) instead of n(n+m) pieces a whole batch
+// row apart -- DRAM page locality for K1's stores and K2's streaming loads.  The public entry points
+// (ilqr_linearize, ilqr_backward) keep the documented [N][n][n][B] / [N][n][m][B] arrays.
+ILQR_DEV size_t ab_off(int rows, int t, int row, int col, int B)
+{
+    const size_t groups = ((size_t)B + 31) >> 5;
+    return ((((size_t)t * groups + ((size_t)col >> 5)) * rows + row) << 5) + (col & 31);
+}
+
 // Solver mode (tol > 0): trajectories converge at different iterations, and the late iterations of a solve
 // serve a small, scattered fraction of the batch.  The select kernels therefore keep a compacted list of the
 // trajectories entering the next iteration (its length is the n_active counter they maintain anyway), and

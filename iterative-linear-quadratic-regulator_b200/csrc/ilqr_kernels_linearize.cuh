@@ -33,7 +33,7 @@ ILQR_DEV void commit_linearize_point(const Sys &sys, T dt, int N, int B, int t, 
                                      const T *__restrict__ Xc, const T *__restrict__ Uc, const int *__restrict__ winner,
                                      const int *__restrict__ wslot, const int *__restrict__ active,
                                      const int *__restrict__ iters, int it, int do_linearize,
-                                     const int *__restrict__ pos)
+                                     const int *__restrict__ pos, int ab_blocked)
 {
     constexpr int n = Sys::N, m = Sys::M;
     int w = winner ? winner[b] : -1;
@@ -67,6 +67,17 @@ ILQR_DEV void commit_linearize_point(const Sys &sys, T dt, int N, int B, int t, 
     T Aj[n][n], Bj[n][m];
     step_jac<INTEG>(sys, dt, x, u, Aj, Bj, sys.time_scalar(t, phi ? phi[b] : T(0)));
     const int c = pos ? pos[b] : b;          // sparse iteration: compact column = position in the active list
+    if (ab_blocked) {                        // workspace layout of ilqr_solve (ab_off)
+        constexpr int R = n * n + n * m;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) A[ab_off(R, t, i * n + j, c, B)] = Aj[i][j];
+#pragma unroll
+            for (int j = 0; j < m; ++j) A[ab_off(R, t, n * n + i * m + j, c, B)] = Bj[i][j];
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < n; ++i) {
 #pragma unroll
@@ -84,7 +95,7 @@ __global__ void __launch_bounds__(128, Sys::N <= 4 ? 4 : 1) commit_linearize_ker
                                         const int *__restrict__ wslot, const int *__restrict__ active,
                                         const int *__restrict__ iters, int it, int do_linearize,
                                         const unsigned int *__restrict__ gate0, const unsigned int *__restrict__ gate1,
-                                        const __grid_constant__ SparseArgs sa)
+                                        const __grid_constant__ SparseArgs sa, int ab_blocked)
 {
     if (gate0 && *gate0 == 0u && *gate1 == 0u) return;   // nobody active now or in the previous iteration
     const int *pos = sparse_now(sa) ? sa.pos : nullptr;  // where K2 will look for A_t, B_t in this iteration
@@ -97,13 +108,13 @@ __global__ void __launch_bounds__(128, Sys::N <= 4 ? 4 : 1) commit_linearize_ker
         const size_t total = (size_t)(N + 1) * cnt, stride = (size_t)nblk * blockDim.x;
         for (size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride)
             commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, (int)(item / cnt), sa.prev[item % cnt], phi, X, U, A, Bd, Xc,
-                                                  Uc, winner, wslot, active, iters, it, do_linearize, pos);
+                                                  Uc, winner, wslot, active, iters, it, do_linearize, pos, ab_blocked);
         return;
     }
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)(N + 1) * B) return;
     commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, (int)(gid / B), (int)(gid % B), phi, X, U, A, Bd, Xc, Uc, winner,
-                                          wslot, active, iters, it, do_linearize, pos);
+                                          wslot, active, iters, it, do_linearize, pos, ab_blocked);
 }
 
 // materialised cost expansion (system_base.py:212-219); one thread per (t,b), t in [0,N]
