@@ -393,9 +393,18 @@ static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const voi
         if (!bs_env && bs > 128) bs = 128;
         // lazy waves: the warps of one trajectory group (one per step size) share a block, hence an L1
         if (!bs_env && h->lazy && n_alpha <= 4 && threads >= (size_t)148 * 16 * 32 * n_alpha) bs = 32 * n_alpha;
-        rollout_kernel<Sys, decltype(qc), I, T><<<grid_for(threads, bs), bs, 0, st>>>(
-            sys, qc, h->p.N, h->p.B, n_alpha, al, (const T *)phi, (const T *)x0, (const T *)X, (const T *)U, (const T *)k,
-            (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref, sp, list, list_count, sa);
+        auto go = [&](const auto &cost) {
+            rollout_kernel<Sys, std::decay_t<decltype(cost)>, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
+                sys, cost, h->p.N, h->p.B, n_alpha, al, (const T *)phi, (const T *)x0, (const T *)X, (const T *)U,
+                (const T *)k, (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref, sp, list,
+                list_count, sa);
+        };
+#ifndef ILQR_USER_SYS
+        // diagonal weights (every reference script): the compact cost keeps the kernel's constants in uniform registers
+        if (qc.diag) go(DiagCost<T, Sys::N, Sys::M>(qc));
+        else
+#endif
+            go(qc);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });

@@ -256,7 +256,7 @@ backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, 
                            const unsigned int *__restrict__ gate, const T *__restrict__ mu,
                            const __grid_constant__ SparseArgs sa, int ab_blocked)
 {
-    constexpr int n = 4, L = 25, LP = 26, SLOTS = 8;       // LP: padded slot stride (bank-conflict free LDS.128)
+    constexpr int n = 4, LP = 26, SLOTS = 8;       // LP: padded slot stride (bank-conflict free LDS.128)
     extern __shared__ __align__(16) unsigned char lanes_raw[];
     T *ring = reinterpret_cast<T *>(lanes_raw);             // [DEPTH][SLOTS][LP]
     T *exQ = ring + DEPTH * SLOTS * LP;                     // [SLOTS][4]   Q_ux exchange

@@ -27,8 +27,13 @@ __global__ void step_kernel(const __grid_constant__ Sys sys, T dt, int B, int t,
 // K1.  One thread per (t,b), t in [0,N].  If the trajectory ran the previous iteration (iters[b] == it) and
 // accepted a candidate (winner[b] >= 0) the thread first copies it (Xc/Uc slab winner[b]) into the nominal X/U; if
 // the trajectory is active it then writes the discrete Jacobians about that nominal point.
+// Written as CONVERGENT code: a lane without work (out of range, inactive trajectory, t = N) follows its warp with
+// its loads redirected and its stores masked instead of returning early, and warps leave only as a whole.  ptxas
+// keeps kernel and system constants in uniform registers only in code it can prove convergent; after a per-thread
+// return it falls back to per-thread registers for them (40-70 registers more in these kernels, and DFMAs with
+// three register operands, which issue at 3 instead of 2 cycles on sm_100a).
 template <class Sys, int INTEG, typename T>
-ILQR_DEV void commit_linearize_point(const Sys &sys, T dt, int N, int B, int t, int b, const T *__restrict__ phi,
+ILQR_DEV void commit_linearize_point(const Sys &sys, T dt, int N, int B, bool valid, int t, int b, const T *__restrict__ phi,
                                      T *__restrict__ X, T *__restrict__ U, T *__restrict__ A, T *__restrict__ Bd,
                                      const T *__restrict__ Xc, const T *__restrict__ Uc, const int *__restrict__ winner,
                                      const int *__restrict__ wslot, const int *__restrict__ active,
@@ -36,36 +41,33 @@ ILQR_DEV void commit_linearize_point(const Sys &sys, T dt, int N, int B, int t, 
                                      const int *__restrict__ pos, int ab_blocked)
 {
     constexpr int n = Sys::N, m = Sys::M;
-    int w = winner ? winner[b] : -1;
+    const unsigned full = 0xffffffffu;
+    if (!valid) { t = 0; b = 0; }
+    int w = (valid && winner) ? winner[b] : -1;
     if (iters && iters[b] != it) w = -1;                 // nothing pending: committed earlier, or never ran
-    const bool act = do_linearize && (active ? active[b] != 0 : true) && t < N;
-    if (w < 0 && !act) return;
+    const bool act = valid && do_linearize && (active ? active[b] != 0 : true) && t < N;
+    if (!__any_sync(full, w >= 0 || act)) return;
     T x[n], u[m];
-    if (w >= 0) {
-        // lazy line search: candidates of the later waves are stored at the trajectory's list position
-        const int col = wslot ? wslot[b] : b;
-        const T *xs = Xc + (size_t)w * (N + 1) * n * B, *us = Uc + (size_t)w * N * m * B;
+    // lazy line search: candidates of the later waves are stored at the trajectory's list position
+    const int col = (w >= 0 && wslot) ? wslot[b] : b;
+    const T *xs = w >= 0 ? Xc + (size_t)w * (N + 1) * n * B : X, *us = w >= 0 ? Uc + (size_t)w * N * m * B : U;
+    const int tu = t < N ? t : N - 1;                    // t = N has no control: read a valid one, never used
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
-            x[i] = xs[((size_t)t * n + i) * B + col];
-            X[((size_t)t * n + i) * B + b] = x[i];
-        }
+    for (int i = 0; i < n; ++i) x[i] = xs[((size_t)t * n + i) * B + col];
+#pragma unroll
+    for (int j = 0; j < m; ++j) u[j] = us[((size_t)tu * m + j) * B + col];
+    if (w >= 0) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) X[((size_t)t * n + i) * B + b] = x[i];
         if (t < N) {
 #pragma unroll
-            for (int j = 0; j < m; ++j) {
-                u[j] = us[((size_t)t * m + j) * B + col];
-                U[((size_t)t * m + j) * B + b] = u[j];
-            }
+            for (int j = 0; j < m; ++j) U[((size_t)t * m + j) * B + b] = u[j];
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < n; ++i) x[i] = X[((size_t)t * n + i) * B + b];
-#pragma unroll
-        for (int j = 0; j < m; ++j) u[j] = U[((size_t)t * m + j) * B + b];
     }
-    if (!act) return;
+    if (!__any_sync(full, act)) return;
     T Aj[n][n], Bj[n][m];
     step_jac<INTEG>(sys, dt, x, u, Aj, Bj, sys.time_scalar(t, phi ? phi[b] : T(0)));
+    if (!act) return;
     const int c = pos ? pos[b] : b;          // sparse iteration: compact column = position in the active list
     if (ab_blocked) {                        // workspace layout of ilqr_solve (ab_off)
         constexpr int R = n * n + n * m;
@@ -106,15 +108,21 @@ __global__ void __launch_bounds__(128, Sys::N <= 4 ? 4 : 1) commit_linearize_ker
         const unsigned int nblk = min(gridDim.x, 148u * 8u);
         if (blockIdx.x >= nblk) return;
         const size_t total = (size_t)(N + 1) * cnt, stride = (size_t)nblk * blockDim.x;
-        for (size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride)
-            commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, (int)(item / cnt), sa.prev[item % cnt], phi, X, U, A, Bd, Xc,
-                                                  Uc, winner, wslot, active, iters, it, do_linearize, pos, ab_blocked);
+        // the loop bound is the warp's first item, so a warp runs its last round together
+        for (size_t base = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
+            const size_t item = base + (threadIdx.x & 31u);
+            const bool valid = item < total;
+            commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, valid, valid ? (int)(item / cnt) : 0,
+                                                  valid ? sa.prev[item % cnt] : 0, phi, X, U, A, Bd, Xc, Uc, winner,
+                                                  wslot, active, iters, it, do_linearize, pos, ab_blocked);
+        }
         return;
     }
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)(N + 1) * B) return;
-    commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, (int)(gid / B), (int)(gid % B), phi, X, U, A, Bd, Xc, Uc, winner,
-                                          wslot, active, iters, it, do_linearize, pos, ab_blocked);
+    const bool valid = gid < (size_t)(N + 1) * B;
+    commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, valid, valid ? (int)(gid / B) : 0, valid ? (int)(gid % B) : 0, phi,
+                                          X, U, A, Bd, Xc, Uc, winner, wslot, active, iters, it, do_linearize, pos,
+                                          ab_blocked);
 }
 
 // materialised cost expansion (system_base.py:212-219); one thread per (t,b), t in [0,N]

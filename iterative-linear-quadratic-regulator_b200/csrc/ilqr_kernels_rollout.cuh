@@ -31,7 +31,7 @@ ILQR_DEV void fwd_load(FwdIn<T, n, m> &d, int t, int b, int B, const T *__restri
 template <int INTEG, class Sys, class Cost, typename T>
 ILQR_DEV void rollout_step(const Sys &sys, const Cost &qc, const FwdIn<T, Sys::N, Sys::M> &in,
                            T alpha, int t, int bw, int B, T phi, T *x, T &cost, T *__restrict__ Xw,
-                           T *__restrict__ Uw)
+                           T *__restrict__ Uw, bool valid)
 {
     constexpr int n = Sys::N, m = Sys::M;
     T u[m], xn[n];
@@ -42,10 +42,12 @@ ILQR_DEV void rollout_step(const Sys &sys, const Cost &qc, const FwdIn<T, Sys::N
         for (int i = 0; i < n; ++i) s += in.K[j][i] * (x[i] - in.xo[i]);
         u[j] = in.uo[j] + alpha * in.kk[j] + s;
     }
+    if (valid) {
 #pragma unroll
-    for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + bw] = x[i];
+        for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + bw] = x[i];
 #pragma unroll
-    for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + bw] = u[j];
+        for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + bw] = u[j];
+    }
     cost += qc.stage(x, u);
     step<INTEG>(sys, qc.dt, x, u, xn, sys.time_scalar(t, phi));
 #pragma unroll
@@ -83,28 +85,31 @@ __global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys s
         if (sparse_all(sa)) n_alpha = sa.n_alpha_all;
     }
     int ai, b, bw;        // bw: column of the candidate slabs / cost_alpha this thread writes
+    // No per-thread early return: a lane without work follows its warp on trajectory 0's data with its stores
+    // masked, so the time loop below is convergent code (whole warps without work leave together).
+    bool valid = true;
     if (wg < ngrp * n_alpha) {
         ai = (int)(wg % n_alpha);
         const unsigned int idx = (unsigned int)(wg / n_alpha) * 32u + (threadIdx.x & 31u);
         if (list) {                                                      // lazy wave: compacted trajectory list;
-            if (idx >= min(*list_count, (unsigned int)B)) return;        // results stored at the list position
-            b = list[idx];
+            valid = idx < min(*list_count, (unsigned int)B);             // results stored at the list position
+            b = valid ? list[idx] : 0;
         } else {
-            if (idx >= (unsigned int)B) return;
-            b = (int)idx;
+            valid = idx < (unsigned int)B;
+            b = valid ? (int)idx : 0;
         }
         bw = (int)idx;
     } else {                                                             // speculative extra threads
         const size_t e = gid - ngrp * n_alpha * 32;
-        if (list || sp.cap == 0 || e >= (size_t)sp.cap * sp.n2) return;
-        const int q = (int)(e % sp.cap);
-        const unsigned int cnt = min(*sp.count_cur, (unsigned int)sp.cap);
-        if ((unsigned int)q >= cnt) return;
-        b = sp.list_cur[q];
+        valid = !(list || sp.cap == 0 || e >= (size_t)sp.cap * sp.n2);
+        const int q = valid ? (int)(e % sp.cap) : 0;
+        if (valid) valid = (unsigned int)q < min(*sp.count_cur, (unsigned int)sp.cap);
+        b = valid ? sp.list_cur[q] : 0;
         bw = b;
-        ai = n_alpha + (int)(e / sp.cap);
+        ai = valid ? n_alpha + (int)(e / sp.cap) : 0;
     }
-    if (active && !active[b]) return;
+    if (valid && active && !active[b]) valid = false;
+    if (!__any_sync(0xffffffffu, valid)) return;
     const T alpha = (T)alphas.a[ai];
     T *Xw = Xc + (size_t)ai * (N + 1) * n * B, *Uw = Uc + (size_t)ai * N * m * B;
     T x[n], cost = T(0);
@@ -140,10 +145,12 @@ __global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys s
                 for (int i = 0; i < n; ++i) s += K[(((size_t)t * m + j) * n + i) * B + b] * dx[i];
                 u[j] = U_old[((size_t)t * m + j) * B + b] + alpha * k[((size_t)t * m + j) * B + b] + s;
             }
+            if (valid) {
 #pragma unroll
-            for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + bw] = x[i];
+                for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + bw] = x[i];
 #pragma unroll
-            for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + bw] = u[j];
+                for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + bw] = u[j];
+            }
             cost += qc.stage(x, u);
             step<INTEG>(sys, qc.dt, x, u, xn, sys.time_scalar(t, ph));
 #pragma unroll
@@ -155,13 +162,13 @@ __global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys s
     fwd_load(in0, 0, b, B, X_old, U_old, k, K);
     for (int t = 0; t < N; t += 2) {
         if (t + 1 < N) fwd_load(in1, t + 1, b, B, X_old, U_old, k, K);
-        rollout_step<INTEG>(sys, qc, in0, alpha, t, bw, B, ph, x, cost, Xw, Uw);
+        rollout_step<INTEG>(sys, qc, in0, alpha, t, bw, B, ph, x, cost, Xw, Uw, valid);
         if (t + 1 >= N) break;
         if (t + 2 < N) fwd_load(in0, t + 2, b, B, X_old, U_old, k, K);
-        rollout_step<INTEG>(sys, qc, in1, alpha, t + 1, bw, B, ph, x, cost, Xw, Uw);
+        rollout_step<INTEG>(sys, qc, in1, alpha, t + 1, bw, B, ph, x, cost, Xw, Uw, valid);
 #if ILQR_REJECT
         if (can_reject && !(cost <= c_ref)) {
-            cost_alpha[(size_t)ai * B + bw] = cost;                       // already > cost to beat (or NaN): rejected
+            if (valid) cost_alpha[(size_t)ai * B + bw] = cost;            // already > cost to beat (or NaN): rejected
             return;
         }
 #endif
@@ -171,17 +178,18 @@ __global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys s
     fwd_load(in0, 0, b, B, X_old, U_old, k, K);
     for (int t = 0; t < N; ++t) {
         if (t + 1 < N) fwd_load(in1, t + 1, b, B, X_old, U_old, k, K);
-        rollout_step<INTEG>(sys, qc, in0, alpha, t, bw, B, ph, x, cost, Xw, Uw);
+        rollout_step<INTEG>(sys, qc, in0, alpha, t, bw, B, ph, x, cost, Xw, Uw, valid);
         in0 = in1;
 #if ILQR_REJECT
         if (can_reject && !(cost <= c_ref)) {
-            cost_alpha[(size_t)ai * B + bw] = cost;
+            if (valid) cost_alpha[(size_t)ai * B + bw] = cost;
             return;
         }
 #endif
     }
 #endif
     }
+    if (!valid) return;
 #pragma unroll
     for (int i = 0; i < n; ++i) Xw[((size_t)N * n + i) * B + bw] = x[i];
     cost_alpha[(size_t)ai * B + bw] = cost + qc.terminal(x);              // :245

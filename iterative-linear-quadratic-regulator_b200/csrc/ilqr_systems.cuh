@@ -53,11 +53,16 @@ ILQR_DEV void sincos_t(double x, double *s, double *c)
     pc = fma(z, pc, kTrig[9]);
     pc = fma(z, pc, kTrig[10]);
     pc = fma(z, pc, kTrig[11]);
-    const double sn = fma(z * r, ps, r);
-    const double cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+    // operand forms chosen for the FP64 pipe's register ports (a DFMA with three distinct register sources
+    // takes 3 issue cycles instead of 2 on sm_100a; scripts/micro/fp64_operands.cu): r + r*(z*ps) reads r twice,
+    // and the cosine continues the Horner chain through the constants -1/2 and 1
+    const double sn = fma(r, z * ps, r);
+    const double cs = fma(z, fma(z, pc, -0.5), 1.0);
     const double a = (k & 1) ? cs : sn, b = (k & 1) ? sn : cs;
-    *s = (k & 2) ? -a : a;
-    *c = ((k + 1) & 2) ? -b : b;
+    // quadrant signs by flipping the sign bit in the integer pipe (a negate-and-select would spend two FP64
+    // pipe slots per sincos on DADDs)
+    *s = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));
+    *c = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
 }
 // FP32 counterpart (optional 1e-4 mode): three-constant Cody-Waite reduction and the cephes sinf/cosf
 // polynomials on [-pi/4, pi/4]; ~2e-7 absolute error for |x| up to ~1e5, no slow path.
@@ -100,6 +105,8 @@ ILQR_DEV float rcp_t(float d)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
     return fmaf(y, fmaf(-d, y, 1.0f), y);                    // one Newton step: ~1 ulp
 }
+ILQR_DEV double fma_t(double a, double b, double c) { return fma(a, b, c); }
+ILQR_DEV float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 ILQR_DEV double sqrt_t(double x) { return sqrt(x); }
 ILQR_DEV float sqrt_t(float x) { return sqrtf(x); }
 ILQR_DEV double abs_t(double x) { return fabs(x); }
@@ -168,9 +175,15 @@ struct DoublePendulumSys {
         const T s12 = s1 * c2 + c1 * s2;
         const T m11 = m11_0 + c * c2, m12 = m12_0 + T(0.5) * c * c2, m22 = m12_0;
         const T inv = rcp_t(m11 * m22 - m12 * m12);
-        const T cs2 = c * s2;
-        T h1 = u[0] + T(0.5) * cs2 * (T(2) * q1d * q2d + q2d * q2d) - g1 * s12 - g2 * s1 - d1 * q1d;
-        T h2 = -T(0.5) * cs2 * (q1d * q1d) - g1 * s12 - d2 * q2d;
+        // h1 = u1 + (c s2 / 2)(2 q1' q2' + q2'^2) - g1 s12 - g2 s1 - d1 q1',  h2 = [u2] - (c s2 / 2) q1'^2 - g1 s12 - d2 q2'
+        // written so that most FMAs read at most two registers besides a constant (see sincos_t)
+        const T hcs2 = (T(0.5) * c) * s2, g = g1 * s12;
+        const T w = fma_t(T(2), q1d, q2d) * q2d;
+        T h1 = fma_t(hcs2, w, u[0]) - g;
+        h1 = fma_t(-g2, s1, h1);
+        h1 = fma_t(-d1, q1d, h1);
+        T h2 = -fma_t(hcs2, q1d * q1d, g);
+        h2 = fma_t(-d2, q2d, h2);
         if (M == 2) h2 += u[M - 1];
         a[0] = inv * (m22 * h1 - m12 * h2);
         a[1] = inv * (m11 * h2 - m12 * h1);
@@ -791,5 +804,38 @@ struct QuadCost {
         }
     }
 };
+
+// The rollout kernel's view of a QuadCost whose three weights are diagonal (every reference script): the
+// diagonals only, so the kernel keeps ~13 constants in uniform registers instead of three dense matrices,
+// and the stage cost has no runtime branch.  Same expressions as QuadCost::stage / ::terminal with diag set.
+template <typename T, int n, int m>
+struct DiagCost {
+    static constexpr bool QUADRATIC = true;
+    T dt;
+    T xt[n], hq[n], hr[m], hqf[n];   // halved diagonals: (0.5 d) q d == ((0.5 q) d) d bit for bit (scaling by 1/2 is exact)
+    int monotone;
+    explicit DiagCost(const QuadCost<T, n, m> &c) : dt(c.dt), monotone(c.monotone)
+    {
+        for (int i = 0; i < n; ++i) { xt[i] = c.xt[i]; hq[i] = T(0.5) * c.Qs[i][i]; hqf[i] = T(0.5) * c.Qfs[i][i]; }
+        for (int j = 0; j < m; ++j) hr[j] = T(0.5) * c.Rs[j][j];
+    }
+    ILQR_DEV T stage(const T *x, const T *u) const
+    {
+        T cx = T(0), cu = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) { const T d = x[i] - xt[i]; cx += (hq[i] * d) * d; }
+#pragma unroll
+        for (int j = 0; j < m; ++j) cu += (hr[j] * u[j]) * u[j];
+        return (cx + cu) * dt;
+    }
+    ILQR_DEV T terminal(const T *x) const
+    {
+        T c = T(0);
+#pragma unroll
+        for (int j = 0; j < n; ++j) { const T d = x[j] - xt[j]; c += (hqf[j] * d) * d; }
+        return c;
+    }
+};
+
 
 }  // namespace ilqr
