@@ -277,8 +277,8 @@ static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U,
     });
 }
 
-template <typename T, int n, int m, int DEPTH, class Cost>
-static int launch_backward_depth(Handle *h, int bs, const Cost &qc, const void *X, const void *U,
+template <typename T, int n, int m, int DEPTH, int bs, class Cost>
+static int launch_backward_depth(Handle *h, const Cost &qc, const void *X, const void *U,
                                  const void *A, const void *Bd, void *K, void *k, const int *active,
                                  const unsigned int *gate, const void *mu, cudaStream_t st, const SparseArgs &sa,
                                  int ab_blocked)
@@ -287,12 +287,12 @@ static int launch_backward_depth(Handle *h, int bs, const Cost &qc, const void *
     const size_t smem = (size_t)DEPTH * L * bs * sizeof(T);
     static size_t configured = 0;           // per instantiation: opt in to > 48 KB dynamic shared memory once
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(backward_kernel<Cost, T, n, m, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(backward_kernel<Cost, T, n, m, DEPTH, bs>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) { h->last_cuda = (int)e; return ILQR_E_CUDA; }
         configured = smem;
     }
-    backward_kernel<Cost, T, n, m, DEPTH><<<grid_for(h->p.B, bs), bs, smem, st>>>(
+    backward_kernel<Cost, T, n, m, DEPTH, bs><<<grid_for(h->p.B, bs), bs, smem, st>>>(
         qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active, gate,
         (const T *)mu, sa, ab_blocked);
     ILQR_CHECK_LAUNCH(h);
@@ -333,11 +333,11 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
         }
         if constexpr (Sys::N > 4) {
             // n = 12, m = 4: a ring stage is 208 rows; two stages of one warp fit the 227 KB limit
-            return launch_backward_depth<T, Sys::N, Sys::M, 2>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa, ab_blocked);
+            return launch_backward_depth<T, Sys::N, Sys::M, 2, 32>(h, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa, ab_blocked);
         } else {
             if (h->p.B <= 32768)
-                return launch_backward_depth<T, Sys::N, Sys::M, 8>(h, 32, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa, ab_blocked);
-            return launch_backward_depth<T, Sys::N, Sys::M, 4>(h, 64, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa, ab_blocked);
+                return launch_backward_depth<T, Sys::N, Sys::M, 8, 32>(h, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa, ab_blocked);
+            return launch_backward_depth<T, Sys::N, Sys::M, 4, 64>(h, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa, ab_blocked);
         }
     });
 }

@@ -24,30 +24,11 @@ ILQR_DEV void cp_async(void *smem_dst, const void *gsrc)
 ILQR_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING> ILQR_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
-// rows of one ring stage: A (n*n), Bd (n*m), x (n), u (m); element [row][tid]
-template <typename T, int n, int m>
-ILQR_DEV void bwd_issue(T *stage, int t, int b, int c, int B, const T *__restrict__ X, const T *__restrict__ U,
-                        const T *__restrict__ A, const T *__restrict__ Bd, int ab_blocked)
-{   // b: trajectory (columns of X, U); c: column of A, Bd (= b, or the list position in a sparse iteration)
-    const int bd = blockDim.x, tid = threadIdx.x;
-    int row = 0;
-#pragma unroll
-    for (int i = 0; i < n * n; ++i, ++row)
-        cp_async<sizeof(T)>(stage + row * bd + tid, ab_blocked ? A + ab_off(n * n + n * m, t, i, c, B) : A + ((size_t)t * n * n + i) * B + c);
-#pragma unroll
-    for (int i = 0; i < n * m; ++i, ++row)
-        cp_async<sizeof(T)>(stage + row * bd + tid,
-                            ab_blocked ? A + ab_off(n * n + n * m, t, n * n + i, c, B) : Bd + ((size_t)t * n * m + i) * B + c);
-#pragma unroll
-    for (int i = 0; i < n; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, X + ((size_t)t * n + i) * B + b);
-#pragma unroll
-    for (int i = 0; i < m; ++i, ++row) cp_async<sizeof(T)>(stage + row * bd + tid, U + ((size_t)t * m + i) * B + b);
-}
-
-template <typename T, int n, int m>
+// rows of one ring stage: A (n*n), Bd (n*m), x (n), u (m); element [row][tid] (filled by backward_kernel's issue())
+template <int bd, typename T, int n, int m>
 ILQR_DEV void bwd_read(BwdIn<T, n, m> &d, const T *stage)
 {
-    const int bd = blockDim.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     int row = 0;
 #pragma unroll
     for (int i = 0; i < n; ++i)
@@ -63,8 +44,8 @@ ILQR_DEV void bwd_read(BwdIn<T, n, m> &d, const T *stage)
     for (int j = 0; j < m; ++j, ++row) d.u[j] = stage[row * bd + tid];
 }
 
-template <class Cost, typename T, int n, int m, int DEPTH>
-__global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, const T *__restrict__ X,
+template <class Cost, typename T, int n, int m, int DEPTH, int BS>
+__global__ void __launch_bounds__(BS) backward_kernel(const __grid_constant__ Cost qc, int N, int B, const T *__restrict__ X,
                                 const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
                                 T *__restrict__ K, T *__restrict__ k, const int *__restrict__ active,
                                 const unsigned int *__restrict__ gate, const T *__restrict__ mu,
@@ -83,10 +64,37 @@ __global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, c
     }
     if (b >= B) return;
     if (active && !active[b]) return;
-    const int stage_elems = L * blockDim.x;
+    constexpr int stage_elems = L * BS, R = n * n + n * m;
+    // Sources of the ring: timesteps are requested in strictly decreasing order, so each is a pointer that steps
+    // back by a fixed stride.  In the solver's blocked layout (ab_off) the R rows of [A_t | B_t] of one trajectory are
+    // 32 elements apart: ONE pointer with compile-time offsets serves all of them (the index arithmetic of 25 copies
+    // per step used to be 60 % of the kernel's instructions).
+    const T *pab = ab_blocked ? A + ab_off(R, N - 1, 0, cAB, B) : nullptr;
+    const size_t ab_dec = (((size_t)B + 31) >> 5) * R * 32;
+    const T *px = X + (size_t)(N - 1) * n * B + b, *pu = U + (size_t)(N - 1) * m * B + b;
+    const size_t sB = (size_t)B;
+    auto issue = [&](T *stage, int t) {
+        T *dst = stage + threadIdx.x;
+        if (ab_blocked) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) cp_async<sizeof(T)>(dst + i * BS, pab + i * 32);
+            pab -= ab_dec;
+        } else {
+#pragma unroll
+            for (int i = 0; i < n * n; ++i) cp_async<sizeof(T)>(dst + i * BS, A + ((size_t)t * n * n + i) * B + cAB);
+#pragma unroll
+            for (int i = 0; i < n * m; ++i) cp_async<sizeof(T)>(dst + (n * n + i) * BS, Bd + ((size_t)t * n * m + i) * B + cAB);
+        }
+#pragma unroll
+        for (int i = 0; i < n; ++i) cp_async<sizeof(T)>(dst + (R + i) * BS, px + i * sB);
+#pragma unroll
+        for (int i = 0; i < m; ++i) cp_async<sizeof(T)>(dst + (R + n + i) * BS, pu + i * sB);
+        px -= n * sB;
+        pu -= m * sB;
+    };
 #pragma unroll
     for (int s = 0; s < DEPTH; ++s) {
-        if (N - 1 - s >= 0) bwd_issue<T, n, m>(ring + s * stage_elems, N - 1 - s, b, cAB, B, X, U, A, Bd, ab_blocked);
+        if (N - 1 - s >= 0) issue(ring + s * stage_elems, N - 1 - s);
         cp_async_commit();
     }
     const T mu_b = mu ? mu[b] : T(0);                                    // regularisation (RegArgs), 0 in the reference
@@ -109,7 +117,7 @@ __global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, c
     int stage = 0;
     for (int t = N - 1; t >= 0; --t) {
         cp_async_wait<DEPTH - 1>();                                       // the group holding step t has landed
-        bwd_read(cur, ring + stage * stage_elems);
+        bwd_read<BS>(cur, ring + stage * stage_elems);
         T lx[n], lu[m];
         // quadratic costs: l_xx = Q dt, l_uu = R dt, l_ux = 0 are constants folded into the sums below;
         // generated user costs (ilqr_user.cuh) provide the full state-dependent expansion
@@ -233,7 +241,7 @@ __global__ void backward_kernel(const __grid_constant__ Cost qc, int N, int B, c
             for (int i = 0; i < n; ++i) K[(((size_t)t * m + j) * n + i) * B + b] = Kt[j][i];
             k[((size_t)t * m + j) * B + b] = kt[j];
         }
-        if (t - DEPTH >= 0) bwd_issue<T, n, m>(ring + stage * stage_elems, t - DEPTH, b, cAB, B, X, U, A, Bd, ab_blocked);
+        if (t - DEPTH >= 0) issue(ring + stage * stage_elems, t - DEPTH);
         cp_async_commit();
         stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
     }

@@ -13,6 +13,7 @@ from helpers import (system_from_golden, cfg2_x0, ua_system, ua_oracle_problem, 
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-9
+UA_OL_PHYS = dict(g=9.81, m1=1.0, m2=1.0, l1=1.0, l2=1.0, d1=0.1, d2=0.1, theta1=1.0 / 12, theta2=1.0 / 12)
 ILL_POSED = 1e-3   # oracle drift under 1e-14 input noise above which a backward pass is not compared (see below)
 
 
@@ -341,6 +342,43 @@ def test_batched_other_systems_vs_oracle(oracle, golden, integ, lazy):
     sol.set_linesearch_waves((2, 2, 2, 4) if lazy else ())
     X, U, cost = sol.optimize_trajectory()
     ref = oracle.optimize_batch(p, x0, np.zeros((B, s.n_u, N)))
+    same = (sol.iterations == ref["iters"]) & (sol.status == ref["status"])
+    assert same.mean() > 0.98
+    ex = np.max(np.abs(X - ref["X"]), axis=(1, 2)) / np.max(np.abs(ref["X"]), axis=(1, 2))
+    ec = np.abs(cost - ref["cost"]) / np.abs(ref["cost"])
+    ek = np.max(np.abs(sol.K - ref["K"]), axis=(1, 2, 3)) / np.max(np.abs(ref["K"]), axis=(1, 2, 3))
+    assert np.quantile(ex[same], 0.95) < TOL and np.quantile(ec[same], 0.95) < TOL, (ex.max(), ec.max())
+    assert np.median(ek[same]) < TOL and np.quantile(ek[same], 0.95) < 1e-6
+
+
+@pytest.mark.parametrize("kind", ["double", "ua"])
+def test_dense_nonsymmetric_weights_vs_oracle(oracle, kind):
+    """Q, R, Q_f as DENSE, NON-SYMMETRIC matrices (the reference takes any array: the cost is the written quadratic
+    form, its derivatives come from autodiff, i.e. from the symmetric part; system_base.py:212-219).  Every shipped
+    script and golden file uses diagonal weights, which the rollout kernel serves through a compact diagonal cost;
+    this is the test of the general path.  A batch, two iterations from identical inputs, against the oracle."""
+    from class_files.iLQR_class import iLQR
+    from class_files.systems.double_pendulum_sys import MyDoublePendulum
+    from class_files.systems.UA_double_pendulum_sys import MyUADoublePendulum
+    rng = np.random.default_rng(77)
+    n, m = 4, (2 if kind == "double" else 1)
+
+    def spd_plus_skew(k, scale):
+        G = rng.standard_normal((k, k))
+        S = rng.standard_normal((k, k))
+        return scale * (G @ G.T / k + np.eye(k)) + 0.3 * scale * (S - S.T)   # PSD symmetric part, non-zero skew part
+
+    Q, R, Qf = spd_plus_skew(n, 1.0), spd_plus_skew(m, 0.5), spd_plus_skew(n, 50.0)
+    xt = np.array([np.pi, 0.0, 0.0, 0.0])
+    phys = UA_OL_PHYS
+    cls = MyDoublePendulum if kind == "double" else MyUADoublePendulum
+    s = cls(dt=0.01, x_target=xt, Q=Q, R=R, Q_f=Qf, integrator="rk4", **phys)
+    B, N = 256, 80
+    p = oracle.make_problem(kind, "rk4", N, 0.01, Q, R, Qf, xt, phys, maxiter=2, tol=0.0)
+    x0 = rng.uniform(-1.0, 1.0, (B, n))
+    sol = iLQR(s, N * 0.01, x0, np.zeros((m, N)), maxiter=2, tol=0.0, verbose=False)
+    X, U, cost = sol.optimize_trajectory()
+    ref = oracle.optimize_batch(p, x0, np.zeros((B, m, N)))
     same = (sol.iterations == ref["iters"]) & (sol.status == ref["status"])
     assert same.mean() > 0.98
     ex = np.max(np.abs(X - ref["X"]), axis=(1, 2)) / np.max(np.abs(ref["X"]), axis=(1, 2))
