@@ -52,10 +52,11 @@ ILQR_DEV void commit_linearize_point(const Sys &sys, T dt, int N, int B, bool va
     const int col = (w >= 0 && wslot) ? wslot[b] : b;
     const T *xs = w >= 0 ? Xc + (size_t)w * (N + 1) * n * B : X, *us = w >= 0 ? Uc + (size_t)w * N * m * B : U;
     const int tu = t < N ? t : N - 1;                    // t = N has no control: read a valid one, never used
+    const bool need = w >= 0 || act;                     // a lane with nothing to commit or linearize reads nothing
 #pragma unroll
-    for (int i = 0; i < n; ++i) x[i] = xs[((size_t)t * n + i) * B + col];
+    for (int i = 0; i < n; ++i) x[i] = need ? xs[((size_t)t * n + i) * B + col] : T(0);
 #pragma unroll
-    for (int j = 0; j < m; ++j) u[j] = us[((size_t)tu * m + j) * B + col];
+    for (int j = 0; j < m; ++j) u[j] = need ? us[((size_t)tu * m + j) * B + col] : T(0);
     if (w >= 0) {
 #pragma unroll
         for (int i = 0; i < n; ++i) X[((size_t)t * n + i) * B + b] = x[i];
