@@ -401,7 +401,9 @@ static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const voi
         };
 #ifndef ILQR_USER_SYS
         // diagonal weights (every reference script): the compact cost keeps the kernel's constants in uniform registers
-        if (qc.diag) go(DiagCost<T, Sys::N, Sys::M>(qc));
+        // (n <= 4 only: with the compact cost ptxas hoists the LTV model's matrix constants into registers and feeds
+        // them to the FP64 pipe through R2UR moves -- 1.75x slower than its kernel with the dense cost)
+        if (Sys::N <= 4 && qc.diag) go(DiagCost<T, Sys::N, Sys::M>(qc));
         else
 #endif
             go(qc);

@@ -85,9 +85,36 @@ __global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys s
         if (sparse_all(sa)) n_alpha = sa.n_alpha_all;
     }
     int ai, b, bw;        // bw: column of the candidate slabs / cost_alpha this thread writes
-    // No per-thread early return: a lane without work follows its warp on trajectory 0's data with its stores
-    // masked, so the time loop below is convergent code (whole warps without work leave together).
     bool valid = true;
+    if constexpr (n > 4) {
+        // The n = 12 LTV model multiplies by 336 matrix constants per step.  Its instantiation keeps per-thread exits:
+        // in convergent form ptxas hoists part of the matrices into registers and feeds them to the FP64 pipe through
+        // R2UR moves (29 instead of 17 ms per rollout wave at B=32768, N=1000).
+        if (wg < ngrp * n_alpha) {
+            ai = (int)(wg % n_alpha);
+            const unsigned int idx = (unsigned int)(wg / n_alpha) * 32u + (threadIdx.x & 31u);
+            if (list) {                                                  // lazy wave: compacted trajectory list;
+                if (idx >= min(*list_count, (unsigned int)B)) return;    // results stored at the list position
+                b = list[idx];
+            } else {
+                if (idx >= (unsigned int)B) return;
+                b = (int)idx;
+            }
+            bw = (int)idx;
+        } else {                                                         // speculative extra threads
+            const size_t e = gid - ngrp * n_alpha * 32;
+            if (list || sp.cap == 0 || e >= (size_t)sp.cap * sp.n2) return;
+            const int q = (int)(e % sp.cap);
+            const unsigned int cnt = min(*sp.count_cur, (unsigned int)sp.cap);
+            if ((unsigned int)q >= cnt) return;
+            b = sp.list_cur[q];
+            bw = b;
+            ai = n_alpha + (int)(e / sp.cap);
+        }
+        if (active && !active[b]) return;
+    } else {
+    // No per-thread early return: a lane without work follows its warp with its stores masked, so the time loop
+    // below is convergent code (whole warps without work leave together); see commit_linearize_point.
     if (wg < ngrp * n_alpha) {
         ai = (int)(wg % n_alpha);
         const unsigned int idx = (unsigned int)(wg / n_alpha) * 32u + (threadIdx.x & 31u);
@@ -112,6 +139,7 @@ __global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys s
     // ptxas schedule the whole time loop 17 % slower -- measured)
     if (valid && active && !active[b]) valid = false;
     if (!__any_sync(0xffffffffu, valid)) return;
+    }
     const T alpha = (T)alphas.a[ai];
     T *Xw = Xc + (size_t)ai * (N + 1) * n * B, *Uw = Uc + (size_t)ai * N * m * B;
     T x[n], cost = T(0);
@@ -148,12 +176,10 @@ __global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys s
                 for (int i = 0; i < n; ++i) s += K[(((size_t)t * m + j) * n + i) * B + b] * dx[i];
                 u[j] = U_old[((size_t)t * m + j) * B + b] + alpha * k[((size_t)t * m + j) * B + b] + s;
             }
-            if (valid) {
 #pragma unroll
-                for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + bw] = x[i];
+            for (int i = 0; i < n; ++i) Xw[((size_t)t * n + i) * B + bw] = x[i];
 #pragma unroll
-                for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + bw] = u[j];
-            }
+            for (int j = 0; j < m; ++j) Uw[((size_t)t * m + j) * B + bw] = u[j];
             cost += qc.stage(x, u);
             step<INTEG>(sys, qc.dt, x, u, xn, sys.time_scalar(t, ph));
 #pragma unroll
