@@ -336,7 +336,11 @@ def main():
     dom = max(("linearize", "backward", "rollout"), key=lambda k: ktimes[k][0])
     roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
             "frac": kern[dom]["achieved_GBps"] / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
-            "note": "rollout is FP64-pipe/latency bound at this batch, not HBM bound (DESIGN.md); "
+            "fp64_pipe_active_pct": traffic.get("fp64_pipe_active_pct", {}).get(dom),
+            "note": "rollout is FP64-pipe/latency bound at this batch, not HBM bound (DESIGN.md section 4; "
+                    "fp64_pipe_active_pct = ncu sm__pipe_fp64_cycles_active of the committed capture, averaged over the "
+                    "kernel class incl. the lone-warp alpha=0 rollout; 100 % is out of reach for this instruction mix: "
+                    "three-register DFMAs issue at 3 cycles); "
                     "see roofline_backward for the HBM-bound kernel north_star names"}
     roof_b = {"bound": "hbm", "kernel": "backward", "achieved": kern["backward"]["achieved_GBps"], "peak": peak,
               "unit": "GB/s", "frac": kern["backward"]["achieved_GBps"] / peak, "traffic": traffic.get("backward")}

@@ -40,11 +40,20 @@ def traffic(rep, key, out):
     # one bucket per iLQR iteration: K1 (linearize) opens it; the rollout waves (and the two K2 kernels of a large
     # batch) of an iteration are summed, matching bench.py's per-iteration kernel times
     buckets = []
+    pipe = {}      # kernel class -> [sum of duration * fp64 pipe %, sum of duration]
     for r in rows[2:]:
         name = r[idx["Kernel Name"]]
         cls = "rollout" if "rollout" in name else "linearize" if "linearize" in name else "backward" if "backward" in name else None
         if cls is None:
             continue
+        try:
+            dur = float(r[idx["gpu__time_duration.sum"]].replace(",", ""))
+            pct = float(r[idx["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]].replace(",", ""))
+            acc_p = pipe.setdefault(cls, [0.0, 0.0])
+            acc_p[0] += dur * pct
+            acc_p[1] += dur
+        except (KeyError, ValueError):
+            pass
         tot = 0.0
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(r[idx[k]].replace(",", "")) * scale[units[idx[k]]]
@@ -56,6 +65,8 @@ def traffic(rep, key, out):
     acc = {c: [b[c] for b in full] for c in ("linearize", "backward", "rollout")} if full else {}
     d = json.load(open(out)) if os.path.exists(out) else {}
     d[key] = {c: sum(v) / len(v) for c, v in acc.items()}
+    # duration-weighted FP64 pipe utilisation per kernel class (a utilisation read under the profiler, not a timing)
+    d[key]["fp64_pipe_active_pct"] = {c: v[0] / v[1] for c, v in pipe.items() if v[1] > 0}
     d[key]["source"] = os.path.basename(rep) + " (ncu --set full; per iLQR iteration: sum over the launches of a kernel class, averaged over the captured iterations)"
     json.dump(d, open(out, "w"), indent=1)
     print(d[key])
