@@ -197,6 +197,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, in front of the one JSON line this prints
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from class_files.iLQR_class import iLQR
     from class_files.systems.UA_double_pendulum_sys import MyUADoublePendulum
