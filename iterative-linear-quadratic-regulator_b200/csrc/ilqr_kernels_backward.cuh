@@ -329,21 +329,42 @@ backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, 
 #pragma unroll
             for (int c = 0; c < n; ++c) Vxx[i][c] = qc.Qfs[i][c];
     }
-    int stage = 0;
-    for (int t = N - 1; t >= 0; --t) {
-        cp_async_wait<DEPTH - 1>();
-        __syncwarp();                                                    // other lanes' copies are visible
-        const T *in = ring + (stage * SLOTS + s) * LP;
-        T Am[n][n], Bv[n], x[n], Acol[n];
+#ifndef ILQR_LANES_PREFETCH
+#define ILQR_LANES_PREFETCH 1
+#endif
+    // Software pipeline: the inputs of step t-1 are read from the ring into registers at the top of step t, so their
+    // shared-memory latency (and the cp.async wait) hides behind step t's arithmetic instead of heading the
+    // dependent chain of step t-1; the ring slot of step t is refilled as soon as step t starts.
+    struct StepIn { T Am[n][n], Bv[n], x[n], Acol[n], u; };
+    auto read_in = [&](StepIn &d, int st) {
+        const T *in = ring + (st * SLOTS + s) * LP;
 #pragma unroll
         for (int i = 0; i < n; ++i) {
 #pragma unroll
-            for (int c = 0; c < n; ++c) Am[i][c] = in[i * 4 + c];
-            Bv[i] = in[16 + i];
-            x[i] = in[20 + i];
-            Acol[i] = in[i * 4 + j];
+            for (int c = 0; c < n; ++c) d.Am[i][c] = in[i * 4 + c];
+            d.Bv[i] = in[16 + i];
+            d.x[i] = in[20 + i];
+            d.Acol[i] = in[i * 4 + j];
         }
-        const T u = in[24];
+        d.u = in[24];
+    };
+    int stage = 0;
+    // one scan step on the inputs `cur`; with the prefetch, `nxt` receives the inputs of step t-1 meanwhile
+    auto scan_step = [&](const StepIn &cur, StepIn &nxt, int t) {
+#if ILQR_LANES_PREFETCH
+        __syncwarp();                                                    // every lane holds its copy of this slot
+        if (t - DEPTH >= 0) issue(stage, t - DEPTH);
+        cp_async_commit();
+        stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
+        if (t > 0) {
+            cp_async_wait<DEPTH - 1>();
+            __syncwarp();                                                // other lanes' copies are visible
+            read_in(nxt, stage);
+        }
+#endif
+        const T (&Am)[n][n] = cur.Am;
+        const T (&Bv)[n] = cur.Bv, (&x)[n] = cur.x, (&Acol)[n] = cur.Acol;
+        const T u = cur.u;
         // Y = V_xx A[:,j] ; Q_xx[:,j] = l_xx[:,j] + A' Y ; Q_ux[j] = B' Y          (iLQR_class.py:102-103)
         T Y[n], Qxxc[n], Quxj = T(0), Qxj = T(0), Qu = T(0), Quu = T(0);
 #pragma unroll
@@ -400,10 +421,30 @@ backward_n4m1_lanes_kernel(const __grid_constant__ QuadCost<T, 4, 1> qc, int N, 
             for (int c = 0; c < n; ++c) Vxx[i][c] = exV[s * 20 + i * 4 + c];
             Vx[i] = exV[s * 20 + 16 + i];
         }
+#if !ILQR_LANES_PREFETCH
         if (t - DEPTH >= 0) issue(stage, t - DEPTH);                     // every lane is past its reads of this stage
         cp_async_commit();
         stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
+#endif
+    };
+#if ILQR_LANES_PREFETCH
+    StepIn in_a, in_b;                                                   // ping-pong: no register copies between steps
+    cp_async_wait<DEPTH - 1>();
+    __syncwarp();
+    read_in(in_a, 0);
+    for (int t = N - 1; t >= 0; t -= 2) {
+        scan_step(in_a, in_b, t);
+        if (t - 1 >= 0) scan_step(in_b, in_a, t - 1);
     }
+#else
+    for (int t = N - 1; t >= 0; --t) {
+        cp_async_wait<DEPTH - 1>();
+        __syncwarp();                                                    // other lanes' copies are visible
+        StepIn cur;
+        read_in(cur, stage);
+        scan_step(cur, cur, t);
+    }
+#endif
 }
 
 // K2 for the synthetic LTV system (n = 12, m = 4; BASELINE.json config 4).  One thread per trajectory
