@@ -58,9 +58,19 @@ P_DP_OL = dict(kind="double", dt=0.01, g=9.81, m1=1.0, m2=1.0, l1=1.0, l2=1.0, d
                Q_f=[1000.0, 1000.0, 100.0, 100.0], x_target=[PI, 0.0, 0.0, 0.0])
 
 
+# DENSE, NON-SYMMETRIC weights on the fully actuated double pendulum (m = 2) and the under-actuated one: no shipped script
+# uses them, but the reference accepts any array -- the cost is the written quadratic form and autodiff differentiates it
+# (system_base.py:212-219), i.e. the derivatives see the symmetric part.  Pins that behaviour for the oracle and the kernels.
+_QD = [[2.0, 0.3, -0.1, 0.05], [-0.2, 1.5, 0.1, 0.0], [0.1, -0.3, 0.4, 0.02], [0.0, 0.1, -0.05, 0.3]]
+_QFD = [[300.0, 40.0, -5.0, 2.0], [-20.0, 250.0, 6.0, 1.0], [5.0, -3.0, 40.0, 4.0], [1.0, 2.0, -6.0, 30.0]]
+P_DP_DENSE = dict(P_DP_OL, Q=_QD, R=[[0.2, 0.05], [-0.03, 0.15]], Q_f=_QFD)
+P_UA_DENSE = dict(P_UA_OL, Q=_QD, R=[[0.8]], Q_f=_QFD)
+
+
 def make_system(p, integrator):
+    import numpy as np
     import jax.numpy as jnp
-    diag = lambda v: jnp.diag(jnp.array(v))
+    diag = lambda v: jnp.diag(jnp.array(v)) if np.ndim(v) == 1 else jnp.array(v)     # weights as diagonals or full matrices
     common = dict(dt=p["dt"], x_target=jnp.array(p["x_target"]), Q=diag(p["Q"]), R=diag(p["R"]),
                   Q_f=diag(p["Q_f"]), integrator=integrator, use_jit=True)
     if p["kind"] == "user_cartpole":
@@ -285,6 +295,13 @@ def build_cases():
     cases["solve_double_euler_T5"] = (case_solve, (P_DP_OL, "euler", 5.0, [0.0, 0.0, 0.0, 0.0], 30, 1e-6))
     # run_iLQR_OL_UA_Pendulum.py down-down start at a shorter horizon (shipped: T=8, backward_euler)
     cases["solve_ua_rk4_T2_down"] = (case_solve, (P_UA_OL, "rk4", 2.0, [0.0, 0.0, 0.0, 0.0], 40, 1e-5))
+    # dense non-symmetric weights (P_DP_DENSE, P_UA_DENSE above)
+    cases["derivs_double_dense_rk4"] = (case_derivs, (P_DP_DENSE, "rk4", 120))
+    cases["derivs_ua_dense_euler"] = (case_derivs, (P_UA_DENSE, "euler", 121))
+    cases["passes_double_dense_rk4"] = (case_passes, (P_DP_DENSE, "rk4", 0.6, 220))
+    cases["passes_ua_dense_midpoint"] = (case_passes, (P_UA_DENSE, "midpoint", 0.6, 221))
+    cases["solve_double_dense_rk4_T1"] = (case_solve, (P_DP_DENSE, "rk4", 1.0, x0s[1].tolist(), 15, 1e-5))
+    cases["solve_ua_dense_rk4_T1"] = (case_solve, (P_UA_DENSE, "rk4", 1.0, x0s[2].tolist(), 15, 1e-5))
     # --- MPC ----------------------------------------------------------------------
     cases["mpc_ua_T0p5_ticks6"] = (case_mpc, (P_UA_MPC, "rk4", "backward_euler", 0.5, 6,
                                              [0.1, -0.1, 0.3, -0.2], 50, 1e-5))

@@ -11,8 +11,9 @@ def system_from_golden(g, integrator=None, dtype="float64"):
     from class_files.systems.UA_double_pendulum_sys import MyUADoublePendulum
     kind = str(g["p_kind"])
     integ = integrator or str(g["p_integrator"])
-    common = dict(dt=float(g["p_dt"]), x_target=np.array(g["p_x_target"]), Q=np.diag(g["p_Q"]), R=np.diag(g["p_R"]),
-                  Q_f=np.diag(g["p_Q_f"]), integrator=integ, dtype=dtype)
+    full = lambda v: np.diag(v) if np.ndim(v) == 1 else np.array(v)      # weights stored as diagonals or full matrices
+    common = dict(dt=float(g["p_dt"]), x_target=np.array(g["p_x_target"]), Q=full(g["p_Q"]), R=full(g["p_R"]),
+                  Q_f=full(g["p_Q_f"]), integrator=integ, dtype=dtype)
     if kind == "pendulum":
         return MyPendulum(g=float(g["p_g"]), l=float(g["p_l"]), d=float(g["p_d"]), **common)
     phys = {k: float(g["p_" + k]) for k in PHYS_DP}
