@@ -56,7 +56,7 @@ typedef struct ilqr_problem_t {
     int32_t model;        /* ILQR_PENDULUM ... */
     int32_t integrator;   /* ILQR_EULER ... */
     int32_t dtype;        /* ILQR_F64 / ILQR_F32 */
-    int32_t n, m;         /* must match the model (2,1), (4,2), (4,1); free for ILQR_LTV */
+    int32_t n, m;         /* must match the model: (2,1), (4,2), (4,1), (12,4) for ILQR_LTV; n <= ILQR_NMAX, m <= ILQR_MMAX */
     int32_t N;            /* horizon: len(arange(0, T+dt, dt)) - 1 (iLQR_class.py:46-47) */
     int32_t B;            /* batch of independent trajectories on this device */
     int32_t n_alpha;      /* line-search tries, 10 in the reference (iLQR_class.py:281) */
@@ -134,7 +134,10 @@ int ilqr_forward_linesearch(ilqr_handle_t h, const void *phi, const void *x0, co
  * rollout uses the incoming X,K,k exactly like :257-259, which is what MPC warm starts rely on).
  * Outputs: cost[B], iters[B] (int32, backward passes executed), status[B] (int32, ILQR_ST_*).
  * total_iters (host pointer, may be NULL) receives sum_b iters[b] after the stream is synchronized
- * by the call -- pass NULL to keep the call fully asynchronous. */
+ * by the call.  With NULL the call does not wait for the solve to finish: the device never waits for the host, but
+ * the HOST may block inside the call until all but the last block of 8 iterations has run (it polls the
+ * device-side active counter one block behind to stop enqueuing once every trajectory has finished), so the call
+ * cannot be captured into a CUDA graph. */
 int ilqr_solve(ilqr_handle_t h, const void *phi, const void *x0, void *X, void *U, void *K, void *k,
                void *cost, int32_t *iters, int32_t *status, void *workspace, size_t workspace_bytes,
                void *stream, int64_t *total_iters);
@@ -147,6 +150,9 @@ int ilqr_solve(ilqr_handle_t h, const void *phi, const void *x0, void *X, void *
  * is the default for small batches where the rollout is latency bound; large batches default to waves of
  * 2,2,2,rest.  The accepted step size of every trajectory is the same under every schedule. */
 int ilqr_set_linesearch_waves(ilqr_handle_t h, int n_waves, const int32_t *sizes);
+/* The schedule in force: returns the number of lazy waves (0 = eager) and, when sizes != NULL, writes the tries per
+ * wave into sizes[ILQR_MAX_WAVES]. */
+int ilqr_get_linesearch_waves(ilqr_handle_t h, int32_t *sizes);
 
 /* Optional device buffer mu[B] (element type of the handle) for the regularisation state of ilqr_solve:
  * initialised to reg_init at the start of every solve and left holding the final values.  NULL (default)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "ilqr_solve": (C.c_int, [_VP] * 8 + [_VP, _VP, _VP, C.c_size_t, _VP, _I64P]),
     "ilqr_set_trace": (C.c_int, [_VP, _VP, _VP]),
     "ilqr_set_linesearch_waves": (C.c_int, [_VP, C.c_int, _I32P]),
+    "ilqr_get_linesearch_waves": (C.c_int, [_VP, _I32P]),
     "ilqr_set_mu_buffer": (C.c_int, [_VP, _VP]),
     "ilqr_set_profiling": (C.c_int, [_VP, C.c_int]),
     "ilqr_get_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_double), _I64P]),

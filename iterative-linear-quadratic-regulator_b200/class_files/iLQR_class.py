@@ -252,18 +252,32 @@ class iLQR:
 
     def optimize_trajectory(self):
         """Runs the full iLQR loop (iLQR_class.py:250-313) for every trajectory of the batch."""
-        want_trace = self.verbose and self.B <= 64
-        if want_trace and self._trace is None:
-            ta = torch.empty((max(self.maxiter, 1), self.B), dtype=torch.int32, device="cuda")
-            tc = torch.empty((self.maxiter + 1, self.B), dtype=self._tdt, device="cuda")
-            self._trace = (ta, tc)
-            h = self._handle
-            h.check(h.lib.ilqr_set_trace(h.h, D.ptr(ta), D.ptr(tc)))
+        if self.verbose and self.B <= 64:
+            self.enable_trace()
         self.solve_device(sync=True)
         if self.verbose:
             self._report()
         cost = self._finish(self._cost) if self.batched else self._scalar(self._cost)
         return self.X, self.U, cost
+
+    def enable_trace(self):
+        """Record the control flow of every following solve on the device (ilqr_set_trace): per iteration the
+        accepted try index and the cost.  Always on for verbose solves of up to 64 trajectories."""
+        if self._trace is None:
+            ta = torch.full((max(self.maxiter, 1), self.B), -2, dtype=torch.int32, device="cuda")
+            tc = torch.full((self.maxiter + 1, self.B), float("nan"), dtype=self._tdt, device="cuda")
+            self._trace = (ta, tc)
+            h = self._handle
+            h.check(h.lib.ilqr_set_trace(h.h, D.ptr(ta), D.ptr(tc)))
+
+    def trace_arrays(self):
+        """(alpha_idx (B, maxiter), cost_trace (B, maxiter + 1)) of the last solve as numpy arrays: accepted try
+        index per iteration (-1 = line search failed; entries at or beyond iterations[b] are stale) and the cost
+        after the initial rollout and after every iteration.  Needs enable_trace()."""
+        if self._trace is None:
+            raise RuntimeError("no trace recorded (call enable_trace() before solving)")
+        ta, tc = self._trace
+        return ta.t().cpu().numpy(), tc.t().cpu().numpy()
 
     def trace(self, b=0):
         """(accepted alpha per iteration, cost after each iteration incl. the initial rollout) of

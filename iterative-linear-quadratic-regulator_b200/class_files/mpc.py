@@ -37,6 +37,10 @@ def run_mpc(ilqr_solver, plant_system, x_0, N_sim, U_init=None, record_plans=Fal
         raise ValueError("plant and optimizer systems must have the same dimensions")
     torch_out = D.is_torch(x_0) and x_0.is_cuda
     tdt = sol._tdt
+    if getattr(plant_system, "TIME_VARYING", False) or getattr(sol.system, "TIME_VARYING", False):
+        # the solver's horizon always starts at time index 0 while the plant's clock runs on: for a time-varying
+        # model the two would silently disagree (the reference has no such system; config 4 is open loop)
+        raise NotImplementedError("run_mpc does not support time-varying systems (MyLTVSystem)")
     plant = D.Handle(plant_system.make_problem(N=1, B=B), lib=plant_system._library())
     lib = plant.lib
     dev = dict(dtype=tdt, device="cuda")

@@ -13,6 +13,8 @@ from .system_base import System
 
 
 class MyLTVSystem(System):
+    TIME_VARYING = True       # f depends on the time index and a per-trajectory phase (System._f / ._jac take t, phi)
+
     def __init__(self, dt, x_target, Q, R, Q_f, Ac, E, Bc, amp: float = 0.1, use_jit: bool = True,
                  integrator: str = "euler", dtype: str = "float64"):
         self.Ac = np.asarray(Ac, dtype=np.float64)

@@ -6,7 +6,7 @@ The dynamics, their analytic Jacobians and the cost run inside libilqr_b200.so (
 csrc/ilqr_systems.cuh).  The reference module's `__main__` integrator demo (:101-313) is
 plotting/printing and is not reproduced.
 """
-from class_files.systems.system_base import System
+from .system_base import System     # (the reference spells this import absolutely, pendulum_sys.py:10; same module either way)
 
 
 class MyPendulum(System):

@@ -39,6 +39,10 @@ def _square(M, k, name):
 class System(ABC):
     def __init__(self, n_x: int, n_u: int, dt: float, use_jit: bool = True, integrator: str = "rk4",
                  dtype: str = "float64"):
+        if not (1 <= int(n_x) <= _cabi.NMAX and 1 <= int(n_u) <= _cabi.MMAX):
+            # the kernels hold a trajectory's value function in registers / shared memory: fixed upper bounds
+            raise ValueError(f"n_x must be in 1..{_cabi.NMAX} and n_u in 1..{_cabi.MMAX} (ILQR_NMAX / ILQR_MMAX of "
+                             f"include/ilqr_b200.h), but got n_x={n_x}, n_u={n_u}")
         self.n_x = n_x
         self.n_u = n_u
         self.dt = dt
@@ -54,8 +58,8 @@ class System(ABC):
         self._point_handles = {}
         # public callables, same names as system_base.py:223-251
         self.f_fcn = self._f
-        self.f_x_fcn = lambda x, u: self._jac(x, u)[0]
-        self.f_u_fcn = lambda x, u: self._jac(x, u)[1]
+        self.f_x_fcn = lambda x, u, **kw: self._jac(x, u, **kw)[0]      # kw: phi, N (MyLTVSystem only)
+        self.f_u_fcn = lambda x, u, **kw: self._jac(x, u, **kw)[1]
         self.l_fcn = lambda x, u: self._cost(x, u, "l")
         self.l_x_fcn = lambda x, u: self._cost(x, u, "lx")
         self.l_u_fcn = lambda x, u: self._cost(x, u, "lu")
@@ -166,15 +170,17 @@ class System(ABC):
         h.check(h.lib.ilqr_step(h.h, int(t), D.ptr(ph), D.ptr(xd), D.ptr(ud), D.ptr(xn), D.stream_ptr()))
         return self._out(xn, single, tout)
 
-    def _jac(self, x, u):
+    def _jac(self, x, u, phi=None, N=1):
+        """(f_x, f_u) at (x,u), time index 0; `phi` and the horizon `N` only matter for MyLTVSystem (as in _f)"""
         xd, ud, P, single, tout = self._points(x, u)
-        h = self._handle(P)
+        h = self._handle(P, N)
         n, m = self.n_x, self.n_u
         X = torch.stack([xd, xd])            # [N+1=2][n][P]; only t=0 is linearized
         U = ud.reshape(1, m, P)
         A = torch.empty((1, n, n, P), dtype=xd.dtype, device="cuda")
         Bd = torch.empty((1, n, m, P), dtype=xd.dtype, device="cuda")
-        h.check(h.lib.ilqr_linearize(h.h, None, D.ptr(X), D.ptr(U), D.ptr(A), D.ptr(Bd), D.stream_ptr()))
+        ph = self._phi(phi, P, xd.dtype)
+        h.check(h.lib.ilqr_linearize(h.h, D.ptr(ph), D.ptr(X), D.ptr(U), D.ptr(A), D.ptr(Bd), D.stream_ptr()))
         return self._out(A[0], single, tout), self._out(Bd[0], single, tout)
 
     def _cost(self, x, u, which):

@@ -121,6 +121,12 @@ struct Handle {
     int env_lanes;            // ILQR_BACKWARD_LANES: -1 [auto: lanes kernel for B <= 32768], 0, 1
     int env_rollout_bs;       // ILQR_ROLLOUT_BS: 0 [auto] or a block size
     int env_check_every;      // ILQR_CHECK_EVERY: iterations enqueued between host polls of the active count [8]
+    long env_sparse_thresh;   // ILQR_SPARSE_THRESH / ILQR_SPARSE_ALL: -1 [auto] or the thresholds of SparseArgs
+    long env_sparse_all;
+    // opt-in to > 48 KB of dynamic shared memory is a per-device, per-kernel attribute: tracked per handle (a handle
+    // lives on one device), never in function statics
+    size_t smem_backward;     // largest size configured for this handle's backward_kernel instantiation
+    int smem_ltv;             // backward_ltv_kernel configured
     void *mu_user;            // optional caller buffer for the per-trajectory regularisation (ilqr_set_mu_buffer)
     int ab_blocked;           // ilqr_solve stores the linearization blocked by groups of 32 trajectories (ab_off)
     int sparse;               // lazy schedule: late iterations index the batch through the active list (SparseArgs)
@@ -285,12 +291,11 @@ static int launch_backward_depth(Handle *h, const Cost &qc, const void *X, const
 {
     constexpr int L = n * n + n * m + n + m;
     const size_t smem = (size_t)DEPTH * L * bs * sizeof(T);
-    static size_t configured = 0;           // per instantiation: opt in to > 48 KB dynamic shared memory once
-    if (smem > configured) {
+    if (smem > h->smem_backward) {          // a handle uses ONE instantiation (fixed model, dtype, batch)
         cudaError_t e = cudaFuncSetAttribute(backward_kernel<Cost, T, n, m, DEPTH, bs>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) { h->last_cuda = (int)e; return ILQR_E_CUDA; }
-        configured = smem;
+        h->smem_backward = smem;
     }
     backward_kernel<Cost, T, n, m, DEPTH, bs><<<grid_for(h->p.B, bs), bs, smem, st>>>(
         qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active, gate,
@@ -353,12 +358,11 @@ static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const 
     auto go = [&](auto tz) -> int {
         using T = decltype(tz);
         const size_t smem = sizeof(T) * (size_t)(504 * TPB + 48 + 144 + 16 + 288);
-        static bool configured = false;
-        if (!configured) {
+        if (!h->smem_ltv) {
             cudaError_t e = cudaFuncSetAttribute(backward_ltv_kernel<T, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)smem);
             if (e != cudaSuccess) { h->last_cuda = (int)e; return ILQR_E_CUDA; }
-            configured = true;
+            h->smem_ltv = 1;
         }
         backward_ltv_kernel<T, TPB><<<grid_for(h->p.B, TPB), TPB * 16, smem, st>>>(
             make_ltv<T>(h->p), make_cost<T, 12, 4>(h->p), h->p.N, h->p.B, (const T *)phi, (const T *)X, (const T *)U,
@@ -625,6 +629,8 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
         h->env_rollout_bs = (e = getenv("ILQR_ROLLOUT_BS")) && atoi(e) >= 32 ? atoi(e) / 32 * 32 : 0;
         h->env_check_every = (e = getenv("ILQR_CHECK_EVERY")) && atoi(e) > 0 ? atoi(e) : 8;
     }
+    h->env_sparse_thresh = (e = getenv("ILQR_SPARSE_THRESH")) ? atol(e) : -1;
+    h->env_sparse_all = (e = getenv("ILQR_SPARSE_ALL")) ? atol(e) : -1;
     h->sparse = (e = getenv("ILQR_SPARSE")) ? atoi(e) != 0 : 1;
     h->ab_blocked = (e = getenv("ILQR_AB_BLOCKED")) ? atoi(e) != 0 : 1;
     h->n_first = first_wave_size(p->B, cnt);
@@ -633,7 +639,12 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
     if (cudaMallocHost((void **)&h->h_flag, 2 * sizeof(unsigned int)) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming) != cudaSuccess) {
-        h->last_cuda = (int)cudaGetLastError();
+        cudaGetLastError();
+        if (h->ev[0]) cudaEventDestroy(h->ev[0]);
+        if (h->ev[1]) cudaEventDestroy(h->ev[1]);
+        if (h->h_flag) cudaFreeHost(h->h_flag);
+        delete h->prof_ev;
+        delete h->prof_kind;
         delete h;
         return ILQR_E_CUDA;
     }
@@ -795,8 +806,8 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
         const long w0 = h->wave_lo[1];
         long t = p.B / 4, ta = 2L * 148 * 4 * 32 / h->n_alpha_eff;
         if (ta > (long)w0 * p.B / h->n_alpha_eff) ta = (long)w0 * p.B / h->n_alpha_eff;
-        if (const char *e = getenv("ILQR_SPARSE_THRESH")) t = atol(e);
-        if (const char *e = getenv("ILQR_SPARSE_ALL")) ta = atol(e);
+        if (h->env_sparse_thresh >= 0) t = h->env_sparse_thresh;
+        if (h->env_sparse_all >= 0) ta = h->env_sparse_all;
         if (ta > t) ta = t;
         t &= ~31L;
         ta &= ~31L;
@@ -954,6 +965,16 @@ int ilqr_set_linesearch_waves(ilqr_handle_t hh, int n_waves, const int32_t *size
     if (!h || n_waves < 0 || n_waves > ILQR_MAX_WAVES || (n_waves > 0 && !sizes)) return ILQR_E_INVALID;
     set_waves(h, n_waves, sizes);
     return ILQR_OK;
+}
+
+int ilqr_get_linesearch_waves(ilqr_handle_t hh, int32_t *sizes)
+{
+    Handle *h = (Handle *)hh;
+    if (!h) return ILQR_E_INVALID;
+    if (!h->lazy) return 0;
+    if (sizes)
+        for (int v = 0; v < h->n_waves; ++v) sizes[v] = h->wave_lo[v + 1] - h->wave_lo[v];
+    return h->n_waves;
 }
 
 int ilqr_set_mu_buffer(ilqr_handle_t hh, void *mu)

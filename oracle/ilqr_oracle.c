@@ -584,6 +584,7 @@ typedef struct {
     const orc_problem *p; int B; const double *phi, *x0, *U_init;
     double *X, *U, *K, *U_ff, *cost; int *iters, *status;
     atomic_int next;
+    int *tr_alpha; double *tr_cost, *cost0;      /* optional per-member traces [B][maxiter] / [B] */
 } batch_job;
 
 static void *batch_worker(void *arg)
@@ -599,9 +600,11 @@ static void *batch_worker(void *arg)
         memset(j->K + b * sk, 0, sizeof(double) * sk);
         memset(j->U_ff + b * su, 0, sizeof(double) * su);
         memcpy(j->U + b * su, j->U_init + b * su, sizeof(double) * su);
+        const size_t mi = (size_t)(p->maxiter > 0 ? p->maxiter : 1);
         j->cost[b] = orc_optimize(p, j->phi ? j->phi[b] : 0.0, j->x0 + (size_t)b * n, j->X + b * sx,
                                   j->U + b * su, j->K + b * sk, j->U_ff + b * su,
-                                  j->iters + b, j->status + b, NULL, NULL, NULL);
+                                  j->iters + b, j->status + b, j->cost0 ? j->cost0 + b : NULL,
+                                  j->tr_alpha ? j->tr_alpha + b * mi : NULL, j->tr_cost ? j->tr_cost + b * mi : NULL);
     }
     return NULL;
 }
@@ -610,7 +613,17 @@ void orc_optimize_batch(const orc_problem *p, int B, const double *phi, const do
                         const double *U_init, double *X, double *U, double *K, double *U_ff,
                         double *cost, int *iters, int *status, int nthreads)
 {
-    batch_job j = { p, B, phi, x0, U_init, X, U, K, U_ff, cost, iters, status, 0 };
+    orc_optimize_batch_trace(p, B, phi, x0, U_init, X, U, K, U_ff, cost, iters, status, nthreads, NULL, NULL, NULL);
+}
+
+/* the same with the per-member control flow recorded: accepted try index and cost after every iteration
+ * ([B][max(maxiter,1)], untouched beyond iters[b]) and the cost of the alpha = 0 rollout ([B]) */
+void orc_optimize_batch_trace(const orc_problem *p, int B, const double *phi, const double *x0,
+                              const double *U_init, double *X, double *U, double *K, double *U_ff,
+                              double *cost, int *iters, int *status, int nthreads,
+                              int *trace_alpha_idx, double *trace_cost, double *cost0)
+{
+    batch_job j = { p, B, phi, x0, U_init, X, U, K, U_ff, cost, iters, status, 0, trace_alpha_idx, trace_cost, cost0 };
     if (nthreads <= 0) nthreads = orc_max_threads();
     if (nthreads > B) nthreads = B;
     if (nthreads <= 1) { batch_worker(&j); return; }

@@ -88,6 +88,13 @@ void orc_optimize_batch(const orc_problem *p, int B, const double *phi, const do
                         const double *U_init, double *X, double *U, double *K, double *U_ff,
                         double *cost, int *iters, int *status, int nthreads);
 
+/* The same with the per-member control flow recorded (accepted try index and cost after every iteration,
+ * [B][max(maxiter,1)]; cost of the alpha = 0 rollout, [B]); any of the three may be NULL. */
+void orc_optimize_batch_trace(const orc_problem *p, int B, const double *phi, const double *x0,
+                              const double *U_init, double *X, double *U, double *K, double *U_ff,
+                              double *cost, int *iters, int *status, int nthreads,
+                              int *trace_alpha_idx, double *trace_cost, double *cost0);
+
 /* Receding-horizon loop, run_iLQR_UA_MPC.py:146-174: one solver object re-used across ticks. */
 void orc_mpc(const orc_problem *p_opt, const orc_problem *p_plant, double phi, const double *x0,
              int ticks, double *X_sim /* (n,ticks+1) */, double *U_sim /* (m,ticks) */,

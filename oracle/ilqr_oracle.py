@@ -90,6 +90,7 @@ def lib():
         L.orc_optimize_ex.restype = C.c_double
         L.orc_backward_pass_mu.argtypes = [P, C.c_double, C.c_double, D, D, D, D]
         L.orc_optimize_batch.argtypes = [P, C.c_int, D, D, D, D, D, D, D, D, I, I, C.c_int]
+        L.orc_optimize_batch_trace.argtypes = [P, C.c_int, D, D, D, D, D, D, D, D, I, I, C.c_int, I, D, D]
         L.orc_mpc.argtypes = [P, P, C.c_double, D, C.c_int, D, D, D, I, D, D, D, D, D, D]
         L.orc_max_threads.restype = C.c_int
         _libs[v] = L
@@ -253,8 +254,10 @@ def optimize(p, x0, U_init, state=None, phi=0.0):
                 status=STATUS[status.value], alpha_idx=tr_a[: iters.value], cost_trace=tr_c[: iters.value])
 
 
-def optimize_batch(p, x0, U_init, phi=None, nthreads=0):
-    """x0 (B,n); U_init (B,m,N).  Returns dict of batch-major arrays."""
+def optimize_batch(p, x0, U_init, phi=None, nthreads=0, trace=False):
+    """x0 (B,n); U_init (B,m,N).  Returns dict of batch-major arrays.  trace=True adds the per-member control
+    flow: alpha_idx (B,maxiter) accepted try index per iteration (-1 failed, -2 not run), cost_trace (B,maxiter)
+    cost after each iteration (NaN where not run), cost0 (B,) cost of the alpha = 0 rollout."""
     n, m, N = p.n, p.m, p.N
     x0 = _arr(x0)
     B = x0.shape[0]
@@ -264,6 +267,15 @@ def optimize_batch(p, x0, U_init, phi=None, nthreads=0):
     cost = np.empty(B)
     iters, status = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
     phi_p = _d(_arr(phi)) if phi is not None else None
+    if trace:
+        mi = max(p.maxiter, 1)
+        tr_a = np.full((B, mi), -2, dtype=np.int32)
+        tr_c = np.full((B, mi), np.nan)
+        c0 = np.empty(B)
+        lib().orc_optimize_batch_trace(C.byref(p), B, phi_p, _d(x0), _d(U_init), _d(X), _d(U), _d(K), _d(U_ff), _d(cost),
+                                       _i(iters), _i(status), int(nthreads), _i(tr_a), _d(tr_c), _d(c0))
+        return dict(X=X, U=U, K=K, U_ff=U_ff, cost=cost, iters=iters, status=status, alpha_idx=tr_a, cost_trace=tr_c,
+                    cost0=c0)
     lib().orc_optimize_batch(C.byref(p), B, phi_p, _d(x0), _d(U_init), _d(X), _d(U), _d(K), _d(U_ff), _d(cost),
                              _i(iters), _i(status), int(nthreads))
     return dict(X=X, U=U, K=K, U_ff=U_ff, cost=cost, iters=iters, status=status)

@@ -153,3 +153,151 @@ def forward_sensitivity(O, p, x0, alpha, X, U, U_ff, K, n_draws=3, eps=1e-14, se
         sU = max(sU, float(np.max(np.abs(U2 - Un)) / max(float(np.max(np.abs(Un))), 1e-3)))
         sc = max(sc, abs(c2 - c) / abs(c))
     return sX, sU, sc
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Per-member parity of a whole batch (no quantiles, no unbounded tail): every member is either at
+# max(1e-9, SENS_FACTOR x its own rounding sensitivity) on X, U, K, U_ff and cost with the oracle's control flow, or
+# its control flow differs from the oracle's at an iteration where the oracle's own flow flips under rounding noise.
+# ----------------------------------------------------------------------------------------------------------
+KEYS = (("X", 0.0), ("U", 1e-3), ("K", 0.0), ("U_ff", 1e-3))
+
+
+def member_rel_err(a, b, floor=0.0):
+    """per member: max |a-b| / max(max |b|, floor); arrays are batch-major"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    ax = tuple(range(1, a.ndim))
+    num = np.max(np.abs(a - b), axis=ax) if ax else np.abs(a - b)
+    den = np.max(np.abs(b), axis=ax) if ax else np.abs(b)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e = num / np.maximum(np.maximum(den, floor), 1e-300)
+    return np.where(np.isnan(num) & np.isnan(den), 0.0, e)       # both NaN (a diverged member): same outcome
+
+
+def flow_prefix(idx_a, it_a, idx_b, it_b):
+    """per member: number of leading iterations on which two runs made the same line-search decision; equals
+    max(it_a, it_b) when the flows are identical"""
+    B, M = idx_a.shape
+    col = np.arange(M)[None, :]
+    a = np.where(col < it_a[:, None], idx_a, -2)
+    b = np.where(col < it_b[:, None], idx_b, -2)
+    diff = a != b
+    first = np.where(diff.any(axis=1), diff.argmax(axis=1), np.maximum(it_a, it_b))
+    return first.astype(np.int64)
+
+
+def batch_sensitivity(O, p, x0, U0, n_draws=4, eps=1e-14, seed=7, phi=None, base=None):
+    """rounding_sensitivity() for every member of a batch: the oracle on `n_draws` copies of x0 perturbed by eps
+    (relative) and once from its FMA-contracted build.  Returns the base run and, per member, the largest relative
+    drift of X, U, K, U_ff, final cost and of the cost after every iteration, and `prefix`: the number of leading
+    iterations whose line-search decision no draw changed."""
+    rng = np.random.default_rng(seed)
+    x0 = np.asarray(x0, dtype=np.float64)
+    B = x0.shape[0]
+    if base is None:
+        base = O.optimize_batch(p, x0, U0, phi=phi, trace=True)
+    M = base["alpha_idx"].shape[1]
+    s = {k: np.zeros(B) for k, _ in KEYS}
+    s["cost"] = np.zeros(B)
+    s["cost_it"] = np.zeros((B, M))
+    s["prefix"] = base["iters"].astype(np.int64).copy()
+    for draw in range(n_draws + 1):
+        if draw == n_draws:
+            with O.rounding_variant():
+                r = O.optimize_batch(p, x0, U0, phi=phi, trace=True)
+        else:
+            r = O.optimize_batch(p, _perturb(rng, x0, eps), U0, phi=phi, trace=True)
+        pre = flow_prefix(r["alpha_idx"], r["iters"], base["alpha_idx"], base["iters"])
+        pre = np.where((r["iters"] == base["iters"]) & (r["status"] == base["status"]) & (pre >= base["iters"]),
+                       base["iters"], np.minimum(pre, base["iters"]))
+        s["prefix"] = np.minimum(s["prefix"], pre)
+        for k, floor in KEYS:
+            s[k] = np.maximum(s[k], member_rel_err(r[k], base[k], floor))
+        s["cost"] = np.maximum(s["cost"], member_rel_err(r["cost"], base["cost"]))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            d = np.abs(r["cost_trace"] - base["cost_trace"]) / np.abs(base["cost_trace"])
+        s["cost_it"] = np.maximum(s["cost_it"], np.nan_to_num(d, nan=0.0))
+    s["cost_it"] = np.maximum.accumulate(s["cost_it"], axis=1)
+    return base, s
+
+
+def member_parity(O, p, x0, U0, got, n_draws=4, deep_draws=24, tol=1e-9, phi=None, base=None):
+    """Compare a GPU batch solve `got` (dict X, U, K, U_ff, cost, iters, status, alpha_idx (B,maxiter), cost_trace
+    (B,maxiter) = cost after each iteration) with the oracle member by member.  Returns (report, failures):
+    `failures` lists every member that is neither within max(tol, SENS_FACTOR x its own sensitivity) on all of X, U, K,
+    U_ff, cost with the oracle's control flow, nor explained by a control-flow flip the oracle itself shows under
+    1e-14 input noise / FMA contraction at or before the same iteration (members whose flip is not reproduced by
+    the first `n_draws` draws get `deep_draws` more)."""
+    x0 = np.asarray(x0, dtype=np.float64)
+    B = x0.shape[0]
+    base, s = batch_sensitivity(O, p, x0, U0, n_draws=n_draws, phi=phi, base=base)
+    M = base["alpha_idx"].shape[1]
+    it_g, it_o = np.asarray(got["iters"]).astype(np.int64), base["iters"].astype(np.int64)
+    pre = flow_prefix(np.asarray(got["alpha_idx"])[:, :M], it_g, base["alpha_idx"], it_o)
+    same = (it_g == it_o) & (np.asarray(got["status"]) == base["status"]) & (pre >= it_o)
+    err = {k: member_rel_err(got[k], base[k], floor) for k, floor in KEYS}
+    err["cost"] = member_rel_err(got["cost"], base["cost"])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e_it = np.nan_to_num(np.abs(np.asarray(got["cost_trace"])[:, :M] - base["cost_trace"]) / np.abs(base["cost_trace"]),
+                             nan=0.0)
+    # members whose flow differs: the oracle must flip at or before the same iteration under rounding noise
+    flipped = np.flatnonzero(~same)
+    unexplained = [int(b) for b in flipped if s["prefix"][b] > pre[b]]
+    if unexplained and deep_draws > 0:
+        sub = np.array(unexplained)
+        U0s = np.broadcast_to(U0, (B, p.m, p.N))[sub]
+        _, s2 = batch_sensitivity(O, p, x0[sub], U0s, n_draws=deep_draws, seed=101,
+                                  phi=None if phi is None else np.asarray(phi)[sub])
+        for j, b in enumerate(sub):
+            s["prefix"][b] = min(s["prefix"][b], s2["prefix"][j])
+            s["cost_it"][b] = np.maximum(s["cost_it"][b], s2["cost_it"][j])
+        unexplained = [int(b) for b in flipped if s["prefix"][b] > pre[b]]
+    failures = [dict(member=b, kind="unexplained control-flow flip", iteration=int(pre[b]),
+                     oracle_stable_prefix=int(s["prefix"][b])) for b in unexplained]
+    # before a flip (and for members without one: everywhere) the per-iteration costs must agree
+    col = np.arange(M)[None, :]
+    upto = np.where(same, it_o, np.minimum(pre, it_o))
+    bound_it = np.maximum(tol, SENS_FACTOR * s["cost_it"])
+    bad_it = (e_it > bound_it) & (col < upto[:, None])
+    for b in np.flatnonzero(bad_it.any(axis=1)):
+        i = int(bad_it[b].argmax())
+        failures.append(dict(member=int(b), kind="cost before any flip", iteration=i, err=float(e_it[b, i]),
+                             sens=float(s["cost_it"][b, i])))
+    worst = {}
+    for k in ("X", "U", "K", "U_ff", "cost"):
+        bound = np.maximum(tol, SENS_FACTOR * s[k])
+        bad = same & (err[k] > bound)
+        for b in np.flatnonzero(bad):
+            failures.append(dict(member=int(b), kind=k, err=float(err[k][b]), sens=float(s[k][b])))
+        es = np.where(same, err[k], 0.0)
+        w = int(es.argmax())
+        worst[k] = dict(member=w, err=float(es[w]), sens=float(s[k][w]), frac_at_tol=float((es[same] <= tol).mean()) if same.any() else None,
+                        max_over_bound=float(np.max(np.where(same, err[k] / bound, 0.0))))
+    report = dict(members=int(B), same_flow=int(same.sum()), flipped=int(len(flipped)),
+                  flips_explained_by_oracle_noise=int(len(flipped) - len(unexplained)), unexplained=int(len(unexplained)),
+                  n_draws=n_draws, deep_draws=deep_draws, tol=tol, sens_factor=SENS_FACTOR, worst=worst,
+                  flip_iteration_hist=np.bincount(pre[~same], minlength=M + 1).tolist() if len(flipped) else [])
+    return report, failures
+
+
+def gpu_result(sol, X, U, cost):
+    """dict for member_parity() from a batched iLQR solver with enable_trace() on"""
+    idx, tc = sol.trace_arrays()
+    return dict(X=np.asarray(X), U=np.asarray(U), K=np.asarray(sol.K), U_ff=np.asarray(sol.U_ff), cost=np.asarray(cost),
+                iters=np.asarray(sol.iterations), status=np.asarray(sol.status), alpha_idx=idx, cost_trace=tc[:, 1:])
+
+
+def write_report(name, report):
+    """parity distributions go to gpurun_out/ on the GPU box (merged back by gpurun) and are committed under profiles/"""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, "parity_r02.json")
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        cur[name] = report
+        json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
