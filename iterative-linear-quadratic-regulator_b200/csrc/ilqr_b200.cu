@@ -17,6 +17,7 @@
 //   ilqr_kernels_common.cuh     structures shared by the kernels (control block, speculation / regularisation args)
 //   ilqr_kernels_linearize.cuh  step_kernel, K1, materialised cost expansion, MPC shift
 //   ilqr_kernels_backward.cuh   K2 in its three forms
+//   ilqr_kernels_fused.cuh      K1 + K2 as one warp-specialised kernel (producers linearize, consumer scans)
 //   ilqr_kernels_rollout.cuh    K3 and K4 (eager and lazy line-search schedules)
 //   ilqr_b200.cu (this file)    handle, workspace layout, launch configuration, ilqr_solve, the C ABI
 #include "ilqr_b200.h"
@@ -40,6 +41,7 @@
 #include "ilqr_kernels_common.cuh"
 #include "ilqr_kernels_linearize.cuh"
 #include "ilqr_kernels_backward.cuh"
+#include "ilqr_kernels_fused.cuh"
 #include "ilqr_kernels_rollout.cuh"
 
 namespace ilqr {
@@ -120,6 +122,9 @@ struct Handle {
     // tuning overrides read once from the environment in ilqr_create (exploration; defaults in brackets):
     int env_lanes;            // ILQR_BACKWARD_LANES: -1 [auto: lanes kernel for B <= 32768], 0, 1
     int env_rollout_bs;       // ILQR_ROLLOUT_BS: 0 [auto] or a block size
+    int env_fused;            // ILQR_FUSED: -1 [auto: fused K1+K2 inside ilqr_solve where it is the faster form], 0 never,
+                              // 1 wherever the model allows (also ilqr_backward_pass)
+    int env_fused_np;         // ILQR_FUSED_NP: producer warps per consumer warp, 2 [default] or 3
     int env_check_every;      // ILQR_CHECK_EVERY: iterations enqueued between host polls of the active count [8]
     long env_sparse_thresh;   // ILQR_SPARSE_THRESH / ILQR_SPARSE_ALL: -1 [auto] or the thresholds of SparseArgs
     long env_sparse_all;
@@ -212,6 +217,10 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
 template <typename T, class Sys, class F> static int dispatch_integ(const Handle *h, const Sys &sys, F &&f)
 {
     auto qc = make_cost<T, Sys::N, Sys::M>(h->p);
+#ifdef ILQR_FAST_BUILD      // kernel experiments (scripts/): UA double pendulum, rk4, FP64 only -- compiles in seconds
+    if (h->p.integrator == ILQR_RK4) return f(T(0), sys, qc, std::integral_constant<int, RK4>{});
+    return ILQR_E_INVALID;
+#else
     switch (h->p.integrator) {
     case ILQR_EULER: return f(T(0), sys, qc, std::integral_constant<int, EULER>{});
     case ILQR_MIDPOINT: return f(T(0), sys, qc, std::integral_constant<int, MIDPOINT>{});
@@ -219,11 +228,16 @@ template <typename T, class Sys, class F> static int dispatch_integ(const Handle
     case ILQR_BACKWARD_EULER: return f(T(0), sys, qc, std::integral_constant<int, BACKWARD_EULER>{});
     }
     return ILQR_E_INVALID;
+#endif
 }
 
 #ifndef ILQR_USER_SYS
 template <typename T, class F> static int dispatch_model(const Handle *h, F &&f)
 {
+#ifdef ILQR_FAST_BUILD
+    if (h->p.model == ILQR_UA_DOUBLE_PENDULUM) return dispatch_integ<T>(h, make_double<T, 1>(h->p), f);
+    return ILQR_E_INVALID;
+#else
     switch (h->p.model) {
     case ILQR_PENDULUM: return dispatch_integ<T>(h, make_pendulum<T>(h->p), f);
     case ILQR_DOUBLE_PENDULUM: return dispatch_integ<T>(h, make_double<T, 2>(h->p), f);
@@ -235,6 +249,7 @@ template <typename T, class F> static int dispatch_model(const Handle *h, F &&f)
     }
     }
     return ILQR_E_INVALID;
+#endif
 }
 #endif
 
@@ -255,7 +270,11 @@ template <class F> static int dispatch(const Handle *h, F &&f)
 template <class F> static int dispatch(const Handle *h, F &&f)
 {
     if (h->p.dtype == ILQR_F64) return dispatch_model<double>(h, f);
+#ifdef ILQR_FAST_BUILD
+    return ILQR_E_INVALID;
+#else
     return dispatch_model<float>(h, f);
+#endif
 }
 #endif
 
@@ -264,7 +283,7 @@ template <class F> static int dispatch(const Handle *h, F &&f)
 static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U, void *A, void *Bd, const void *Xc, const void *Uc,
                                    const int *winner, const int *wslot, const int *active, int do_lin, const unsigned int *g0,
                                    const unsigned int *g1, cudaStream_t st, const int *iters = nullptr, int it = 0,
-                                   const SparseArgs *sparse = nullptr, int ab_blocked = 0)
+                                   const SparseArgs *sparse = nullptr, int ab_blocked = 0, int sparse_only = 0)
 {
     SparseArgs sa;
     std::memset(&sa, 0, sizeof sa);
@@ -277,7 +296,7 @@ static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U,
         const int bs = 128;
         commit_linearize_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
             sys, qc.dt, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (T *)A, (T *)Bd, (const T *)Xc, (const T *)Uc, winner, wslot,
-            active, iters, it, do_lin, g0, g1, sa, ab_blocked);
+            active, iters, it, do_lin, g0, g1, sa, ab_blocked, sparse_only);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });
@@ -306,7 +325,7 @@ static int launch_backward_depth(Handle *h, const Cost &qc, const void *X, const
 
 static int launch_backward(Handle *h, const void *X, const void *U, const void *A, const void *Bd, void *K, void *k,
                            const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr,
-                           const SparseArgs *sparse = nullptr, int ab_blocked = 0)
+                           const SparseArgs *sparse = nullptr, int ab_blocked = 0, int sparse_only = 0)
 {
     SparseArgs sa;
     std::memset(&sa, 0, sizeof sa);
@@ -321,7 +340,7 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
             // ones, where it runs next to the thread-per-trajectory kernel and each returns at once when the
             // iteration is not its kind (SparseArgs::only)
             const bool lanes = h->env_lanes >= 0 ? h->env_lanes != 0 : h->p.B <= 32768;
-            const bool both = !lanes && sa.cur != nullptr && h->env_lanes < 0;
+            const bool both = sparse_only || (!lanes && sa.cur != nullptr && h->env_lanes < 0);
             if (lanes || both) {
                 constexpr int DEPTH = 8, SLOTS = 8, LP = 26;
                 const size_t smem = sizeof(T) * (size_t)(DEPTH * SLOTS * LP + SLOTS * 4 + SLOTS * 20);
@@ -332,10 +351,11 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
                     qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active,
                     gate, (const T *)mu, sl, ab_blocked);
                 ILQR_CHECK_LAUNCH(h);
-                if (!both) return ILQR_OK;
+                if (!both || sparse_only) return ILQR_OK;
                 sa.only = 1;
             }
         }
+        if (sparse_only) sa.only = 2;        // dense iterations belong to the fused kernel
         if constexpr (Sys::N > 4) {
             // n = 12, m = 4: a ring stage is 208 rows; two stages of one warp fit the 227 KB limit
             return launch_backward_depth<T, Sys::N, Sys::M, 2, 32>(h, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa, ab_blocked);
@@ -347,11 +367,59 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
     });
 }
 
+// The fused K1+K2 kernel exists for the hand-written second-order models with the quadratic cost (n <= 4).
+template <class Sys, class Cost> constexpr bool fused_eligible()
+{
+    return !Sys::GENERIC && !Sys::FIRST_ORDER && Sys::N <= 4 && Cost::QUADRATIC;
+}
+
+static bool fused_available(const Handle *h)
+{
+#ifdef ILQR_USER_SYS
+    (void)h;
+    return false;
+#else
+    return h->p.model != ILQR_LTV && h->env_fused != 0;
+#endif
+}
+
+// K1 + K2 in one launch (ilqr_kernels_fused.cuh): commit of the accepted candidates, linearization and reverse scan
+static int launch_fused(Handle *h, const void *phi, void *X, void *U, const void *Xc, const void *Uc, const int *winner,
+                        const int *wslot, const int *active, const int *iters, int it, const unsigned int *g0,
+                        const unsigned int *g1, void *K, void *k, const void *mu, cudaStream_t st,
+                        const SparseArgs *sparse = nullptr)
+{
+    SparseArgs sa;
+    std::memset(&sa, 0, sizeof sa);
+    if (sparse) sa = *sparse;
+    return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
+        using T = decltype(tz);
+        using Sys = decltype(sys);
+        using Cost = decltype(qc);
+        constexpr int I = decltype(integ)::value;
+        if constexpr (fused_eligible<Sys, Cost>()) {
+            const int groups = (h->p.B + 31) / 32;
+            if (h->env_fused_np == 3)
+                fused_backward_kernel<Sys, Cost, I, T, 3, 3><<<groups, 128, 0, st>>>(
+                    sys, qc, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (const T *)Xc, (const T *)Uc, winner, wslot, active,
+                    iters, it, g0, g1, (T *)K, (T *)k, (const T *)mu, sa);
+            else
+                fused_backward_kernel<Sys, Cost, I, T, 2, 4><<<groups, 96, 0, st>>>(
+                    sys, qc, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (const T *)Xc, (const T *)Uc, winner, wslot, active,
+                    iters, it, g0, g1, (T *)K, (T *)k, (const T *)mu, sa);
+            ILQR_CHECK_LAUNCH(h);
+            return ILQR_OK;
+        } else {
+            return ILQR_E_INVALID;
+        }
+    });
+}
+
 // K2 of the LTV model: A_t, B_t generated in the kernel (no linearization buffers)
 static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const void *U, void *K, void *k,
                                const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr)
 {
-#ifdef ILQR_USER_SYS
+#if defined(ILQR_USER_SYS) || defined(ILQR_FAST_BUILD)
     return ILQR_E_INVALID;
 #else
     constexpr int TPB = 16;
@@ -628,6 +696,8 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
         h->env_lanes = (e = getenv("ILQR_BACKWARD_LANES")) ? (atoi(e) != 0) : -1;
         h->env_rollout_bs = (e = getenv("ILQR_ROLLOUT_BS")) && atoi(e) >= 32 ? atoi(e) / 32 * 32 : 0;
         h->env_check_every = (e = getenv("ILQR_CHECK_EVERY")) && atoi(e) > 0 ? atoi(e) : 8;
+        h->env_fused = (e = getenv("ILQR_FUSED")) ? (atoi(e) != 0) : -1;
+        h->env_fused_np = (e = getenv("ILQR_FUSED_NP")) && atoi(e) == 3 ? 3 : 2;
     }
     h->env_sparse_thresh = (e = getenv("ILQR_SPARSE_THRESH")) ? atol(e) : -1;
     h->env_sparse_all = (e = getenv("ILQR_SPARSE_ALL")) ? atol(e) : -1;
@@ -746,6 +816,9 @@ int ilqr_backward_pass(ilqr_handle_t hh, const void *phi, const void *X, const v
     char *w = (char *)ws;
     if (!X || !U || !K || !k) return ILQR_E_INVALID;
     if (h->p.model == ILQR_LTV) return launch_backward_ltv(h, phi, X, U, K, k, nullptr, nullptr, (cudaStream_t)stream);
+    if (h->env_fused == 1 && fused_available(h))            // opt-in: the fused kernel, nothing to commit
+        return launch_fused(h, phi, (void *)X, (void *)U, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr,
+                            nullptr, K, k, nullptr, (cudaStream_t)stream);
     int rc = ilqr_linearize(hh, phi, X, U, w + L.A, w + L.Bd, stream);
     if (rc) return rc;
     return ilqr_backward(hh, X, U, w + L.A, w + L.Bd, K, k, stream);
@@ -823,6 +896,9 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     }
     const int B = p.B, bsB = 128;
     int rc;
+    // fused K1+K2 (ilqr_kernels_fused.cuh): thread-per-trajectory consumers, i.e. the large-batch regime where the
+    // separate kernels stream A_t, B_t through HBM; small batches keep the latency-optimised four-lane scan
+    const bool fused = fused_available(h) && (h->env_fused == 1 || B > 32768);
     // two-wave line search (see select_kernel): n1 eager step sizes, n2 deferred ones
     const int n1 = h->n_first, n2 = h->n_alpha_eff - h->n_first;
     const size_t wbytes = p.dtype == ILQR_F64 ? 8 : 4;
@@ -877,12 +953,28 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
                 sa.thresh_all = sparse_all;
                 sa.n_alpha_all = h->n_alpha_eff;
             }
+            if (fused) {
+                // dense iterations: ONE kernel commits, linearizes and scans; the sparse iterations of the lazy
+                // schedule keep K1 + the four-lane list kernel (each kernel returns at once when the iteration is not
+                // its kind, decided on the device from the same counter)
+                if (sparse_thresh > 0) {
+                    if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, it > 0 ? wslot : nullptr, active,
+                                                      1, g, gprev, st, iters, it, &sa, h->ab_blocked, 1))) return rc;
+                    prof_mark(h, ILQR_KC_LINEARIZE, st);
+                }
+                if ((rc = launch_fused(h, phi, X, U, Xc, Uc, winner, it > 0 ? wslot : nullptr, active, iters, it, g, gprev, K, k,
+                                       rg.mu, st, &sa))) return rc;
+                if (sparse_thresh > 0 &&
+                    (rc = launch_backward(h, X, U, A, Bd, K, k, active, g, st, rg.mu, &sa, h->ab_blocked, 1))) return rc;
+                prof_mark(h, ILQR_KC_BACKWARD, st);
+            } else {
             if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, it > 0 ? wslot : nullptr, active,
                                               ltv ? 0 : 1, g, gprev, st, iters, it, &sa, h->ab_blocked))) return rc;
             prof_mark(h, ILQR_KC_LINEARIZE, st);
             if ((rc = ltv ? launch_backward_ltv(h, phi, X, U, K, k, active, g, st, rg.mu)
                           : launch_backward(h, X, U, A, Bd, K, k, active, g, st, rg.mu, &sa, h->ab_blocked))) return rc;
             prof_mark(h, ILQR_KC_BACKWARD, st);
+            }
             if (h->lazy) {
                 // lazy line search: wave v rolls out step sizes [wave_lo[v], wave_lo[v+1]) for the trajectories
                 // that accepted none so far (wave 0: every active one); later waves return at once while

@@ -44,6 +44,130 @@ ILQR_DEV void bwd_read(BwdIn<T, n, m> &d, const T *stage)
     for (int j = 0; j < m; ++j, ++row) d.u[j] = stage[row * bd + tid];
 }
 
+// One step of the reverse scan (iLQR_class.py:92-119) on the inputs `cur` = (A_t, B_t, x_t, u_t): updates the value
+// function (V_x, V_xx) in place and returns the gains K_t, k_t.  Shared by backward_kernel and the fused
+// linearize+backward kernel so that both execute the same operation sequence.
+template <class Cost, typename T, int n, int m>
+ILQR_DEV void riccati_step(const Cost &qc, const BwdIn<T, n, m> &cur, T mu_b, T *Vx, T (*Vxx)[n], T (*Kt)[n], T *kt)
+{
+    T lx[n], lu[m];
+    // quadratic costs: l_xx = Q dt, l_uu = R dt, l_ux = 0 are constants folded into the sums below;
+    // generated user costs (ilqr_user.cuh) provide the full state-dependent expansion
+    [[maybe_unused]] T lxx[Cost::QUADRATIC ? 1 : n][Cost::QUADRATIC ? 1 : n];
+    [[maybe_unused]] T luu[Cost::QUADRATIC ? 1 : m][Cost::QUADRATIC ? 1 : m];
+    [[maybe_unused]] T lux[Cost::QUADRATIC ? 1 : m][Cost::QUADRATIC ? 1 : n];
+    if constexpr (Cost::QUADRATIC) qc.grad(cur.x, cur.u, lx, lu);
+    else qc.expand(cur.x, cur.u, lx, lu, lxx, luu, lux);
+    // Q_x = l_x + f_x' V_x ; Q_u = l_u + f_u' V_x                    (:100-101)
+    T Qx[n], Qu[m];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        T s = T(0);
+#pragma unroll
+        for (int l = 0; l < n; ++l) s += cur.A[l][i] * Vx[l];
+        Qx[i] = lx[i] + s;
+    }
+#pragma unroll
+    for (int j = 0; j < m; ++j) {
+        T s = T(0);
+#pragma unroll
+        for (int l = 0; l < n; ++l) s += cur.Bd[l][j] * Vx[l];
+        Qu[j] = lu[j] + s;
+    }
+    // T1 = f_x' V_xx, T2 = f_u' V_xx ; Q_xx = l_xx + T1 f_x ; Q_ux = T2 f_x ; Q_uu = l_uu + T2 f_u   (:102-104)
+    T T1[n][n], T2[m][n], Qxx[n][n], Qux[m][n], Quu[m][m];
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            T s = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) s += cur.A[l][i] * Vxx[l][j];
+            T1[i][j] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < m; ++i)
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            T s = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) s += cur.Bd[l][i] * Vxx[l][j];
+            T2[i][j] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            T s = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) s += T1[i][l] * cur.A[l][j];
+            if constexpr (Cost::QUADRATIC) Qxx[i][j] = qc.Qs[i][j] * qc.dt + s;
+            else Qxx[i][j] = lxx[i][j] + s;
+        }
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            T s = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) s += T2[i][l] * cur.A[l][j];
+            if constexpr (Cost::QUADRATIC) Qux[i][j] = s;            // l_ux = 0 for the quadratic cost
+            else Qux[i][j] = lux[i][j] + s;
+        }
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+            T s = T(0);
+#pragma unroll
+            for (int l = 0; l < n; ++l) s += T2[i][l] * cur.Bd[l][j];
+            if constexpr (Cost::QUADRATIC) Quu[i][j] = qc.Rs[i][j] * qc.dt + s;
+            else Quu[i][j] = luu[i][j] + s;
+            if (i == j) Quu[i][j] += mu_b;
+        }
+    }
+    // K = -Q_uu^-1 Q_ux, k = -Q_uu^-1 Q_u                            (:109-110; no regularisation)
+    if (m == 1) {
+        const T r = -rcp_t(Quu[0][0]);
+#pragma unroll
+        for (int j = 0; j < n; ++j) Kt[0][j] = Qux[0][j] * r;
+        kt[0] = Qu[0] * r;
+    } else {
+        T rhs[m][n + 1];
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) rhs[i][j] = Qux[i][j];
+            rhs[i][n] = Qu[i];
+        }
+        T Lm[m][m];
+#pragma unroll
+        for (int i = 0; i < m; ++i)
+#pragma unroll
+            for (int j = 0; j < m; ++j) Lm[i][j] = Quu[i][j];
+        lu_solve_inplace<m, n + 1>(Lm, rhs);
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) Kt[i][j] = -rhs[i][j];
+            kt[i] = -rhs[i][n];
+        }
+    }
+    // V_x = Q_x + K' Q_u ; V_xx = Q_xx + Q_ux' K                      (:113-114; not symmetrised)
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        T s = T(0);
+#pragma unroll
+        for (int j = 0; j < m; ++j) s += Kt[j][i] * Qu[j];
+        Vx[i] = Qx[i] + s;
+#pragma unroll
+        for (int c = 0; c < n; ++c) {
+            T s2 = T(0);
+#pragma unroll
+            for (int j = 0; j < m; ++j) s2 += Qux[j][i] * Kt[j][c];
+            Vxx[i][c] = Qxx[i][c] + s2;
+        }
+    }
+}
+
 template <class Cost, typename T, int n, int m, int DEPTH, int BS>
 __global__ void __launch_bounds__(BS) backward_kernel(const __grid_constant__ Cost qc, int N, int B, const T *__restrict__ X,
                                 const T *__restrict__ U, const T *__restrict__ A, const T *__restrict__ Bd,
@@ -61,6 +185,8 @@ __global__ void __launch_bounds__(BS) backward_kernel(const __grid_constant__ Co
         if (sa.only == 1) return;                                        // ... which the four-lane kernel does better
         if ((unsigned int)b >= *sa.n_cur) return;
         b = sa.cur[b];                                                   // A_t, B_t stay at the list position (K1)
+    } else if (sa.only == 2) {
+        return;                                                          // dense iterations: another kernel's
     }
     if (b >= B) return;
     if (active && !active[b]) return;
@@ -118,123 +244,8 @@ __global__ void __launch_bounds__(BS) backward_kernel(const __grid_constant__ Co
     for (int t = N - 1; t >= 0; --t) {
         cp_async_wait<DEPTH - 1>();                                       // the group holding step t has landed
         bwd_read<BS>(cur, ring + stage * stage_elems);
-        T lx[n], lu[m];
-        // quadratic costs: l_xx = Q dt, l_uu = R dt, l_ux = 0 are constants folded into the sums below;
-        // generated user costs (ilqr_user.cuh) provide the full state-dependent expansion
-        [[maybe_unused]] T lxx[Cost::QUADRATIC ? 1 : n][Cost::QUADRATIC ? 1 : n];
-        [[maybe_unused]] T luu[Cost::QUADRATIC ? 1 : m][Cost::QUADRATIC ? 1 : m];
-        [[maybe_unused]] T lux[Cost::QUADRATIC ? 1 : m][Cost::QUADRATIC ? 1 : n];
-        if constexpr (Cost::QUADRATIC) qc.grad(cur.x, cur.u, lx, lu);
-        else qc.expand(cur.x, cur.u, lx, lu, lxx, luu, lux);
-        // Q_x = l_x + f_x' V_x ; Q_u = l_u + f_u' V_x                    (:100-101)
-        T Qx[n], Qu[m];
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-            T s = T(0);
-#pragma unroll
-            for (int l = 0; l < n; ++l) s += cur.A[l][i] * Vx[l];
-            Qx[i] = lx[i] + s;
-        }
-#pragma unroll
-        for (int j = 0; j < m; ++j) {
-            T s = T(0);
-#pragma unroll
-            for (int l = 0; l < n; ++l) s += cur.Bd[l][j] * Vx[l];
-            Qu[j] = lu[j] + s;
-        }
-        // T1 = f_x' V_xx, T2 = f_u' V_xx ; Q_xx = l_xx + T1 f_x ; Q_ux = T2 f_x ; Q_uu = l_uu + T2 f_u   (:102-104)
-        T T1[n][n], T2[m][n], Qxx[n][n], Qux[m][n], Quu[m][m];
-#pragma unroll
-        for (int i = 0; i < n; ++i)
-#pragma unroll
-            for (int j = 0; j < n; ++j) {
-                T s = T(0);
-#pragma unroll
-                for (int l = 0; l < n; ++l) s += cur.A[l][i] * Vxx[l][j];
-                T1[i][j] = s;
-            }
-#pragma unroll
-        for (int i = 0; i < m; ++i)
-#pragma unroll
-            for (int j = 0; j < n; ++j) {
-                T s = T(0);
-#pragma unroll
-                for (int l = 0; l < n; ++l) s += cur.Bd[l][i] * Vxx[l][j];
-                T2[i][j] = s;
-            }
-#pragma unroll
-        for (int i = 0; i < n; ++i)
-#pragma unroll
-            for (int j = 0; j < n; ++j) {
-                T s = T(0);
-#pragma unroll
-                for (int l = 0; l < n; ++l) s += T1[i][l] * cur.A[l][j];
-                if constexpr (Cost::QUADRATIC) Qxx[i][j] = qc.Qs[i][j] * qc.dt + s;
-                else Qxx[i][j] = lxx[i][j] + s;
-            }
-#pragma unroll
-        for (int i = 0; i < m; ++i) {
-#pragma unroll
-            for (int j = 0; j < n; ++j) {
-                T s = T(0);
-#pragma unroll
-                for (int l = 0; l < n; ++l) s += T2[i][l] * cur.A[l][j];
-                if constexpr (Cost::QUADRATIC) Qux[i][j] = s;            // l_ux = 0 for the quadratic cost
-                else Qux[i][j] = lux[i][j] + s;
-            }
-#pragma unroll
-            for (int j = 0; j < m; ++j) {
-                T s = T(0);
-#pragma unroll
-                for (int l = 0; l < n; ++l) s += T2[i][l] * cur.Bd[l][j];
-                if constexpr (Cost::QUADRATIC) Quu[i][j] = qc.Rs[i][j] * qc.dt + s;
-                else Quu[i][j] = luu[i][j] + s;
-                if (i == j) Quu[i][j] += mu_b;
-            }
-        }
-        // K = -Q_uu^-1 Q_ux, k = -Q_uu^-1 Q_u                            (:109-110; no regularisation)
         T Kt[m][n], kt[m];
-        if (m == 1) {
-            const T r = -rcp_t(Quu[0][0]);
-#pragma unroll
-            for (int j = 0; j < n; ++j) Kt[0][j] = Qux[0][j] * r;
-            kt[0] = Qu[0] * r;
-        } else {
-            T rhs[m][n + 1];
-#pragma unroll
-            for (int i = 0; i < m; ++i) {
-#pragma unroll
-                for (int j = 0; j < n; ++j) rhs[i][j] = Qux[i][j];
-                rhs[i][n] = Qu[i];
-            }
-            T Lm[m][m];
-#pragma unroll
-            for (int i = 0; i < m; ++i)
-#pragma unroll
-                for (int j = 0; j < m; ++j) Lm[i][j] = Quu[i][j];
-            lu_solve_inplace<m, n + 1>(Lm, rhs);
-#pragma unroll
-            for (int i = 0; i < m; ++i) {
-#pragma unroll
-                for (int j = 0; j < n; ++j) Kt[i][j] = -rhs[i][j];
-                kt[i] = -rhs[i][n];
-            }
-        }
-        // V_x = Q_x + K' Q_u ; V_xx = Q_xx + Q_ux' K                      (:113-114; not symmetrised)
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-            T s = T(0);
-#pragma unroll
-            for (int j = 0; j < m; ++j) s += Kt[j][i] * Qu[j];
-            Vx[i] = Qx[i] + s;
-#pragma unroll
-            for (int c = 0; c < n; ++c) {
-                T s2 = T(0);
-#pragma unroll
-                for (int j = 0; j < m; ++j) s2 += Qux[j][i] * Kt[j][c];
-                Vxx[i][c] = Qxx[i][c] + s2;
-            }
-        }
+        riccati_step<Cost, T, n, m>(qc, cur, mu_b, Vx, Vxx, Kt, kt);
 #pragma unroll
         for (int j = 0; j < m; ++j) {
 #pragma unroll

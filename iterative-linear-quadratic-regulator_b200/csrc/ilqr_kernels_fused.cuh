@@ -1,0 +1,222 @@
+// ilqr_kernels_fused.cuh -- K1 and K2 as ONE warp-specialised kernel: producer warps commit the accepted line-search
+// candidate and compute the analytic A_t, B_t of the steps ahead (K1's work, iLQR_class.py:318-331), the consumer warp
+// runs the Riccati recursion behind them (K2's work, iLQR_class.py:79-161).  A_t, B_t travel through a shared-memory
+// ring guarded by mbarriers and never touch HBM: of the 600 algorithmic bytes per trajectory-timestep of the three-kernel
+// iteration, the 320 that existed only because linearization and recursion were two kernels disappear, together with
+// one launch per iteration.
+// Part of libilqr_b200.so; included by ilqr_b200.cu only (see the file map at its top).
+#pragma once
+#include "ilqr_systems.cuh"
+#include "ilqr_kernels_common.cuh"
+#include "ilqr_kernels_backward.cuh"
+
+namespace ilqr {
+
+// ---- mbarrier (shared::cta) -------------------------------------------------------------------------------------------
+ILQR_DEV void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+// release: the caller's earlier shared-memory writes are visible to whoever observes the phase complete
+ILQR_DEV void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+// acquire: spin until the phase of the given parity has completed (a fresh barrier passes parity 1 at once)
+ILQR_DEV void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(a),
+                 "r"(parity)
+                 : "memory");
+}
+
+// Thread-per-trajectory form (large batches, HBM/FP64-throughput regime).  One block = one group of 32 trajectories
+// (lane = trajectory) = 1 consumer warp + NP producer warps.  Producer p owns the scan steps i = N-1-t with
+// i mod NP == p; ring stage i mod S (S a multiple of NP, so a producer always meets the same stages).  A lane only ever
+// reads what the same lane of a producer wrote, so a stage is [rows][32 lanes]: conflict-free in both directions.
+//   producer:  x_t,u_t from the accepted candidate slab (or the nominal; cp.async, one step ahead) -> commit into X,U ->
+//              wait empty[s] -> step_jac -> ring -> arrive full[s]
+//   consumer:  wait full[s] -> ring -> registers -> arrive empty[s] -> riccati_step -> coalesced K_t, k_t stores
+#ifndef ILQR_FUSED_MINBLOCKS
+#define ILQR_FUSED_MINBLOCKS 1
+#endif
+template <class Sys, class Cost, int INTEG, typename T, int NP, int S>
+__global__ void __launch_bounds__(32 * (NP + 1), ILQR_FUSED_MINBLOCKS)
+fused_backward_kernel(const __grid_constant__ Sys sys, const __grid_constant__ Cost qc, int N, int B, const T *__restrict__ phi,
+                      T *__restrict__ X, T *__restrict__ U, const T *__restrict__ Xc, const T *__restrict__ Uc,
+                      const int *__restrict__ winner, const int *__restrict__ wslot, const int *__restrict__ active,
+                      const int *__restrict__ iters, int it, const unsigned int *__restrict__ gate0,
+                      const unsigned int *__restrict__ gate1, T *__restrict__ K, T *__restrict__ k,
+                      const T *__restrict__ mu, const __grid_constant__ SparseArgs sa)
+{
+    constexpr int n = Sys::N, m = Sys::M, L = n * n + n * m + n + m;
+    static_assert(S % NP == 0, "ring stages must be a multiple of the producer count");
+    __shared__ __align__(16) T ring[S][L][32];
+    __shared__ __align__(16) T pre[NP][2][n + m][32];       // producers' input staging (cp.async)
+    __shared__ __align__(8) unsigned long long full[S], empty[S];
+    if (gate0 && *gate0 == 0u && *gate1 == 0u) return;       // nobody active now or in the previous iteration
+    if (sparse_now(sa)) return;                              // a sparse iteration belongs to K1 + the list kernels
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b_raw = blockIdx.x * 32 + lane;
+    const bool valid = b_raw < B;
+    const int b = valid ? b_raw : B - 1;                     // lanes past the batch compute on a copy, never store
+    int w = (valid && winner) ? winner[b] : -1;
+    if (iters && iters[b] != it) w = -1;                     // nothing pending: committed earlier, or never ran
+    const bool act = valid && (active ? active[b] != 0 : true);
+    const unsigned full_mask = 0xffffffffu;
+    const bool any_act = __any_sync(full_mask, act), any_commit = __any_sync(full_mask, w >= 0);
+    if (!any_act && !any_commit) return;                     // every warp of the block sees the same 32 trajectories
+    // source of x_t, u_t: the accepted candidate (lazy schedule: stored at the trajectory's list position) or the nominal
+    const int col = (w >= 0 && wslot) ? wslot[b] : b;
+    const T *xs = w >= 0 ? Xc + (size_t)w * (N + 1) * n * B + col : X + col;
+    const T *us = w >= 0 ? Uc + (size_t)w * N * m * B + col : U + col;
+    const size_t sB = (size_t)B;
+    if (!any_act) {
+        // the group only has candidates to commit (its trajectories finished in the previous iteration): plain copy
+        for (int t = wid; t <= N; t += NP + 1) {
+            if (w >= 0) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) X[((size_t)t * n + i) * sB + b] = xs[((size_t)t * n + i) * sB];
+                if (t < N) {
+#pragma unroll
+                    for (int j = 0; j < m; ++j) U[((size_t)t * m + j) * sB + b] = us[((size_t)t * m + j) * sB];
+                }
+            }
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 32); mbar_init(&empty[s], 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (wid == 0) {
+        // ---------------- consumer: the reverse scan, value function in registers ----------------
+        const T mu_b = mu ? mu[b] : T(0);                    // regularisation (RegArgs), 0 in the reference
+        T Vx[n], Vxx[n][n];
+        {
+            T xN[n];
+#pragma unroll
+            for (int i = 0; i < n; ++i) xN[i] = xs[((size_t)N * n + i) * sB];
+            if (w >= 0) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) X[((size_t)N * n + i) * sB + b] = xN[i];
+            }
+            if constexpr (Cost::QUADRATIC) {
+                qc.terminal_grad(xN, Vx);                    // iLQR_class.py:136-138
+#pragma unroll
+                for (int i = 0; i < n; ++i)
+#pragma unroll
+                    for (int j = 0; j < n; ++j) Vxx[i][j] = qc.Qfs[i][j];
+            } else {
+                qc.terminal_expand(xN, Vx, Vxx);
+            }
+        }
+        T *Kp = K + (size_t)(N - 1) * m * n * sB + b, *kp = k + (size_t)(N - 1) * m * sB + b;
+        for (int i = 0; i < N; ++i) {
+            const int s = i % S;
+            mbar_wait(&full[s], (unsigned)(i / S) & 1u);
+            BwdIn<T, n, m> cur;
+            {
+                const T *st = &ring[s][0][lane];
+                int row = 0;
+#pragma unroll
+                for (int r = 0; r < n; ++r)
+#pragma unroll
+                    for (int c = 0; c < n; ++c, ++row) cur.A[r][c] = st[row * 32];
+#pragma unroll
+                for (int r = 0; r < n; ++r)
+#pragma unroll
+                    for (int c = 0; c < m; ++c, ++row) cur.Bd[r][c] = st[row * 32];
+#pragma unroll
+                for (int r = 0; r < n; ++r, ++row) cur.x[r] = st[row * 32];
+#pragma unroll
+                for (int c = 0; c < m; ++c, ++row) cur.u[c] = st[row * 32];
+            }
+            mbar_arrive(&empty[s]);                          // the stage is in registers: hand it back at once
+            T Kt[m][n], kt[m];
+            riccati_step<Cost, T, n, m>(qc, cur, mu_b, Vx, Vxx, Kt, kt);
+            if (act) {
+#pragma unroll
+                for (int j = 0; j < m; ++j) {
+#pragma unroll
+                    for (int c = 0; c < n; ++c) Kp[((size_t)j * n + c) * sB] = Kt[j][c];
+                    kp[(size_t)j * sB] = kt[j];
+                }
+            }
+            Kp -= (size_t)m * n * sB;
+            kp -= (size_t)m * sB;
+        }
+        return;
+    }
+
+    // ---------------- producers: commit + linearization, NP steps apart ----------------
+    // The inputs of a producer's NEXT step travel by cp.async into a two-deep staging row of its own (no registers held
+    // across step_jac); the ring stage is claimed BEFORE the arithmetic, so that x_t, u_t go into it at once and A_t, B_t
+    // as they are finished (with S stages a claim only waits when the producers are a full ring ahead anyway).
+    const int p = wid - 1;
+    const T ph = phi ? phi[b] : T(0);
+    const T *px = xs + (size_t)(N - 1 - p) * n * sB, *pu = us + (size_t)(N - 1 - p) * m * sB;
+    T *qx = X + (size_t)(N - 1 - p) * n * sB + b, *qu = U + (size_t)(N - 1 - p) * m * sB + b;
+    const size_t dx = (size_t)NP * n * sB, du = (size_t)NP * m * sB;
+    auto prefetch = [&](int buf) {
+        T *dst = &pre[p][buf][0][lane];
+#pragma unroll
+        for (int r = 0; r < n; ++r) cp_async<sizeof(T)>(dst + r * 32, px + (size_t)r * sB);
+#pragma unroll
+        for (int c = 0; c < m; ++c) cp_async<sizeof(T)>(dst + (n + c) * 32, pu + (size_t)c * sB);
+        px -= dx;
+        pu -= du;
+    };
+    if (p < N) prefetch(0);
+    cp_async_commit();
+    int buf = 0;
+    for (int i = p; i < N; i += NP) {
+        const int t = N - 1 - i, s = i % S;
+        if (i + NP < N) prefetch(buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();                                  // this step's inputs have landed (own copies only)
+        T x[n], u[m];
+        {
+            const T *src = &pre[p][buf][0][lane];
+#pragma unroll
+            for (int r = 0; r < n; ++r) x[r] = src[r * 32];
+#pragma unroll
+            for (int c = 0; c < m; ++c) u[c] = src[(n + c) * 32];
+        }
+        buf ^= 1;
+        if (w >= 0) {                                        // commit the accepted candidate into the nominal
+#pragma unroll
+            for (int r = 0; r < n; ++r) qx[(size_t)r * sB] = x[r];
+#pragma unroll
+            for (int c = 0; c < m; ++c) qu[(size_t)c * sB] = u[c];
+        }
+        qx -= dx;
+        qu -= du;
+        mbar_wait(&empty[s], ((unsigned)(i / S) & 1u) ^ 1u);
+        T *st = &ring[s][0][lane];
+#pragma unroll
+        for (int r = 0; r < n; ++r) st[(n * n + n * m + r) * 32] = x[r];
+#pragma unroll
+        for (int c = 0; c < m; ++c) st[(n * n + n * m + n + c) * 32] = u[c];
+        T Aj[n][n], Bj[n][m];
+        step_jac<INTEG>(sys, qc.dt, x, u, Aj, Bj, sys.time_scalar(t, ph));
+#pragma unroll
+        for (int r = 0; r < n; ++r) {
+#pragma unroll
+            for (int c = 0; c < n; ++c) st[(r * n + c) * 32] = Aj[r][c];
+#pragma unroll
+            for (int c = 0; c < m; ++c) st[(n * n + r * m + c) * 32] = Bj[r][c];
+        }
+        mbar_arrive(&full[s]);
+    }
+}
+
+}  // namespace ilqr

@@ -98,9 +98,10 @@ __global__ void __launch_bounds__(128, Sys::N <= 4 ? 4 : 1) commit_linearize_ker
                                         const int *__restrict__ wslot, const int *__restrict__ active,
                                         const int *__restrict__ iters, int it, int do_linearize,
                                         const unsigned int *__restrict__ gate0, const unsigned int *__restrict__ gate1,
-                                        const __grid_constant__ SparseArgs sa, int ab_blocked)
+                                        const __grid_constant__ SparseArgs sa, int ab_blocked, int sparse_only)
 {
     if (gate0 && *gate0 == 0u && *gate1 == 0u) return;   // nobody active now or in the previous iteration
+    if (sparse_only && !sparse_now(sa)) return;          // dense iterations: the fused kernel commits and linearizes
     const int *pos = sparse_now(sa) ? sa.pos : nullptr;  // where K2 will look for A_t, B_t in this iteration
     if (sparse_prev(sa)) {
         // few trajectories ran the previous iteration: the first blocks stride over (t, list entry) pairs, the

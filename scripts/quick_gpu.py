@@ -86,7 +86,7 @@ def profiled_solves(sol, iters):
         torch.cuda.synchronize(); t0 = time.time(); tot = sol.solve_device(); t1 = time.time()
         print(f"solve maxiter={iters}: {tot} traj-iters in {(t1-t0)*1e3:.2f} ms -> {tot/(t1-t0)/1e6:.3f} M traj-iter/s")
     kt = sol.kernel_times()
-    nit = max(1, kt["linearize"][1])
+    nit = max(1, kt["linearize"][1], kt["backward"][1])
     print("  per iteration ms: " + ", ".join(f"{k} {v[0]/nit:.3f}" for k, v in kt.items()) + f"  ({nit} iterations)")
 
 

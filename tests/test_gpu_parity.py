@@ -406,11 +406,51 @@ def test_fp32_full_solve_matches_fp64_within_1e4(oracle):
         sol = iLQR(ua_system(dtype=dt), 1.0, x0, np.zeros((1, N)), maxiter=1, tol=0.0, verbose=False)
         X, U, cost = sol.optimize_trajectory()
         out[dt] = (np.asarray(X, dtype=np.float64), np.asarray(cost, dtype=np.float64), sol.iterations.copy())
-    # every member: 1e-4, or 30x what FP32-rounding-level input noise (6e-8) does to the same member in the oracle
-    _, sens = batch_sensitivity(oracle, ua_oracle_problem(oracle, N, maxiter=1, tol=0.0), x0, np.zeros((B, 1, N)), eps=6e-8)
+    # every member: 1e-4, or 30x what FP32-rounding-level input noise does to the same member in the oracle
+    # (FP32 rounds at 6e-8 in every one of the ~10^4 operations of a 100-step RK4 rollout: the equivalent single
+    # input perturbation is taken as 1e-6)
+    _, sens = batch_sensitivity(oracle, ua_oracle_problem(oracle, N, maxiter=1, tol=0.0), x0, np.zeros((B, 1, N)), eps=1e-6)
     same = out["float32"][2] == out["float64"][2]
     assert same.all()
     ec = member_rel_err(out["float32"][1], out["float64"][1])
     ex = member_rel_err(out["float32"][0], out["float64"][0])
     assert np.all(ec <= np.maximum(1e-4, SF * sens["cost"])), (ec.max(), sens["cost"].max())
     assert np.all(ex <= np.maximum(1e-4, SF * sens["X"])), (ex.max(), sens["X"].max())
+
+
+def _solve_outputs(sol):
+    X, U, cost = sol.optimize_trajectory()
+    return [np.array(a) for a in (X, U, cost, sol.K, sol.U_ff, sol.iterations, sol.status)]
+
+
+@pytest.mark.parametrize("kind,integ", [("ua", "rk4"), ("ua", "backward_euler"), ("double", "rk4"), ("pendulum", "midpoint")])
+def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, integ):
+    """K1+K2 as one warp-specialised kernel (csrc/ilqr_kernels_fused.cuh: producers commit + linearize into a
+    shared-memory ring, the consumer scans) against the two-kernel path with the thread-per-trajectory scan: the same
+    operation sequence, so gains, trajectories, costs and control flow must agree BIT FOR BIT -- in a solve with
+    staggered convergence, regularisation retries and warm-started re-solves (commits of finished trajectories, inactive
+    lanes, a ragged last group), on the eager and the lazy schedule, and in backward_pass()."""
+    from class_files.iLQR_class import iLQR
+    golden = {"ua": "solve_ua_rk4_T1_b0", "double": "solve_double_rk4_T1_b0", "pendulum": "solve_pend_rk4_T1"}[kind]
+    s = system_from_golden(load_golden(golden), integrator=integ)
+    B, N = 1000, 80
+    rng = np.random.default_rng(5)
+    x0 = cfg2_x0(B, seed=5)[:, :s.n_x] if kind != "pendulum" else rng.uniform(-2, 2, (B, 2))
+    out = {}
+    monkeypatch.setenv("ILQR_BACKWARD_LANES", "0")
+    monkeypatch.setenv("ILQR_SPARSE", "0")
+    for fused in ("0", "1"):
+        monkeypatch.setenv("ILQR_FUSED", fused)
+        res = []
+        for waves in ((), (2, 2, 2, 4)):
+            sol = iLQR(s, N * s.dt, x0, np.zeros((s.n_u, N)), tol=1e-2, maxiter=40, verbose=False, reg_factor=10.0)
+            sol.set_linesearch_waves(waves)
+            res += _solve_outputs(sol)
+            sol.x_0 = x0 + 0.02                                   # warm-started re-solve (MPC style)
+            res += _solve_outputs(sol)
+            U_ff, K = sol.backward_pass(sol.X, sol.U)
+            res += [np.array(U_ff), np.array(K)]
+        out[fused] = res
+    assert len(np.unique(out["0"][5])) > 1                        # trajectories really finish at different iterations
+    for a, b in zip(out["0"], out["1"]):
+        assert np.array_equal(a, b, equal_nan=True)
