@@ -178,6 +178,11 @@ enum { ILQR_KC_LINEARIZE = 0, ILQR_KC_BACKWARD = 1, ILQR_KC_ROLLOUT = 2, ILQR_KC
 int ilqr_set_profiling(ilqr_handle_t h, int enable);
 int ilqr_get_kernel_times(ilqr_handle_t h, double *ms, int64_t *launches);
 
+/* Measured FP64 FMA throughput of the current device in TFLOP/s (best of three ~10 ms runs of independent DFMA
+ * chains on every SM): the denominator of bench.py's FP64 roofline for the rollout kernel, which is bound by the FP64
+ * pipe, not by HBM.  scratch = any device buffer of >= 8 bytes.  Synchronizes the stream. */
+int ilqr_fp64_peak(double *tflops, void *scratch, void *stream);
+
 /* number of kernel launches issued through this handle since creation */
 int64_t ilqr_launch_count(ilqr_handle_t h);
 /* last cudaError_t seen by this handle (0 = none) and its string */

@@ -54,6 +54,7 @@ SIGNATURES = {
     "ilqr_set_mu_buffer": (C.c_int, [_VP, _VP]),
     "ilqr_set_profiling": (C.c_int, [_VP, C.c_int]),
     "ilqr_get_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_double), _I64P]),
+    "ilqr_fp64_peak": (C.c_int, [C.POINTER(C.c_double), _VP, _VP]),
     "ilqr_mpc_shift": (C.c_int, [_VP, _VP, _VP, _VP]),
     "ilqr_launch_count": (C.c_int64, [_VP]),
     "ilqr_last_cuda_error": (C.c_int, [_VP]),

@@ -58,6 +58,69 @@ def to_host(t):
     return arr.view(HostArray)
 
 
+class PendingSolve:
+    """Handle on the results of iLQR.optimize_trajectory_async()."""
+
+    def __init__(self, owner, slot):
+        self._owner, self._slot = owner, slot
+
+    def done(self):
+        return self._slot["done"].query()
+
+    def result(self):
+        """(X, U, cost) in the reference layout; blocks until the device->host copies of this solve have landed"""
+        sl, sol = self._slot, self._owner.sol
+        sl["done"].synchronize()
+        self.total_iterations = int(sl["h_tot"][0])
+        sol.total_iterations = self.total_iterations
+        X, U, cost = sl["h_X"].numpy(), sl["h_U"].numpy(), sl["h_cost"].numpy()
+        if not sol.batched:
+            return host(X[0]), host(U[0]), host(cost[0])
+        return host(X), host(U), host(cost)
+
+
+class AsyncResults:
+    """Two result slots (device staging in the reference layout + pinned host buffers) and a copy stream: the
+    device->host copies of one solve overlap the kernels of the next (iLQR.optimize_trajectory_async)."""
+
+    def __init__(self, sol):
+        self.sol = sol
+        B, n, m, N = sol.B, sol.n_x, sol.n_u, sol.N
+        dev = dict(dtype=sol._tdt, device="cuda")
+        self.copy_stream = torch.cuda.Stream()
+        self.slots = []
+        for _ in range(2):
+            self.slots.append(dict(
+                d_X=torch.empty((B, n, N + 1), **dev), d_U=torch.empty((B, m, N), **dev), d_cost=torch.empty((B,), **dev),
+                d_tot=torch.zeros((1,), dtype=torch.int64, device="cuda"),
+                h_X=torch.empty((B, n, N + 1), dtype=sol._tdt, pin_memory=True),
+                h_U=torch.empty((B, m, N), dtype=sol._tdt, pin_memory=True),
+                h_cost=torch.empty((B,), dtype=sol._tdt, pin_memory=True),
+                h_tot=torch.zeros((1,), dtype=torch.int64, pin_memory=True),
+                ready=torch.cuda.Event(), done=torch.cuda.Event(), used=False))
+        self.next = 0
+
+    def enqueue(self):
+        sol, sl = self.sol, self.slots[self.next]
+        self.next ^= 1
+        cur = torch.cuda.current_stream()
+        if sl["used"]:
+            cur.wait_event(sl["done"])               # the slot's previous copies have left its device staging
+        # device [time][dim][B] -> reference layout (B, dim, time), on the solve's stream
+        sl["d_X"].copy_(sol._X.permute(2, 1, 0))
+        sl["d_U"].copy_(sol._U.permute(2, 1, 0))
+        sl["d_cost"].copy_(sol._cost)
+        torch.sum(sol._iters, dim=0, keepdim=True, dtype=torch.int64, out=sl["d_tot"])
+        sl["ready"].record(cur)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(sl["ready"])
+            for k in ("X", "U", "cost", "tot"):
+                sl["h_" + k].copy_(sl["d_" + k], non_blocking=True)
+            sl["done"].record(self.copy_stream)
+        sl["used"] = True
+        return PendingSolve(self, sl)
+
+
 def require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError("iLQR (B200 build) needs a CUDA device: the solver has no CPU fallback.")
@@ -68,9 +131,10 @@ def torch_dtype(name):
 
 
 def to_device(a, dtype):
-    """numpy / list / torch (any device) -> contiguous CUDA tensor of `dtype`."""
+    """numpy / list / torch (any device) -> contiguous CUDA tensor of `dtype`.  A pinned CPU tensor is copied
+    asynchronously on the current stream."""
     if isinstance(a, torch.Tensor):
-        return a.to(device="cuda", dtype=dtype)
+        return a.to(device="cuda", dtype=dtype, non_blocking=a.device.type == "cpu" and a.is_pinned())
     return torch.as_tensor(np.asarray(a, dtype=np.float64), dtype=dtype).cuda()
 
 

@@ -93,6 +93,7 @@ class iLQR:
             self._phi = D.to_device(phi, self._tdt).reshape(-1).contiguous()
             if self._phi.shape[0] != self.B:
                 raise ValueError(f"phi must hold {self.B} value(s), got {tuple(self._phi.shape)}")
+        self._async = None
         self.x_0 = x_0
         self.U = U_init
         self.total_iterations = 0
@@ -269,6 +270,34 @@ class iLQR:
             self._trace = (ta, tc)
             h = self._handle
             h.check(h.lib.ilqr_set_trace(h.h, D.ptr(ta), D.ptr(tc)))
+
+    # ------------------------------------------------------------------ pipelined host-in / host-out solves
+    def optimize_trajectory_async(self):
+        """optimize_trajectory() without waiting for the results: enqueues the solve, then the device-side transposes
+        into the reference layout and, on a second stream, the device->host copies into pinned memory.  Returns a
+        PendingSolve whose .result() gives (X, U, cost) exactly as optimize_trajectory() would.
+
+        The next solve may be set up (x_0 / U / reset_state) and started while the copies of this one are still in
+        flight -- with two result slots alternating, the D2H traffic of solve i runs under the kernels of solve i+1:
+
+            pending = None
+            for x0 in batches:
+                sol.x_0 = x0; sol.U = U_init; sol.reset_state()
+                nxt = sol.optimize_trajectory_async()
+                if pending is not None:
+                    X, U, cost = pending.result()
+                pending = nxt
+
+        The arrays returned by .result() are views of the slot's pinned buffers: they stay valid until the second
+        following optimize_trajectory_async() call re-uses the slot (copy them if they must live longer).  (The
+        reference returns JAX arrays, which are futures too: its scripts call .block_until_ready() on them.)"""
+        if self._torch_out:
+            raise RuntimeError("optimize_trajectory_async() is the host-in/host-out path; with CUDA tensors use "
+                               "solve_device(sync=False)")
+        if self._async is None:
+            self._async = D.AsyncResults(self)
+        self.solve_device(sync=False)
+        return self._async.enqueue()
 
     def trace_arrays(self):
         """(alpha_idx (B, maxiter), cost_trace (B, maxiter + 1)) of the last solve as numpy arrays: accepted try

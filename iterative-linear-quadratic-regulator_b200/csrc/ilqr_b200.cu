@@ -125,6 +125,7 @@ struct Handle {
     int env_fused;            // ILQR_FUSED: -1 [auto: fused K1+K2 inside ilqr_solve where it is the faster form], 0 never,
                               // 1 wherever the model allows (also ilqr_backward_pass)
     int env_fused_np;         // ILQR_FUSED_NP: producer warps per consumer warp, 2 [default] or 3
+    int env_fused_minb;       // ILQR_FUSED_MINB: 0 [auto: by batch size], 1 = uncapped registers, 5 = capped for 5 blocks/SM
     int env_check_every;      // ILQR_CHECK_EVERY: iterations enqueued between host polls of the active count [8]
     long env_sparse_thresh;   // ILQR_SPARSE_THRESH / ILQR_SPARSE_ALL: -1 [auto] or the thresholds of SparseArgs
     long env_sparse_all;
@@ -294,7 +295,11 @@ static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U,
         constexpr int I = decltype(integ)::value;
         const size_t threads = (size_t)(h->p.N + 1) * h->p.B;
         const int bs = 128;
-        commit_linearize_kernel<Sys, I, T><<<grid_for(threads, bs), bs, 0, st>>>(
+        int grid = grid_for(threads, bs);
+        // next to the fused kernel K1 only serves sparse iterations: a capped grid that strides over its items, so
+        // that the launch costs nothing in the dense ones (513k empty blocks took 0.28 ms at B=131072)
+        if (sparse_only && grid > 148 * 16) grid = 148 * 16;
+        commit_linearize_kernel<Sys, I, T><<<grid, bs, 0, st>>>(
             sys, qc.dt, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (T *)A, (T *)Bd, (const T *)Xc, (const T *)Uc, winner, wslot,
             active, iters, it, do_lin, g0, g1, sa, ab_blocked, sparse_only);
         ILQR_CHECK_LAUNCH(h);
@@ -399,14 +404,17 @@ static int launch_fused(Handle *h, const void *phi, void *X, void *U, const void
         constexpr int I = decltype(integ)::value;
         if constexpr (fused_eligible<Sys, Cost>()) {
             const int groups = (h->p.B + 31) / 32;
-            if (h->env_fused_np == 3)
-                fused_backward_kernel<Sys, Cost, I, T, 3, 3><<<groups, 128, 0, st>>>(
+            auto go = [&](auto np, auto stages, auto minb) {
+                constexpr int NP = decltype(np)::value, S = decltype(stages)::value, MB = decltype(minb)::value;
+                fused_backward_kernel<Sys, Cost, I, T, NP, S, MB><<<groups, 32 * (NP + 1), 0, st>>>(
                     sys, qc, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (const T *)Xc, (const T *)Uc, winner, wslot, active,
                     iters, it, g0, g1, (T *)K, (T *)k, (const T *)mu, sa);
-            else
-                fused_backward_kernel<Sys, Cost, I, T, 2, 4><<<groups, 96, 0, st>>>(
-                    sys, qc, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (const T *)Xc, (const T *)Uc, winner, wslot, active,
-                    iters, it, g0, g1, (T *)K, (T *)k, (const T *)mu, sa);
+            };
+            using std::integral_constant;
+            const bool big = h->env_fused_minb > 0 ? h->env_fused_minb > 1 : h->p.B > 32768;
+            if (h->env_fused_np == 3) go(integral_constant<int, 3>{}, integral_constant<int, 3>{}, integral_constant<int, 1>{});
+            else if (big) go(integral_constant<int, 2>{}, integral_constant<int, 4>{}, integral_constant<int, 5>{});
+            else go(integral_constant<int, 2>{}, integral_constant<int, 4>{}, integral_constant<int, 1>{});
             ILQR_CHECK_LAUNCH(h);
             return ILQR_OK;
         } else {
@@ -623,6 +631,25 @@ static void prof_collect(Handle *h)
     h->prof_kind->clear();
 }
 
+// DFMA throughput probe for the FP64 roofline of bench.py: 8 independent chains per thread, operands in the
+// two-register + uniform form that issues at the pipe's full rate (scripts/micro/fp64_operands.cu)
+__global__ void __launch_bounds__(128) fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 12345.678) out[0] = s;          // never true: keeps the chains alive without a store per thread
+}
+
 }  // namespace ilqr
 
 using namespace ilqr;
@@ -698,6 +725,7 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
         h->env_check_every = (e = getenv("ILQR_CHECK_EVERY")) && atoi(e) > 0 ? atoi(e) : 8;
         h->env_fused = (e = getenv("ILQR_FUSED")) ? (atoi(e) != 0) : -1;
         h->env_fused_np = (e = getenv("ILQR_FUSED_NP")) && atoi(e) == 3 ? 3 : 2;
+        h->env_fused_minb = (e = getenv("ILQR_FUSED_MINB")) ? atoi(e) : 0;
     }
     h->env_sparse_thresh = (e = getenv("ILQR_SPARSE_THRESH")) ? atol(e) : -1;
     h->env_sparse_all = (e = getenv("ILQR_SPARSE_ALL")) ? atol(e) : -1;
@@ -896,9 +924,9 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     }
     const int B = p.B, bsB = 128;
     int rc;
-    // fused K1+K2 (ilqr_kernels_fused.cuh): thread-per-trajectory consumers, i.e. the large-batch regime where the
-    // separate kernels stream A_t, B_t through HBM; small batches keep the latency-optimised four-lane scan
-    const bool fused = fused_available(h) && (h->env_fused == 1 || B > 32768);
+    // fused K1+K2 (ilqr_kernels_fused.cuh) wherever the model has it: at B=131072 A_t, B_t no longer stream through HBM
+    // (7.26 -> 5.4 ms per iteration), at B=4096 the linearization hides behind the scan (0.328 -> 0.272 ms)
+    const bool fused = fused_available(h);
     // two-wave line search (see select_kernel): n1 eager step sizes, n2 deferred ones
     const int n1 = h->n_first, n2 = h->n_alpha_eff - h->n_first;
     const size_t wbytes = p.dtype == ILQR_F64 ? 8 : 4;
@@ -1092,6 +1120,35 @@ int ilqr_get_kernel_times(ilqr_handle_t hh, double *ms, int64_t *launches)
     Handle *h = (Handle *)hh;
     if (!h || !ms || !launches) return ILQR_E_INVALID;
     for (int i = 0; i < ILQR_N_KERNEL_CLASSES; ++i) { ms[i] = h->prof_ms[i]; launches[i] = h->prof_cnt[i]; }
+    return ILQR_OK;
+}
+
+int ilqr_fp64_peak(double *tflops, void *scratch, void *stream)
+{
+    if (!tflops || !scratch) return ILQR_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return ILQR_E_CUDA;
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return ILQR_E_CUDA;
+    const int blocks = sms * 8, threads = 128, iters = 4096;          // 8 warps per SM sub-partition
+    fp64_peak_kernel<<<blocks, threads, 0, st>>>((double *)scratch, 64, 1.0000001, 1e-9);       // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, st);
+        fp64_peak_kernel<<<blocks, threads, 0, st>>>((double *)scratch, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return ILQR_E_CUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
     return ILQR_OK;
 }
 

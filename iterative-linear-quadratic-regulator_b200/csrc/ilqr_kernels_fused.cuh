@@ -42,11 +42,11 @@ ILQR_DEV void mbar_wait(unsigned long long *bar, unsigned parity)
 //   producer:  x_t,u_t from the accepted candidate slab (or the nominal; cp.async, one step ahead) -> commit into X,U ->
 //              wait empty[s] -> step_jac -> ring -> arrive full[s]
 //   consumer:  wait full[s] -> ring -> registers -> arrive empty[s] -> riccati_step -> coalesced K_t, k_t stores
-#ifndef ILQR_FUSED_MINBLOCKS
-#define ILQR_FUSED_MINBLOCKS 1
-#endif
-template <class Sys, class Cost, int INTEG, typename T, int NP, int S>
-__global__ void __launch_bounds__(32 * (NP + 1), ILQR_FUSED_MINBLOCKS)
+// MINB = resident blocks per SM the register allocation is capped for: 1 (no cap: small batches, one block per SM or
+// fewer, latency bound) or 5 (large batches: 15 warps per SM at 128 registers keep the FP64 pipe busier than 12 at 164;
+// measured 5.37 vs 5.50 vs 6.16 ms per pass at B=131072 for caps of 5 / 4 / none).
+template <class Sys, class Cost, int INTEG, typename T, int NP, int S, int MINB>
+__global__ void __launch_bounds__(32 * (NP + 1), MINB)
 fused_backward_kernel(const __grid_constant__ Sys sys, const __grid_constant__ Cost qc, int N, int B, const T *__restrict__ phi,
                       T *__restrict__ X, T *__restrict__ U, const T *__restrict__ Xc, const T *__restrict__ Uc,
                       const int *__restrict__ winner, const int *__restrict__ wslot, const int *__restrict__ active,

@@ -120,11 +120,15 @@ __global__ void __launch_bounds__(128, Sys::N <= 4 ? 4 : 1) commit_linearize_ker
         }
         return;
     }
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = gid < (size_t)(N + 1) * B;
-    commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, valid, valid ? (int)(gid / B) : 0, valid ? (int)(gid % B) : 0, phi,
-                                          X, U, A, Bd, Xc, Uc, winner, wslot, active, iters, it, do_linearize, pos,
-                                          ab_blocked);
+    // one item per thread; a grid smaller than the item count (sparse_only launches) strides over them, warps staying whole
+    const size_t total = (size_t)(N + 1) * B, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
+        const size_t gid = base + (threadIdx.x & 31u);
+        const bool valid = gid < total;
+        commit_linearize_point<Sys, INTEG, T>(sys, dt, N, B, valid, valid ? (int)(gid / B) : 0, valid ? (int)(gid % B) : 0, phi,
+                                              X, U, A, Bd, Xc, Uc, winner, wslot, active, iters, it, do_linearize, pos,
+                                              ab_blocked);
+    }
 }
 
 // materialised cost expansion (system_base.py:212-219); one thread per (t,b), t in [0,N]
