@@ -36,8 +36,13 @@ UNIT = "traj-iter/s"
 N_H, T_H, DT = 500, 5.0, 0.01
 ITERS = 10
 N_ALPHA = 10
-# algorithmic bytes per trajectory-timestep, FP64 (DESIGN.md "Roofline accounting")
-BYTES = {"linearize": 240, "backward": 240, "rollout": 120}
+# algorithmic bytes per trajectory-timestep, FP64.  The fused K1+K2 kernel reads
+# x_t,u_t from the accepted candidate (40 B), commits them into the nominal (40 B) and writes K_t,k_t (40 B).
+BYTES = {"linearize": 240, "backward": 240, "rollout": 120, "fused_backward": 120}
+# FP64 flop per trajectory-timestep (rollout: per step size), DFMA = 2, DMUL/DADD = 1, counted from the SASS of the
+# f64 / rk4 / UA-double-pendulum kernels by scripts/sass_flops.py: step_jac 485+150+59, riccati_step 246+10+26,
+# rollout step 229+61+24 instructions
+FLOPS = {"linearize": 1179, "backward": 528, "rollout": 543}
 
 
 def cfg2_x0(count, seed=0):
@@ -136,38 +141,139 @@ def workload_config(args, world):
                          "no explicit flush"}
 
 
-def large_batch_line(torch, iLQR, sysm, BL, steps=3, warmup=2):
-    """The bench step at BL trajectories on this GPU (x0 from the same generator): traj-iter/s and per-kernel
-    times per iLQR iteration.  At this size the backward pass streams its linearization at HBM speed."""
-    x0 = torch.as_tensor(cfg2_x0(BL, seed=1)).cuda()
-    U0 = torch.zeros((1, N_H), dtype=torch.float64, device="cuda")
-    sol = iLQR(sysm, T_H, x0, U0, tol=0.0, maxiter=ITERS, verbose=False, n_alpha=N_ALPHA)
+def shard_x0(count, rank, world, seed):
+    """rank's contiguous shard of a global batch of count*world seeded initial states"""
+    return np.ascontiguousarray(cfg2_x0(count * world, seed=seed)[rank * count:(rank + 1) * count])
 
-    def step():
+
+def evaluated_rollouts(idx, iters, waves, n_first, n_alpha):
+    """(step size, trajectory) rollouts the line-search schedule had to evaluate in the traced solve: idx (B, maxiter) =
+    accepted try index per iteration (-1 none).  Lazy schedule: every wave up to the one holding the accepted index;
+    eager: the first wave, plus the deferred step sizes where none of the first was accepted (speculative extra
+    rollouts are not counted)."""
+    total = 0
+    col = np.arange(idx.shape[1])[None, :]
+    ran = col < iters[:, None]
+    w = np.where(idx < 0, n_alpha - 1, idx)
+    if waves:
+        hi = np.cumsum(waves)
+        hi[-1] = max(hi[-1], n_alpha)
+        upto = hi[np.searchsorted(hi, w + 1)]
+    else:
+        upto = np.where(w < n_first, n_first, n_alpha)
+    total = int(upto[ran].sum())
+    return total
+
+
+def kernel_report(sol, torch, B, steps, peak_hbm, peak_fp64, fused):
+    """Per-kernel times (CUDA events chained between the launches of ilqr_solve, on its stream) of `steps` fresh solves,
+    and the rooflines: FP64 flop/s against the measured DFMA peak for the pipe-bound kernels, algorithmic bytes/s
+    against the measured HBM peak for every kernel."""
+    sol.set_profiling(True)
+    sol.enable_trace()
+    rollouts, units = 0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
         sol.reset_state()
         sol._U.zero_()
-        return sol.solve_device(sync=True)
-    for _ in range(warmup):
-        step()
-    sol.set_profiling(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    units = sum(step() for _ in range(steps))
+        units += sol.solve_device(sync=True)
+        idx, _ = sol.trace_arrays()
+        rollouts += evaluated_rollouts(idx, sol._iters.cpu().numpy(), sol.linesearch_waves(), sol.first_wave(), N_ALPHA)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     kt = sol.kernel_times()
-    nit = max(1, kt["linearize"][1])
+    sol.set_profiling(False)
+    nit = max(1, kt["backward"][1] if fused else kt["linearize"][1])         # iLQR iterations profiled
+    per_it_rollouts = rollouts / nit
     kern = {}
     for name in ("linearize", "backward", "rollout"):
-        avg = kt[name][0] / nit
-        alg = BYTES[name] * N_H * BL + (8 * N_ALPHA * BL if name == "rollout" else 0)
-        kern[name] = {"ms_per_iteration": avg, "achieved_GBps": alg / avg / 1e6}
-    return {"batch": BL, "value": units / (ms * 1e-3), "unit": UNIT, "steps": steps, "ms_per_step": ms / steps,
-            "line_search": "lazy waves of 2,2,2,4 step sizes over compacted lists", "kernels": kern,
-            "roofline_backward": {"bound": "hbm", "kernel": "backward", "unit": "GB/s",
-                                  "achieved": kern["backward"]["achieved_GBps"]}}
+        tot, cnt = kt[name]
+        if fused and name == "linearize":
+            continue
+        avg = tot / nit
+        if name == "rollout":
+            flop = FLOPS["rollout"] * N_H * per_it_rollouts
+            alg = BYTES["rollout"] * N_H * B + 8 * N_ALPHA * B
+        elif name == "backward" and fused:
+            flop = (FLOPS["linearize"] + FLOPS["backward"]) * N_H * B
+            alg = BYTES["fused_backward"] * N_H * B
+        else:
+            flop = FLOPS[name] * N_H * B
+            alg = BYTES[name] * N_H * B
+        kern[name] = {"ms_per_iteration": avg, "launches": cnt, "share_of_step": tot / ms, "algorithmic_bytes": alg,
+                      "achieved_GBps": alg / avg / 1e6, "hbm_frac": alg / avg / 1e6 / peak_hbm,
+                      "algorithmic_flop": flop, "achieved_TFLOPs": flop / avg / 1e9,
+                      "fp64_frac": flop / avg / 1e9 / peak_fp64 if peak_fp64 else None}
+    kern["fused_linearize_backward"] = bool(fused)
+    kern["rollouts_evaluated_per_iteration"] = per_it_rollouts
+    kern["init_rollout_ms"] = kt["init_rollout"][0] / max(1, kt["init_rollout"][1])
+    kern["other_ms_per_iteration"] = kt["other"][0] / nit
+    return kern, units / (ms * 1e-3)
+
+
+def make_solver(torch, iLQR, sysm, x0, fused=None):
+    """device-resident solver on the bench workload; fused=False builds it on the two-kernel K1/K2 path"""
+    old = os.environ.get("ILQR_FUSED")
+    if fused is False:
+        os.environ["ILQR_FUSED"] = "0"
+    try:
+        U0 = torch.zeros((1, N_H), dtype=torch.float64, device="cuda")
+        return iLQR(sysm, T_H, torch.as_tensor(x0).cuda(), U0, tol=0.0, maxiter=ITERS, verbose=False, n_alpha=N_ALPHA)
+    finally:
+        if fused is False:
+            if old is None:
+                os.environ.pop("ILQR_FUSED", None)
+            else:
+                os.environ["ILQR_FUSED"] = old
+
+
+def timed_steps(torch, dist, sol, steps, warmup, world, barrier):
+    """`steps` fresh solves, device resident, nothing host-synchronous inside the loop: the solve is enqueued with
+    sync=False, the iteration counts accumulate on the device, and (N > 1) the per-shard cost/status all-gather -- the
+    path's only exchange -- is issued asynchronously so that it runs under the next step's first kernels."""
+    B = sol.B
+    units_dev = torch.zeros((), dtype=torch.int64, device="cuda")
+    bufs = None
+    if world > 1:
+        bufs = [(torch.empty((2, B), dtype=torch.float64, device="cuda"),
+                 torch.empty((world, 2, B), dtype=torch.float64, device="cuda"), [None]) for _ in range(2)]
+
+    def step(i):
+        sol.reset_state()
+        sol._U.zero_()
+        sol.solve_device(sync=False)
+        units_dev.add_(sol._iters.sum())
+        if world > 1:
+            pack, gathered, work = bufs[i & 1]
+            if work[0] is not None:
+                work[0].wait()                       # the all-gather that last used this pair (two steps ago)
+            pack[0].copy_(sol._cost)
+            pack[1].copy_(sol._status)
+            work[0] = dist.all_gather_into_tensor(gathered, pack, async_op=True)
+
+    for i in range(warmup):
+        step(i)
+    if world > 1:
+        for _, _, work in bufs:
+            if work[0] is not None:
+                work[0].wait()
+    units_dev.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for i in range(steps):
+        step(i)
+    if world > 1:
+        for _, _, work in bufs:
+            if work[0] is not None:
+                work[0].wait()
+    e1.record()
+    barrier()
+    t1 = time.time()
+    return e0.elapsed_time(e1), int(units_dev.item()), t0, t1
 
 
 def main():
@@ -179,11 +285,10 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="trajectories per GPU")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="trajectories per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--skip-e2e", action="store_true",
-                    help="secondary runs only (e.g. --batch 131072 on 8 GPUs = config 5): skip the host-in/host-out arm")
+    ap.add_argument("--skip-e2e", action="store_true", help="skip the host-in/host-out arm")
     ap.add_argument("--large-batch", type=int, default=131072,
-                    help="N=1 only: also time a few steps at this batch (config 5's per-GPU shard at 8 GPUs), where "
-                         "the passes are throughput bound; reported under 'large_batch'.  0 disables.")
+                    help="also time a few steps at this batch PER GPU (config 5's shard: 8 x 131072 = 1M trajectories), "
+                         "where the passes are throughput bound; reported under 'large_batch'.  0 disables.")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,110 +308,28 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from class_files.iLQR_class import iLQR
     from class_files.systems.UA_double_pendulum_sys import MyUADoublePendulum
-
-    sysm = MyUADoublePendulum(dt=DT, x_target=np.array(UA["x_target"]), Q=np.diag(UA["Q"]), R=np.diag(UA["R"]),
-                              Q_f=np.diag(UA["Q_f"]), integrator="rk4", **UA["phys"])
-    B = args.batch
-    x0_all = cfg2_x0(B * world)
-    x0_host = np.ascontiguousarray(x0_all[rank * B:(rank + 1) * B])        # this rank's contiguous shard
-    U_host = np.zeros((1, N_H))
-    # ---- device-resident arm: torch tensors in, nothing crosses PCIe in the timed region --------------
-    x0_dev = torch.as_tensor(x0_host).cuda()
-    U_dev = torch.zeros((1, N_H), dtype=torch.float64, device="cuda")
-    sol = iLQR(sysm, T_H, x0_dev, U_dev, tol=0.0, maxiter=ITERS, verbose=False, n_alpha=N_ALPHA)
-    # the path's only exchange: per-shard cost and exit status, packed into ONE NCCL all-gather per step
-    pack = torch.empty((2, B), dtype=torch.float64, device="cuda") if world > 1 else None
-    gathered = torch.empty((world, 2, B), dtype=torch.float64, device="cuda") if world > 1 else None
-
-    def step_device():
-        sol.reset_state()
-        sol._U.zero_()
-        units = sol.solve_device(sync=True)
-        if world > 1:
-            pack[0].copy_(sol._cost)
-            pack[1].copy_(sol._status)
-            dist.all_gather_into_tensor(gathered, pack)
-        return units
+    from class_files import _cabi
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    l0 = sol.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sysm = MyUADoublePendulum(dt=DT, x_target=np.array(UA["x_target"]), Q=np.diag(UA["Q"]), R=np.diag(UA["R"]),
+                              Q_f=np.diag(UA["Q_f"]), integrator="rk4", **UA["phys"])
+    B = args.batch
+    x0_host = shard_x0(B, rank, world, seed=0)
+    # ---- device-resident arm: torch tensors in, nothing crosses PCIe in the timed region --------------
+    sol = make_solver(torch, iLQR, sysm, x0_host)
+    fused = os.environ.get("ILQR_FUSED", "") != "0"
+    l0 = None
     sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    t0 = time.time()
-    e0.record()
-    units = 0
-    for _ in range(args.steps):
-        units += step_device()
-    e1.record()
-    barrier()
-    t1 = time.time()
-    ms = e0.elapsed_time(e1)
+    # (launch count of the timed steps only: read before and after)
+    timed_steps(torch, dist, sol, 0, args.warmup, world, barrier)
+    l0 = sol.launches()
+    ms, units, t0, t1 = timed_steps(torch, dist, sol, args.steps, 0, world, barrier)
     launches = sol.launches() - l0
     clocks = sampler.stop(t0, t1) if sampler else None
-    # per-kernel breakdown: the same steps again with CUDA events chained between the launches (kept out of
-    # the timed region above: the extra event records cost ~3 % at this batch)
-    sol.set_profiling(True)
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pe0.record()
-    for _ in range(max(1, min(args.steps, 10))):
-        step_device()
-    pe1.record()
-    torch.cuda.synchronize()
-    ms_prof = pe0.elapsed_time(pe1)
-    ktimes = sol.kernel_times()
-    sol.set_profiling(False)
-
-    # ---- end-to-end arm: host numpy in, host numpy out through the public API -----------------------
-    te, units_e, h2d, d2h = float("nan"), 0, 0, 0
-    sol_h = None
-    if not args.skip_e2e:
-        sol_h = iLQR(sysm, T_H, x0_host, U_host, tol=0.0, maxiter=ITERS, verbose=False, n_alpha=N_ALPHA)
-
-        def step_e2e():
-            sol_h.x_0 = x0_host                   # H2D
-            sol_h.U = U_host                      # H2D
-            sol_h.reset_state()
-            X, U, cost = sol_h.optimize_trajectory()   # D2H of X, U, cost
-            return sol_h.total_iterations, X, U, cost
-
-        for _ in range(max(3, args.warmup)):
-            # keep the results alive across steps exactly as the timed loop does, so that the pinned staging
-            # buffers of the steady state (two per output) exist before the clock starts
-            u, X, U, cost = step_e2e()
-        barrier()
-        te0 = time.perf_counter()
-        for _ in range(args.steps):
-            u, X, U, cost = step_e2e()
-            units_e += u
-        barrier()
-        te = time.perf_counter() - te0
-        h2d = x0_host.nbytes + U_host.nbytes
-        d2h = X.nbytes + U.nbytes + cost.nbytes
-
-    # ---- N=1 only: the same solve at config 5's per-GPU shard size (HBM/FP64-throughput-bound regime) ------
-    large = None
-    if world == 1 and args.large_batch > 0:
-        del sol_h
-        torch.cuda.empty_cache()
-        large = large_batch_line(torch, iLQR, sysm, args.large_batch)
-
-    if world > 1:
-        t = torch.tensor([ms, te, float(units), float(units_e)], dtype=torch.float64, device="cuda")
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, te = float(tmax[0]), float(tmax[1])
-        units, units_e = int(tsum[2]), int(tsum[3])
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
     peaks = {}
     try:
@@ -314,39 +337,160 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "6650 GB/s (fallback)"
+    # FP64 FMA peak of THIS device, measured now by the library's DFMA probe (ilqr_fp64_peak)
+    tf = __import__("ctypes").c_double(0.0)
+    scratch = torch.zeros(8, dtype=torch.float64, device="cuda")
+    lib = _cabi.load()
+    _cabi.check(lib.ilqr_fp64_peak(__import__("ctypes").byref(tf), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    peak_fp64 = float(tf.value)
 
-    def kinfo(name):
-        tot, cnt = ktimes[name]
-        if cnt == 0:
-            return None
-        # per iLQR iteration (the lazy line-search schedule launches the rollout kernel once per wave)
-        avg = tot / max(1, ktimes["linearize"][1])
-        alg = BYTES[name] * N_H * B + (8 * N_ALPHA * B if name == "rollout" else 0)
-        return {"avg_ms": avg, "launches": cnt, "share_of_step": tot / ms_prof, "algorithmic_bytes": alg,
-                "achieved_GBps": alg / avg / 1e6}
-    kern = {k: kinfo(k) for k in ("linearize", "backward", "rollout")}
-    kern["init_rollout_ms"] = ktimes["init_rollout"][0] / max(1, ktimes["init_rollout"][1])
-    kern["other_ms_per_iteration"] = ktimes["other"][0] / max(1, ktimes["other"][1])
+    # per-kernel breakdown: a few more steps with CUDA events chained between the launches (kept out of the timed
+    # region above: the event records cost ~3 % at this batch)
+    kern, _ = kernel_report(sol, torch, B, max(1, min(args.steps, 10)), peak, peak_fp64, fused)
+
+    # ---- end-to-end arm: pinned host arrays in, host arrays out through the public API ---------------------
+    # optimize_trajectory_async() keeps two result slots: while the 82 MB of X, U of solve i travel to the host on a
+    # copy stream, solve i+1 (its own H2D included) already runs.  Every step's H2D and D2H is inside the timed region;
+    # `e2e_blocking` is the same loop with optimize_trajectory(), i.e. one solve at a time.
+    te = tb = float("nan")
+    units_e = units_b = h2d = d2h = 0
+    sol_h = None
+    if not args.skip_e2e:
+        x0_pin = torch.as_tensor(x0_host).pin_memory()
+        U_pin = torch.zeros((1, N_H), dtype=torch.float64).pin_memory()
+        sol_h = iLQR(sysm, T_H, x0_pin, U_pin, tol=0.0, maxiter=ITERS, verbose=False, n_alpha=N_ALPHA)
+
+        def submit():
+            sol_h.x_0 = x0_pin                    # H2D (pinned, asynchronous)
+            sol_h.U = U_pin                       # H2D
+            sol_h.reset_state()
+            return sol_h.optimize_trajectory_async()
+
+        def pipelined(n):
+            got, pend = 0, None
+            for _ in range(n):
+                nxt = submit()
+                if pend is not None:
+                    X, U, cost = pend.result()    # D2H of X, U, cost of the previous solve has landed
+                    got += pend.total_iterations
+                pend = nxt
+            X, U, cost = pend.result()
+            return got + pend.total_iterations, X, U, cost
+
+        pipelined(max(3, args.warmup))
+        barrier()
+        te0 = time.perf_counter()
+        units_e, X, U, cost = pipelined(args.steps)
+        barrier()
+        te = time.perf_counter() - te0
+        h2d = x0_pin.numel() * 8 + U_pin.numel() * 8
+        d2h = X.nbytes + U.nbytes + cost.nbytes + 8
+
+        def blocking():
+            sol_h.x_0 = x0_pin
+            sol_h.U = U_pin
+            sol_h.reset_state()
+            X, U, cost = sol_h.optimize_trajectory()
+            return sol_h.total_iterations
+
+        for _ in range(3):
+            blocking()
+        barrier()
+        tb0 = time.perf_counter()
+        for _ in range(max(3, args.steps // 2)):
+            units_b += blocking()
+        barrier()
+        tb = time.perf_counter() - tb0
+
+    # ---- the same solve at config 5's per-GPU shard size (HBM/FP64-throughput-bound regime) -----------------
+    large = None
+    if args.large_batch > 0:
+        del sol_h, sol
+        torch.cuda.empty_cache()
+        BL = args.large_batch
+        sol_l = make_solver(torch, iLQR, sysm, shard_x0(BL, rank, world, seed=1))
+        lms, lunits, _, _ = timed_steps(torch, dist, sol_l, 3, 2, world, barrier)
+        lkern, _ = kernel_report(sol_l, torch, BL, 2, peak, peak_fp64, fused)
+        large = {"batch_per_gpu": BL, "global_batch": BL * world, "steps": 3, "ms_per_step": lms / 3, "units": lunits,
+                 "unit": UNIT, "line_search": "lazy waves of 2,2,2,4 step sizes over compacted lists", "kernels": lkern}
+        # north_star's evidence for the backward pass is its HBM fraction: with K1 fused into it the pass no longer
+        # streams A_t, B_t through HBM at all, so the two-kernel scan is timed once more on the same data (N=1 only)
+        if world == 1 and fused:
+            del sol_l
+            torch.cuda.empty_cache()
+            sol_u = make_solver(torch, iLQR, sysm, shard_x0(BL, rank, world, seed=1), fused=False)
+            timed_steps(torch, dist, sol_u, 1, 1, world, barrier)
+            ukern, _ = kernel_report(sol_u, torch, BL, 2, peak, peak_fp64, False)
+            large["two_kernel_path"] = {k: ukern[k] for k in ("linearize", "backward")}
+            del sol_u
+
+    if world > 1:
+        vals = [ms, te, tb, float(units), float(units_e), float(units_b)]
+        if large:
+            vals += [large["ms_per_step"], float(large["units"])]
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, te, tb = float(tmax[0]), float(tmax[1]), float(tmax[2])
+        units, units_e, units_b = int(tsum[3]), int(tsum[4]), int(tsum[5])
+        if large:
+            large["ms_per_step"], large["units"] = float(tmax[6]), int(tsum[7])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    if large:
+        large["value"] = large.pop("units") / (large["ms_per_step"] * 3 * 1e-3)
+        large["workload"] = (f"cfg5 shard: {large['batch_per_gpu']} trajectories per GPU x {world} GPU(s) = "
+                             f"{large['global_batch']} (BASELINE configs[4] is 1M over 8), N={N_H}, {ITERS} iterations per step")
+
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
     # command (profiles/traffic.json, written by scripts/ncu_summary.py --traffic); null when absent
-    traffic, traffic_all = {}, {}
+    traffic = {}
     try:
-        traffic_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = traffic_all.get(f"B{B}", {})
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    dom = max(("linearize", "backward", "rollout"), key=lambda k: ktimes[k][0])
-    roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
-            "frac": kern[dom]["achieved_GBps"] / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
-            "fp64_pipe_active_pct": traffic.get("fp64_pipe_active_pct", {}).get(dom),
-            "note": "rollout is FP64-pipe/latency bound at this batch, not HBM bound (DESIGN.md section 4; "
-                    "fp64_pipe_active_pct = ncu sm__pipe_fp64_cycles_active of the committed capture, averaged over the "
-                    "kernel class incl. the lone-warp alpha=0 rollout; 100 % is out of reach for this instruction mix: "
-                    "three-register DFMAs issue at 3 cycles); "
-                    "see roofline_backward for the HBM-bound kernel north_star names"}
-    roof_b = {"bound": "hbm", "kernel": "backward", "achieved": kern["backward"]["achieved_GBps"], "peak": peak,
-              "unit": "GB/s", "frac": kern["backward"]["achieved_GBps"] / peak, "traffic": traffic.get("backward")}
+    tB = traffic.get(f"B{B}", {})
+    dom = max((k for k in ("linearize", "backward", "rollout") if k in kern), key=lambda k: kern[k]["share_of_step"])
+    kd = kern[dom]
+    pipe_bound = dom == "rollout" or fused
+    roof = {"kernel": dom, "peak_source": peak_src, "traffic": tB.get(dom),
+            "hbm": {"achieved": kd["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": kd["hbm_frac"]},
+            "fp64": {"achieved": kd["achieved_TFLOPs"], "peak": peak_fp64, "unit": "TFLOP/s", "frac": kd["fp64_frac"],
+                     "peak_source": "ilqr_fp64_peak(): DFMA chains on every SM, measured in this run",
+                     "flop_per_rollout_step": FLOPS["rollout"]},
+            "pipe_active_pct_from_profiles": tB.get("fp64_pipe_active_pct", {}).get(dom),
+            "note": "the rollout is bound by the FP64 pipe, not by HBM (DESIGN.md section 4): frac = FP64 flop/s (DFMA = 2, "
+                    "counted from the kernel's SASS, x rollouts the schedule evaluated) / measured DFMA peak; the HBM figures "
+                    "are kept beside it; pipe_active_pct_from_profiles is ncu's number in the committed capture, not "
+                    "measured in this run"}
+    if pipe_bound:
+        roof.update(bound="fp64", achieved=kd["achieved_TFLOPs"], peak=peak_fp64, unit="TFLOP/s", frac=kd["fp64_frac"])
+    else:
+        roof.update(bound="hbm", achieved=kd["achieved_GBps"], peak=peak, unit="GB/s", frac=kd["hbm_frac"])
+    kb = kern["backward"]
+    roof_b = {"kernel": "backward" + (" (fused with linearization)" if fused else ""), "bound": "fp64" if fused else "hbm",
+              "achieved": kb["achieved_TFLOPs"] if fused else kb["achieved_GBps"],
+              "peak": peak_fp64 if fused else peak, "unit": "TFLOP/s" if fused else "GB/s",
+              "frac": kb["fp64_frac"] if fused else kb["hbm_frac"], "traffic": tB.get("backward"),
+              "hbm": {"achieved": kb["achieved_GBps"], "peak": peak, "frac": kb["hbm_frac"],
+                      "algorithmic_bytes_per_trajectory_step": BYTES["fused_backward" if fused else "backward"]}}
+    if large:
+        lk = large["kernels"]["backward"]
+        large["roofline_backward"] = {"bound": "fp64" if fused else "hbm", "unit": "TFLOP/s" if fused else "GB/s",
+                                      "achieved": lk["achieved_TFLOPs"] if fused else lk["achieved_GBps"],
+                                      "peak": peak_fp64 if fused else peak,
+                                      "frac": lk["fp64_frac"] if fused else lk["hbm_frac"],
+                                      "traffic": traffic.get(f"B{large['batch_per_gpu']}", {}).get("backward")}
+        if "two_kernel_path" in large:
+            u = large["two_kernel_path"]["backward"]
+            large["roofline_backward"]["two_kernel_scan_hbm"] = {
+                "bound": "hbm", "achieved": u["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": u["hbm_frac"],
+                "algorithmic_bytes": u["algorithmic_bytes"],
+                "note": "backward_kernel alone on K1's materialised A_t, B_t (ILQR_FUSED=0): the >= 60 % of HBM "
+                        "roofline north_star asks of the backward pass"}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -364,19 +508,20 @@ def main():
                "sample": f"first {ns} trajectories of the batch x {ITERS} iterations, {cdt:.1f} s wall on {threads} threads"}
 
     value = units / (ms * 1e-3)
+    e2e = None
+    if not args.skip_e2e:
+        e2e = {"value": units_e / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": te / args.steps * 1e3, "pipeline_depth": 2,
+               "api": "iLQR.optimize_trajectory_async(): pinned host x_0, U in; host X, U, cost out; the D2H of solve i "
+                      "overlaps solve i+1 on a copy stream",
+               "blocking": {"value": units_b / tb, "unit": UNIT, "api": "iLQR.optimize_trajectory(), one solve at a time",
+                            "ms_per_step": tb / max(3, args.steps // 2) * 1e3}}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-           "traj_iterations_per_step": units / args.steps,
-           "e2e": None if args.skip_e2e else {"value": units_e / te, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                                              "d2h_bytes_per_step": int(d2h), "ms_per_step": te / args.steps * 1e3},
+           "traj_iterations_per_step": units / args.steps, "e2e": e2e,
            "gpu_launches": int(launches), "roofline": roof, "roofline_backward": roof_b, "kernels": kern,
            "large_batch": large, "cpu_baseline": cpu, "clocks": clocks}
-    if large:
-        large["roofline_backward"]["peak"] = peak
-        large["roofline_backward"]["frac"] = large["roofline_backward"]["achieved"] / peak
-        large["roofline_backward"]["algorithmic_bytes"] = BYTES["backward"] * N_H * large["batch"]
-        large["roofline_backward"]["traffic"] = traffic_all.get(f"B{large['batch']}", {}).get("backward")
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -151,7 +151,7 @@ int ilqr_solve(ilqr_handle_t h, const void *phi, const void *x0, void *X, void *
  * 2,2,2,rest.  The accepted step size of every trajectory is the same under every schedule. */
 int ilqr_set_linesearch_waves(ilqr_handle_t h, int n_waves, const int32_t *sizes);
 /* The schedule in force: returns the number of lazy waves (0 = eager) and, when sizes != NULL, writes the tries per
- * wave into sizes[ILQR_MAX_WAVES]. */
+ * wave into sizes[ILQR_MAX_WAVES] (eager: sizes[0] = tries of the first, dense wave). */
 int ilqr_get_linesearch_waves(ilqr_handle_t h, int32_t *sizes);
 
 /* Optional device buffer mu[B] (element type of the handle) for the regularisation state of ilqr_solve:

@@ -364,6 +364,20 @@ class iLQR:
         arr = (C.c_int32 * max(len(sizes), 1))(*sizes)
         h.check(h.lib.ilqr_set_linesearch_waves(h.h, len(sizes), arr))
 
+    def linesearch_waves(self):
+        """tries per lazily evaluated wave, () for the eager schedule (ilqr_get_linesearch_waves)"""
+        h = self._handle
+        arr = (C.c_int32 * 8)()
+        n = h.lib.ilqr_get_linesearch_waves(h.h, arr)
+        return tuple(int(arr[i]) for i in range(n))
+
+    def first_wave(self):
+        """eager schedule: step sizes rolled out for every trajectory in the first wave"""
+        h = self._handle
+        arr = (C.c_int32 * 8)()
+        n = h.lib.ilqr_get_linesearch_waves(h.h, arr)
+        return int(arr[0]) if n == 0 else 0
+
     def set_profiling(self, enable=True):
         """chain CUDA events between the solve's kernels (see ilqr_set_profiling)"""
         h = self._handle

@@ -330,7 +330,7 @@ static int launch_backward_depth(Handle *h, const Cost &qc, const void *X, const
 
 static int launch_backward(Handle *h, const void *X, const void *U, const void *A, const void *Bd, void *K, void *k,
                            const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr,
-                           const SparseArgs *sparse = nullptr, int ab_blocked = 0, int sparse_only = 0)
+                           const SparseArgs *sparse = nullptr, int ab_blocked = 0)
 {
     SparseArgs sa;
     std::memset(&sa, 0, sizeof sa);
@@ -345,7 +345,7 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
             // ones, where it runs next to the thread-per-trajectory kernel and each returns at once when the
             // iteration is not its kind (SparseArgs::only)
             const bool lanes = h->env_lanes >= 0 ? h->env_lanes != 0 : h->p.B <= 32768;
-            const bool both = sparse_only || (!lanes && sa.cur != nullptr && h->env_lanes < 0);
+            const bool both = !lanes && sa.cur != nullptr && h->env_lanes < 0;
             if (lanes || both) {
                 constexpr int DEPTH = 8, SLOTS = 8, LP = 26;
                 const size_t smem = sizeof(T) * (size_t)(DEPTH * SLOTS * LP + SLOTS * 4 + SLOTS * 20);
@@ -356,11 +356,10 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
                     qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active,
                     gate, (const T *)mu, sl, ab_blocked);
                 ILQR_CHECK_LAUNCH(h);
-                if (!both || sparse_only) return ILQR_OK;
+                if (!both) return ILQR_OK;
                 sa.only = 1;
             }
         }
-        if (sparse_only) sa.only = 2;        // dense iterations belong to the fused kernel
         if constexpr (Sys::N > 4) {
             // n = 12, m = 4: a ring stage is 208 rows; two stages of one warp fit the 227 KB limit
             return launch_backward_depth<T, Sys::N, Sys::M, 2, 32>(h, qc, X, U, A, Bd, K, k, active, gate, mu, st, sa, ab_blocked);
@@ -982,18 +981,17 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
                 sa.n_alpha_all = h->n_alpha_eff;
             }
             if (fused) {
-                // dense iterations: ONE kernel commits, linearizes and scans; the sparse iterations of the lazy
-                // schedule keep K1 + the four-lane list kernel (each kernel returns at once when the iteration is not
-                // its kind, decided on the device from the same counter)
+                // ONE kernel commits, linearizes and scans; in the sparse iterations of the lazy schedule it walks the
+                // active list and K1, in its commit-only form, first commits what the previous iteration accepted
+                // (dense or sparse is decided on the device from the same counter in every kernel)
                 if (sparse_thresh > 0) {
+                    // commit only, sparse iterations only (finished trajectories are on no list the fused kernel walks)
                     if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, it > 0 ? wslot : nullptr, active,
-                                                      1, g, gprev, st, iters, it, &sa, h->ab_blocked, 1))) return rc;
+                                                      0, g, gprev, st, iters, it, &sa, h->ab_blocked, 1))) return rc;
                     prof_mark(h, ILQR_KC_LINEARIZE, st);
                 }
                 if ((rc = launch_fused(h, phi, X, U, Xc, Uc, winner, it > 0 ? wslot : nullptr, active, iters, it, g, gprev, K, k,
                                        rg.mu, st, &sa))) return rc;
-                if (sparse_thresh > 0 &&
-                    (rc = launch_backward(h, X, U, A, Bd, K, k, active, g, st, rg.mu, &sa, h->ab_blocked, 1))) return rc;
                 prof_mark(h, ILQR_KC_BACKWARD, st);
             } else {
             if ((rc = launch_commit_linearize(h, phi, X, U, A, Bd, Xc, Uc, winner, it > 0 ? wslot : nullptr, active,
@@ -1091,7 +1089,10 @@ int ilqr_get_linesearch_waves(ilqr_handle_t hh, int32_t *sizes)
 {
     Handle *h = (Handle *)hh;
     if (!h) return ILQR_E_INVALID;
-    if (!h->lazy) return 0;
+    if (!h->lazy) {
+        if (sizes) sizes[0] = h->n_first;      // eager: the first (dense) wave; the other tries follow where needed
+        return 0;
+    }
     if (sizes)
         for (int v = 0; v < h->n_waves; ++v) sizes[v] = h->wave_lo[v + 1] - h->wave_lo[v];
     return h->n_waves;

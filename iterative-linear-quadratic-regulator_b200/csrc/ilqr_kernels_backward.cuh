@@ -185,8 +185,6 @@ __global__ void __launch_bounds__(BS) backward_kernel(const __grid_constant__ Co
         if (sa.only == 1) return;                                        // ... which the four-lane kernel does better
         if ((unsigned int)b >= *sa.n_cur) return;
         b = sa.cur[b];                                                   // A_t, B_t stay at the list position (K1)
-    } else if (sa.only == 2) {
-        return;                                                          // dense iterations: another kernel's
     }
     if (b >= B) return;
     if (active && !active[b]) return;

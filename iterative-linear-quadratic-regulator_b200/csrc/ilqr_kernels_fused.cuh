@@ -35,7 +35,7 @@ ILQR_DEV void mbar_wait(unsigned long long *bar, unsigned parity)
                  : "memory");
 }
 
-// Thread-per-trajectory form (large batches, HBM/FP64-throughput regime).  One block = one group of 32 trajectories
+// Thread-per-trajectory form.  One block = one group of 32 trajectories
 // (lane = trajectory) = 1 consumer warp + NP producer warps.  Producer p owns the scan steps i = N-1-t with
 // i mod NP == p; ring stage i mod S (S a multiple of NP, so a producer always meets the same stages).  A lane only ever
 // reads what the same lane of a producer wrote, so a stage is [rows][32 lanes]: conflict-free in both directions.
@@ -60,12 +60,17 @@ fused_backward_kernel(const __grid_constant__ Sys sys, const __grid_constant__ C
     __shared__ __align__(16) T pre[NP][2][n + m][32];       // producers' input staging (cp.async)
     __shared__ __align__(8) unsigned long long full[S], empty[S];
     if (gate0 && *gate0 == 0u && *gate1 == 0u) return;       // nobody active now or in the previous iteration
-    if (sparse_now(sa)) return;                              // a sparse iteration belongs to K1 + the list kernels
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int b_raw = blockIdx.x * 32 + lane;
-    const bool valid = b_raw < B;
-    const int b = valid ? b_raw : B - 1;                     // lanes past the batch compute on a copy, never store
-    int w = (valid && winner) ? winner[b] : -1;
+    // Sparse iteration (SparseArgs; lazy schedule, few trajectories left): the groups walk the compacted active list.
+    // The pending commits of such an iteration -- which include trajectories that have just finished and are on no list
+    // any more -- were made by K1 in its commit-only form just before this launch.
+    const bool sparse = sparse_now(sa);
+    const int n_items = sparse ? (int)*sa.n_cur : B;
+    if (blockIdx.x * 32 >= n_items) return;
+    const int item = blockIdx.x * 32 + lane;
+    const bool valid = item < n_items;
+    const int b = sparse ? sa.cur[valid ? item : n_items - 1] : (valid ? item : B - 1);   // spare lanes: a copy, never stored
+    int w = (valid && winner && !sparse) ? winner[b] : -1;
     if (iters && iters[b] != it) w = -1;                     // nothing pending: committed earlier, or never ran
     const bool act = valid && (active ? active[b] != 0 : true);
     const unsigned full_mask = 0xffffffffu;
