@@ -301,3 +301,52 @@ def write_report(name, report):
         json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
     except OSError:
         pass
+
+
+def mpc_member_parity(O, p_opt, p_plant, x0, ticks, X_sim, iters, n_draws=4, deep_draws=24, tol=1e-9, members=None):
+    """Closed-loop MPC runs member by member against the oracle (orc_mpc): X_sim (B, n, ticks+1), iters (B, ticks) from
+    the GPU.  A member with the oracle's per-tick iteration counts must be within max(tol, SENS_FACTOR x its own drift
+    under 1e-14 noise / FMA contraction); a member whose counts differ must be one whose counts the oracle itself
+    changes under that noise.  Returns (report, failures)."""
+    x0 = np.asarray(x0, dtype=np.float64)
+    members = np.arange(x0.shape[0]) if members is None else np.asarray(members)
+    rng = np.random.default_rng(17)
+    failures, errs, sens, same_n, flipped, explained = [], [], [], 0, 0, 0
+
+    def drift(b, base, nd, seed_rng):
+        s, stable = 0.0, True
+        for d in range(nd + 1):
+            if d == nd:
+                with O.rounding_variant():
+                    r = O.mpc(p_opt, p_plant, x0[b], ticks)
+            else:
+                r = O.mpc(p_opt, p_plant, _perturb(seed_rng, x0[b], 1e-14), ticks)
+            if not np.array_equal(r["iters"], base["iters"]):
+                stable = False
+            s = max(s, float(np.max(np.abs(r["X_sim"] - base["X_sim"])) / np.max(np.abs(base["X_sim"]))))
+        return s, stable
+
+    for j, b in enumerate(members):
+        base = O.mpc(p_opt, p_plant, x0[b], ticks)
+        s, stable = drift(b, base, n_draws, rng)
+        e = float(np.max(np.abs(X_sim[j] - base["X_sim"])) / np.max(np.abs(base["X_sim"])))
+        if np.array_equal(base["iters"], iters[j]):
+            same_n += 1
+            errs.append(e)
+            sens.append(s)
+            if e > max(tol, SENS_FACTOR * s):
+                failures.append(dict(member=int(b), kind="X_sim", err=e, sens=s))
+        else:
+            flipped += 1
+            if stable:
+                _, stable = drift(b, base, deep_draws, np.random.default_rng(1000 + int(b)))
+            if stable:
+                failures.append(dict(member=int(b), kind="unexplained iteration-count difference",
+                                     got=np.asarray(iters[j]).tolist(), oracle=base["iters"].tolist()))
+            else:
+                explained += 1
+    errs = np.array(errs) if errs else np.zeros(1)
+    report = dict(members=int(len(members)), same_flow=same_n, flipped=flipped, flips_explained_by_oracle_noise=explained,
+                  worst_err=float(errs.max()), frac_at_tol=float((errs <= tol).mean()), tol=tol, sens_factor=SENS_FACTOR,
+                  max_sens=float(max(sens)) if sens else 0.0)
+    return report, failures
