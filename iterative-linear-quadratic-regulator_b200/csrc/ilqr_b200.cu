@@ -124,7 +124,7 @@ struct Handle {
     int env_rollout_bs;       // ILQR_ROLLOUT_BS: 0 [auto] or a block size
     int env_fused;            // ILQR_FUSED: -1 [auto: fused K1+K2 inside ilqr_solve where it is the faster form], 0 never,
                               // 1 wherever the model allows (also ilqr_backward_pass)
-    int env_fused_np;         // ILQR_FUSED_NP: producer warps per consumer warp, 2 [default] or 3
+    int env_fused_np;         // ILQR_FUSED_NP: producer warps per consumer warp, 2 [default], 3, or 1 (four-lane form only)
     int env_fused_minb;       // ILQR_FUSED_MINB: 0 [auto: by batch size], 1 = uncapped registers, 5 = capped for 5 blocks/SM
     int env_check_every;      // ILQR_CHECK_EVERY: iterations enqueued between host polls of the active count [8]
     long env_sparse_thresh;   // ILQR_SPARSE_THRESH / ILQR_SPARSE_ALL: -1 [auto] or the thresholds of SparseArgs
@@ -402,6 +402,24 @@ static int launch_fused(Handle *h, const void *phi, void *X, void *U, const void
         using Cost = decltype(qc);
         constexpr int I = decltype(integ)::value;
         if constexpr (fused_eligible<Sys, Cost>()) {
+            if constexpr (Sys::N == 4 && Sys::M == 1) {
+                // small batches: the four-lane scan as the consumer (ILQR_BACKWARD_LANES overrides, as for K2 alone)
+                const bool lanes = h->env_lanes >= 0 ? h->env_lanes != 0 : h->p.B <= 32768;
+                if (lanes) {
+                    // B=4096 is 512 blocks on 148 SMs: the block must fit four times per SM (register cap), or a
+                    // quarter of them waits for a second round
+                    if (h->env_fused_np == 1)
+                        fused_backward_lanes_kernel<Sys, I, T, 1, 3, 1><<<grid_for(h->p.B, 8), 64, 0, st>>>(
+                            sys, qc, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (const T *)Xc, (const T *)Uc, winner, wslot,
+                            active, iters, it, g0, g1, (T *)K, (T *)k, (const T *)mu, sa);
+                    else
+                        fused_backward_lanes_kernel<Sys, I, T, 2, 4, 4><<<grid_for(h->p.B, 8), 96, 0, st>>>(
+                            sys, qc, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (const T *)Xc, (const T *)Uc, winner, wslot,
+                            active, iters, it, g0, g1, (T *)K, (T *)k, (const T *)mu, sa);
+                    ILQR_CHECK_LAUNCH(h);
+                    return ILQR_OK;
+                }
+            }
             const int groups = (h->p.B + 31) / 32;
             auto go = [&](auto np, auto stages, auto minb) {
                 constexpr int NP = decltype(np)::value, S = decltype(stages)::value, MB = decltype(minb)::value;
@@ -723,7 +741,7 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
         h->env_rollout_bs = (e = getenv("ILQR_ROLLOUT_BS")) && atoi(e) >= 32 ? atoi(e) / 32 * 32 : 0;
         h->env_check_every = (e = getenv("ILQR_CHECK_EVERY")) && atoi(e) > 0 ? atoi(e) : 8;
         h->env_fused = (e = getenv("ILQR_FUSED")) ? (atoi(e) != 0) : -1;
-        h->env_fused_np = (e = getenv("ILQR_FUSED_NP")) && atoi(e) == 3 ? 3 : 2;
+        h->env_fused_np = (e = getenv("ILQR_FUSED_NP")) && atoi(e) >= 1 && atoi(e) <= 3 ? atoi(e) : 2;
         h->env_fused_minb = (e = getenv("ILQR_FUSED_MINB")) ? atoi(e) : 0;
     }
     h->env_sparse_thresh = (e = getenv("ILQR_SPARSE_THRESH")) ? atol(e) : -1;

@@ -423,13 +423,15 @@ def _solve_outputs(sol):
     return [np.array(a) for a in (X, U, cost, sol.K, sol.U_ff, sol.iterations, sol.status)]
 
 
-@pytest.mark.parametrize("kind,integ", [("ua", "rk4"), ("ua", "backward_euler"), ("double", "rk4"), ("pendulum", "midpoint")])
-def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, integ):
+@pytest.mark.parametrize("kind,integ,lanes", [("ua", "rk4", "0"), ("ua", "rk4", "1"), ("ua", "backward_euler", "1"),
+                                              ("double", "rk4", "0"), ("pendulum", "midpoint", "0")])
+def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, integ, lanes):
     """K1+K2 as one warp-specialised kernel (csrc/ilqr_kernels_fused.cuh: producers commit + linearize into a
-    shared-memory ring, the consumer scans) against the two-kernel path with the thread-per-trajectory scan: the same
-    operation sequence, so gains, trajectories, costs and control flow must agree BIT FOR BIT -- in a solve with
-    staggered convergence, regularisation retries and warm-started re-solves (commits of finished trajectories, inactive
-    lanes, a ragged last group), on the eager and the lazy schedule, and in backward_pass()."""
+    shared-memory ring, the consumer scans) against the two-kernel path with the same scan (lanes = 0: one thread per
+    trajectory, lanes = 1: four lanes per trajectory): the same operation sequence, so gains, trajectories, costs and
+    control flow must agree BIT FOR BIT -- in a solve with staggered convergence, regularisation retries and
+    warm-started re-solves (commits of finished trajectories, inactive lanes, a ragged last group), on the eager and the
+    lazy schedule, and in backward_pass()."""
     from class_files.iLQR_class import iLQR
     golden = {"ua": "solve_ua_rk4_T1_b0", "double": "solve_double_rk4_T1_b0", "pendulum": "solve_pend_rk4_T1"}[kind]
     s = system_from_golden(load_golden(golden), integrator=integ)
@@ -437,7 +439,7 @@ def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, in
     rng = np.random.default_rng(5)
     x0 = cfg2_x0(B, seed=5)[:, :s.n_x] if kind != "pendulum" else rng.uniform(-2, 2, (B, 2))
     out = {}
-    monkeypatch.setenv("ILQR_BACKWARD_LANES", "0")
+    monkeypatch.setenv("ILQR_BACKWARD_LANES", lanes)
     monkeypatch.setenv("ILQR_SPARSE", "0")
     for fused in ("0", "1"):
         monkeypatch.setenv("ILQR_FUSED", fused)
