@@ -23,8 +23,13 @@
 #ifndef ILQR_B200_H
 #define ILQR_B200_H
 
+#ifdef __CUDACC_RTC__      /* device-side compile of the kernels by NVRTC: no host headers */
+typedef int int32_t;
+typedef long long int64_t;
+#else
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -36,7 +41,7 @@ extern "C" {
 #define ILQR_MAX_WAVES 8
 
 enum { ILQR_PENDULUM = 0, ILQR_DOUBLE_PENDULUM = 1, ILQR_UA_DOUBLE_PENDULUM = 2, ILQR_LTV = 3,
-       /* a user-defined System subclass: valid only in a library generated for it (class_files/codegen.py) */
+       /* a user-defined System subclass: its kernels come from a module (ilqr_module_load, ilqr_create_user) */
        ILQR_USER = 4 };
 enum { ILQR_EULER = 0, ILQR_MIDPOINT = 1, ILQR_RK4 = 2, ILQR_BACKWARD_EULER = 3 };
 enum { ILQR_F64 = 0, ILQR_F32 = 1 };
@@ -82,11 +87,37 @@ typedef struct ilqr_problem_t {
 
 typedef struct ilqr_handle_s *ilqr_handle_t;
 
+#ifndef __CUDACC_RTC__     /* the entry points are host functions: not part of a device-side (NVRTC) compile */
+
 /* iLQR.__init__ / System.__init__: validates the problem (unknown integrator or a model/dimension
  * mismatch -> ILQR_E_INVALID, the counterpart of the ValueErrors at iLQR_class.py:50-52 and
  * system_base.py:197-198) and precomputes the device-side constants. */
 int ilqr_create(const ilqr_problem_t *problem, ilqr_handle_t *out);
 int ilqr_destroy(ilqr_handle_t h);
+
+/* ---- user-defined System subclasses (model ILQR_USER) -------------------------------------------------------------
+ * The reference derives and jit-compiles everything a new System needs at construction, in process
+ * (system_base.py:203-251).  Here the host side (class_files/codegen.py) traces the subclass's three methods, generates
+ * the device model (ilqr::UserSys<T>, ilqr::UserCost<T>), compiles the library's generic kernel templates against it
+ * with NVRTC for sm_100a -- in process, no nvcc, no host compiler -- and hands the cubin to the library:
+ *   image        cubin (NVRTC output) holding the instantiations of the ILQR_UK_* kernels for ONE (integrator, dtype)
+ *   kernel_names their lowered (mangled) names, indexed by ILQR_UK_*
+ *   n, m         state / control dimension of the generated model (n <= ILQR_NMAX, m <= ILQR_MMAX)
+ * A module serves any number of handles (ilqr_create_user) on the device that was current at load time and must
+ * outlive them. */
+typedef struct ilqr_module_s *ilqr_module_t;
+enum { ILQR_UK_STEP = 0,            /* step_kernel<UserSys, INTEG, T> */
+       ILQR_UK_LINEARIZE = 1,       /* commit_linearize_kernel<UserSys, INTEG, T> */
+       ILQR_UK_COST_EXPANSION = 2,  /* cost_expansion_kernel<UserCost, T, n, m> */
+       ILQR_UK_BACKWARD_SMALL = 3,  /* backward_kernel<UserCost, T, n, m, 8, 32>   (n > 4: <.., 2, 32>) */
+       ILQR_UK_BACKWARD_LARGE = 4,  /* backward_kernel<UserCost, T, n, m, 4, 64>   (n > 4: <.., 2, 32>) */
+       ILQR_UK_ROLLOUT = 5,         /* rollout_kernel<UserSys, UserCost, INTEG, T> */
+       ILQR_N_USER_KERNELS = 6 };
+int ilqr_module_load(const void *image, size_t bytes, const char *const *kernel_names, int n, int m, int integrator,
+                     int dtype, ilqr_module_t *out);
+int ilqr_module_unload(ilqr_module_t mod);
+/* ilqr_create for problem->model == ILQR_USER: n, m, integrator and dtype must be the module's */
+int ilqr_create_user(const ilqr_problem_t *problem, ilqr_module_t mod, ilqr_handle_t *out);
 
 /* bytes of caller-provided device scratch needed by ilqr_backward_pass / ilqr_solve */
 size_t ilqr_workspace_bytes(ilqr_handle_t h);
@@ -189,6 +220,7 @@ int64_t ilqr_launch_count(ilqr_handle_t h);
 int ilqr_last_cuda_error(ilqr_handle_t h);
 const char *ilqr_strerror(int code);
 const char *ilqr_version(void);
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

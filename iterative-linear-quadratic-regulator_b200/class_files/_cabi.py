@@ -39,6 +39,10 @@ _VP, _I32P, _I64P = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)
 SIGNATURES = {
     "ilqr_create": (C.c_int, [C.POINTER(Problem), C.POINTER(_VP)]),
     "ilqr_destroy": (C.c_int, [_VP]),
+    "ilqr_module_load": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(_VP)]),
+    "ilqr_module_unload": (C.c_int, [_VP]),
+    "ilqr_create_user": (C.c_int, [C.POINTER(Problem), _VP, C.POINTER(_VP)]),
     "ilqr_workspace_bytes": (C.c_size_t, [_VP]),
     "ilqr_step": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP]),
     "ilqr_linearize": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),

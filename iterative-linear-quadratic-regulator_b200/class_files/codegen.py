@@ -4,21 +4,22 @@ The reference's contract for a new system is three methods, `_f_cont_fcn(x,u)`, 
 (system_base.py:255-275); everything else -- the discrete step, f_x, f_u, l_x, l_u, l_xx, l_uu, l_ux, l_f_x,
 l_f_xx -- JAX derives by tracing and autodiff (system_base.py:203-219).  Here the three methods are traced once
 with sympy symbols (class_files/symbolic.py), differentiated analytically, passed through common-subexpression
-elimination and printed as a CUDA header defining ilqr::UserSys<T> and ilqr::UserCost<T>.  csrc/ilqr_b200.cu is
-then compiled against that header with nvcc for sm_100a into its own shared library with the SAME C ABI
-(include/ilqr_b200.h, model ILQR_USER), cached in-tree under _user_cache/ by content hash.  The integrators and
-the chain rule through their stages are the generic device templates of csrc/ilqr_systems.cuh.
+elimination and printed as a CUDA header defining ilqr::UserSys<T> and ilqr::UserCost<T>.  The library's generic
+kernel templates (csrc/*.cuh: integrators, chain rule through their stages, K1/K2/K3) are then compiled against that
+header by NVRTC for sm_100a -- in this process, without nvcc or a host compiler, like the reference's jit at
+construction -- and the cubin is handed to libilqr_b200.so (ilqr_module_load, ilqr_create_user; model ILQR_USER).
+Cubins are cached under _user_cache/ by content hash.
 """
 import ctypes as C
 import hashlib
 import os
-import subprocess
 
 import numpy as np
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
 from . import _cabi
+from . import _nvrtc
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _ROOT = os.path.dirname(_PKG)
@@ -152,44 +153,109 @@ struct UserCost {{
     return text, n, m
 
 
-def _sources_digest():
-    h = hashlib.sha1()
+def _sources():
+    """{include name: text} of everything the kernel translation unit includes besides the generated model"""
     csrc = os.path.join(_PKG, "csrc")
-    for name in sorted(os.listdir(csrc)):
-        if name.endswith((".cu", ".cuh")):
-            h.update(open(os.path.join(csrc, name), "rb").read())
-    h.update(open(os.path.join(_ROOT, "include", "ilqr_b200.h"), "rb").read())
-    return h.hexdigest()
+    out = {name: open(os.path.join(csrc, name)).read() for name in sorted(os.listdir(csrc)) if name.endswith(".cuh")}
+    out["ilqr_b200.h"] = open(os.path.join(_ROOT, "include", "ilqr_b200.h")).read()
+    return out
 
 
-def library_path(header_text, integrator, dtype):
-    key = hashlib.sha1((header_text + integrator + dtype + _sources_digest()).encode()).hexdigest()[:16]
-    return os.path.join(CACHE, f"libilqr_user_{key}.so"), os.path.join(CACHE, f"ilqr_user_{key}.cuh")
+# the translation unit NVRTC compiles: the generic kernel templates of the library against the generated model
+_TU = """#include "ilqr_systems.cuh"
+#include "ilqr_user.cuh"
+#include "ilqr_kernels_common.cuh"
+#include "ilqr_kernels_linearize.cuh"
+#include "ilqr_kernels_backward.cuh"
+#include "ilqr_kernels_rollout.cuh"
+"""
+_NVRTC_OPTIONS = ("--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo")
+
+
+def kernel_expressions(n, m, integrator, dtype):
+    """the template instantiations a module holds, in ILQR_UK_* order (include/ilqr_b200.h)"""
+    T = "float" if dtype == "float32" else "double"
+    S, Cst, I = f"ilqr::UserSys<{T}>", f"ilqr::UserCost<{T}>", _cabi.INTEGRATORS[integrator]
+    small, large = ((2, 32), (2, 32)) if n > 4 else ((8, 32), (4, 64))
+    return [f"ilqr::step_kernel<{S}, {I}, {T}>",
+            f"ilqr::commit_linearize_kernel<{S}, {I}, {T}>",
+            f"ilqr::cost_expansion_kernel<{Cst}, {T}, {n}, {m}>",
+            f"ilqr::backward_kernel<{Cst}, {T}, {n}, {m}, {small[0]}, {small[1]}>",
+            f"ilqr::backward_kernel<{Cst}, {T}, {n}, {m}, {large[0]}, {large[1]}>",
+            f"ilqr::rollout_kernel<{S}, {Cst}, {I}, {T}>"]
+
+
+def cubin_path(header_text, integrator, dtype):
+    h = hashlib.sha1()
+    for name, text in _sources().items():
+        h.update(name.encode() + text.encode())
+    h.update((header_text + integrator + dtype + _TU + " ".join(_NVRTC_OPTIONS) + "%d.%d" % _nvrtc.version()).encode())
+    return os.path.join(CACHE, f"ilqr_user_{h.hexdigest()[:16]}.cubin")
+
+
+def compile_module(system):
+    """-> (cubin bytes, lowered kernel names in ILQR_UK_* order, n, m): generated model + kernel templates compiled by
+    NVRTC in this process (no nvcc, no host compiler), or fetched from the on-disk cache keyed by the content of the
+    model, the kernel sources and the NVRTC version."""
+    text, n, m = generate_header(system)
+    exprs = kernel_expressions(n, m, system.integrator, system.dtype)
+    path = cubin_path(text, system.integrator, system.dtype)
+    if os.path.exists(path) and os.path.exists(path + ".names"):
+        names = open(path + ".names").read().split("\n")
+        if len(names) == len(exprs):
+            return open(path, "rb").read(), names, n, m
+    headers = _sources()
+    headers["ilqr_user.cuh"] = text
+    try:
+        cubin, lowered = _nvrtc.compile_cubin(_TU, headers, exprs, _NVRTC_OPTIONS)
+    except RuntimeError as e:
+        raise RuntimeError(f"NVRTC failed for the generated system {type(system).__name__}:\n{e}") from e
+    names = [lowered[e] for e in exprs]
+    try:                                             # the cache is an optimisation: a read-only tree still works
+        os.makedirs(CACHE, exist_ok=True)
+        tmp = path + f".tmp{os.getpid()}"
+        with open(tmp, "wb") as fh:
+            fh.write(cubin)
+        os.replace(tmp, path)
+        with open(path + ".names", "w") as fh:
+            fh.write("\n".join(names))
+        with open(path[:-6] + ".cuh", "w") as fh:    # the generated model, for inspection
+            fh.write(text)
+    except OSError:
+        pass
+    return cubin, names, n, m
+
+
+class UserLibrary:
+    """libilqr_b200.so as seen by ONE user-defined system: every entry point of the C ABI, with ilqr_create bound to the
+    module that holds the system's kernels (ilqr_module_load / ilqr_create_user)."""
+
+    def __init__(self, system):
+        self._lib = _cabi.load()
+        cubin, names, n, m = compile_module(system)
+        self._image = cubin                          # the runtime may reference the image while the module lives
+        arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
+        self._module = C.c_void_p()
+        rc = self._lib.ilqr_module_load(cubin, len(cubin), arr, n, m, _cabi.INTEGRATORS[system.integrator],
+                                        _cabi.DTYPES[system.dtype], C.byref(self._module))
+        _cabi.check(rc)
+
+    def ilqr_create(self, problem, out):
+        return self._lib.ilqr_create_user(problem, self._module, out)
+
+    def __getattr__(self, name):
+        return getattr(self._lib, name)
+
+
+_LIBRARIES = {}
 
 
 def build_library(system):
-    """Generate + compile (or fetch from the in-tree cache) the library of `system`; returns the loaded CDLL."""
-    text, n, m = generate_header(system)
-    so, hdr = library_path(text, system.integrator, system.dtype)
-    if not os.path.exists(so):
-        os.makedirs(CACHE, exist_ok=True)
-        with open(hdr, "w") as fh:
-            fh.write(text)
-        from importlib import util
-        spec = util.spec_from_file_location("ilqr_b200_build", os.path.join(_PKG, "build.py"))
-        bld = util.module_from_spec(spec)
-        spec.loader.exec_module(bld)
-        tmp = so + f".tmp{os.getpid()}"
-        cmd = [bld.nvcc_path()] + bld.NVCC_FLAGS + [
-            "-DILQR_USER_SYS", f'-DILQR_USER_HEADER="{hdr}"', f"-DILQR_USER_INTEG={_cabi.INTEGRATORS[system.integrator]}",
-            f"-DILQR_USER_F32={1 if system.dtype == 'float32' else 0}", "-o", tmp] + bld.SRC
-        try:
-            subprocess.run(cmd, check=True, capture_output=True, text=True)
-        except subprocess.CalledProcessError as e:
-            raise RuntimeError(f"nvcc failed for the generated system {type(system).__name__}:\n{e.stderr[-4000:]}") from e
-        os.replace(tmp, so)
-    lib = C.CDLL(so)
-    for fname, (res, args) in _cabi.SIGNATURES.items():
-        fn = getattr(lib, fname)
-        fn.restype, fn.argtypes = res, args
-    return lib
+    """the library object of a user-defined system (its kernels compiled by NVRTC on first use, then cached on disk;
+    systems with the same generated code, integrator and element type share one loaded module per process)"""
+    from . import _device
+    _device.require_cuda()
+    key = cubin_path(generate_header(system)[0], system.integrator, system.dtype)
+    if key not in _LIBRARIES:
+        _LIBRARIES[key] = UserLibrary(system)
+    return _LIBRARIES[key]

@@ -22,13 +22,9 @@
 //   ilqr_b200.cu (this file)    handle, workspace layout, launch configuration, ilqr_solve, the C ABI
 #include "ilqr_b200.h"
 #include "ilqr_systems.cuh"
-// A library for ONE user-defined System subclass is this same file compiled with
-//   -DILQR_USER_SYS -DILQR_USER_HEADER="<generated>.cuh" -DILQR_USER_INTEG=<0..3> -DILQR_USER_F32=<0|1>
-// (class_files/codegen.py): the generated header defines ilqr::UserSys<T> / ilqr::UserCost<T>, and only that
-// model, integrator and element type are instantiated.
-#ifdef ILQR_USER_SYS
-#include ILQR_USER_HEADER
-#endif
+// A user-defined System subclass (model ILQR_USER) brings its own device code: class_files/codegen.py generates
+// ilqr::UserSys<T> / ilqr::UserCost<T>, NVRTC compiles the generic kernel templates of csrc/*.cuh against them in
+// process, and this library loads the cubin (ilqr_module_load) and launches those kernels by handle (UserModule).
 
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -114,8 +110,22 @@ template <typename T, int n, int m> QuadCost<T, n, m> make_cost(const ilqr_probl
     return c;
 }
 
+// Kernels of a user-defined system: a cubin built by NVRTC (class_files/codegen.py) from the generic templates of
+// csrc/*.cuh and the generated ilqr::UserSys / ilqr::UserCost, loaded through the runtime's library API.  The kernels
+// are the SAME templates this file instantiates for the shipped models, so their parameter lists are marshalled here
+// exactly as the <<< >>> launches below pass them.
+struct UserModule {
+    cudaLibrary_t lib;
+    cudaKernel_t k[ILQR_N_USER_KERNELS];
+    int n, m, integrator, dtype;
+};
+// host mirrors of the generated parameter structs (UserSys<T> is empty; UserCost<T> = { T dt; int diag, monotone; })
+struct UserSysArg { char unused; };
+template <typename T> struct UserCostArg { T dt; int diag, monotone; };
+
 struct Handle {
     ilqr_problem_t p;
+    UserModule *umod;         // model ILQR_USER: where the kernels live (not owned)
     int n_alpha_eff;          // tries actually made: stops once alpha < min_alpha (iLQR_class.py:300-302)
     int n_first;              // step sizes rolled out eagerly (first wave); the rest only where needed
     int spec_cap;             // trajectories whose deferred step sizes ride along speculatively (SpecArgs)
@@ -124,8 +134,8 @@ struct Handle {
     int env_rollout_bs;       // ILQR_ROLLOUT_BS: 0 [auto] or a block size
     int env_fused;            // ILQR_FUSED: -1 [auto: fused K1+K2 inside ilqr_solve where it is the faster form], 0 never,
                               // 1 wherever the model allows (also ilqr_backward_pass)
-    int env_fused_np;         // ILQR_FUSED_NP: producer warps per consumer warp, 2 [default], 3, or 1 (four-lane form only)
-    int env_fused_minb;       // ILQR_FUSED_MINB: 0 [auto: by batch size], 1 = uncapped registers, 5 = capped for 5 blocks/SM
+    int env_fused_np;         // ILQR_FUSED_NP: producer warps per consumer warp: 0 [auto: by batch size], 2, 3, 4
+    int env_fused_minb;       // ILQR_FUSED_MINB: 0 [auto: by batch size], 1 = uncapped registers, 4 / 5 = capped for 4 / 5 blocks per SM
     int env_check_every;      // ILQR_CHECK_EVERY: iterations enqueued between host polls of the active count [8]
     long env_sparse_thresh;   // ILQR_SPARSE_THRESH / ILQR_SPARSE_ALL: -1 [auto] or the thresholds of SparseArgs
     long env_sparse_all;
@@ -214,6 +224,29 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
         if (e_ != cudaSuccess) { (h)->last_cuda = (int)e_; return ILQR_E_CUDA; } \
     } while (0)
 
+// launch kernel `which` of the handle's user module; args = addresses of the kernel's parameters in order
+static int launch_user(Handle *h, int which, int grid, int block, size_t smem, cudaStream_t st, void **args)
+{
+    cudaError_t e = cudaLaunchKernel((const void *)h->umod->k[which], dim3((unsigned)grid), dim3((unsigned)block), args, smem, st);
+    h->launches++;
+    if (e != cudaSuccess) { h->last_cuda = (int)e; cudaGetLastError(); return ILQR_E_CUDA; }
+    return ILQR_OK;
+}
+
+// the generated cost's parameter block in the handle's element type (UserCost<T> = { T dt; int diag, monotone; })
+struct UserCostAny {
+    UserCostArg<double> d;
+    UserCostArg<float> f;
+    void *ptr(const Handle *h) { return h->p.dtype == ILQR_F64 ? (void *)&d : (void *)&f; }
+    explicit UserCostAny(const Handle *h) : d{h->p.dt, 0, 0}, f{(float)h->p.dt, 0, 0} {}
+};
+struct ScalarAny {           // a `T` kernel parameter
+    double d;
+    float f;
+    void *ptr(const Handle *h) { return h->p.dtype == ILQR_F64 ? (void *)&d : (void *)&f; }
+    explicit ScalarAny(double v) : d(v), f((float)v) {}
+};
+
 // dispatch on (dtype, model, integrator): calls f(T{}, sys, qc, integral_constant<int,INTEG>{})
 template <typename T, class Sys, class F> static int dispatch_integ(const Handle *h, const Sys &sys, F &&f)
 {
@@ -232,7 +265,6 @@ template <typename T, class Sys, class F> static int dispatch_integ(const Handle
 #endif
 }
 
-#ifndef ILQR_USER_SYS
 template <typename T, class F> static int dispatch_model(const Handle *h, F &&f)
 {
 #ifdef ILQR_FAST_BUILD
@@ -252,22 +284,7 @@ template <typename T, class F> static int dispatch_model(const Handle *h, F &&f)
     return ILQR_E_INVALID;
 #endif
 }
-#endif
 
-#ifdef ILQR_USER_SYS
-#if ILQR_USER_F32
-typedef float user_t;
-#else
-typedef double user_t;
-#endif
-template <class F> static int dispatch(const Handle *h, F &&f)
-{
-    UserSys<user_t> sys;
-    UserCost<user_t> qc;
-    qc.dt = (user_t)h->p.dt;
-    return f(user_t(0), sys, qc, std::integral_constant<int, ILQR_USER_INTEG>{});
-}
-#else
 template <class F> static int dispatch(const Handle *h, F &&f)
 {
     if (h->p.dtype == ILQR_F64) return dispatch_model<double>(h, f);
@@ -277,7 +294,6 @@ template <class F> static int dispatch(const Handle *h, F &&f)
     return dispatch_model<float>(h, f);
 #endif
 }
-#endif
 
 // ---- launch helpers -----------------------------------------------------------------------
 
@@ -289,6 +305,16 @@ static int launch_commit_linearize(Handle *h, const void *phi, void *X, void *U,
     SparseArgs sa;
     std::memset(&sa, 0, sizeof sa);
     if (sparse) sa = *sparse;
+    if (h->umod) {
+        UserSysArg us{};
+        ScalarAny dt(h->p.dt);
+        int N = h->p.N, B = h->p.B;
+        void *args[] = { &us, dt.ptr(h), &N, &B, &phi, &X, &U, &A, &Bd, &Xc, &Uc, &winner, &wslot, &active, &iters, &it, &do_lin,
+                         &g0, &g1, &sa, &ab_blocked, &sparse_only };
+        int grid = grid_for((size_t)(N + 1) * B, 128);
+        if (sparse_only && grid > 148 * 16) grid = 148 * 16;
+        return launch_user(h, ILQR_UK_LINEARIZE, grid, 128, 0, st, args);
+    }
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
         using T = decltype(tz);
         using Sys = decltype(sys);
@@ -335,6 +361,23 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
     SparseArgs sa;
     std::memset(&sa, 0, sizeof sa);
     if (sparse) sa = *sparse;
+    if (h->umod) {
+        // the generic thread-per-trajectory scan, ring depth / block size by state dimension and batch as below
+        const int n = h->p.n, m = h->p.m, L = n * n + n * m + n + m;
+        const bool large = n <= 4 && h->p.B > 32768;
+        const int depth = n > 4 ? 2 : (large ? 4 : 8), bs = large ? 64 : 32;
+        const int which = large ? ILQR_UK_BACKWARD_LARGE : ILQR_UK_BACKWARD_SMALL;
+        const size_t smem = (size_t)depth * L * bs * (h->p.dtype == ILQR_F64 ? 8 : 4);
+        if (smem > h->smem_backward) {
+            cudaError_t e = cudaFuncSetAttribute((const void *)h->umod->k[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { h->last_cuda = (int)e; return ILQR_E_CUDA; }
+            h->smem_backward = smem;
+        }
+        UserCostAny qc(h);
+        int N = h->p.N, B = h->p.B;
+        void *args[] = { qc.ptr(h), &N, &B, &X, &U, &A, &Bd, &K, &k, &active, &gate, &mu, &sa, &ab_blocked };
+        return launch_user(h, which, grid_for(B, bs), bs, smem, st, args);
+    }
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto) -> int {
         using T = decltype(tz);
         using Sys = decltype(sys);
@@ -379,12 +422,7 @@ template <class Sys, class Cost> constexpr bool fused_eligible()
 
 static bool fused_available(const Handle *h)
 {
-#ifdef ILQR_USER_SYS
-    (void)h;
-    return false;
-#else
-    return h->p.model != ILQR_LTV && h->env_fused != 0;
-#endif
+    return h->p.model != ILQR_LTV && h->p.model != ILQR_USER && h->env_fused != 0;
 }
 
 // K1 + K2 in one launch (ilqr_kernels_fused.cuh): commit of the accepted candidates, linearization and reverse scan
@@ -402,24 +440,6 @@ static int launch_fused(Handle *h, const void *phi, void *X, void *U, const void
         using Cost = decltype(qc);
         constexpr int I = decltype(integ)::value;
         if constexpr (fused_eligible<Sys, Cost>()) {
-            if constexpr (Sys::N == 4 && Sys::M == 1) {
-                // small batches: the four-lane scan as the consumer (ILQR_BACKWARD_LANES overrides, as for K2 alone)
-                const bool lanes = h->env_lanes >= 0 ? h->env_lanes != 0 : h->p.B <= 32768;
-                if (lanes) {
-                    // B=4096 is 512 blocks on 148 SMs: the block must fit four times per SM (register cap), or a
-                    // quarter of them waits for a second round
-                    if (h->env_fused_np == 1)
-                        fused_backward_lanes_kernel<Sys, I, T, 1, 3, 1><<<grid_for(h->p.B, 8), 64, 0, st>>>(
-                            sys, qc, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (const T *)Xc, (const T *)Uc, winner, wslot,
-                            active, iters, it, g0, g1, (T *)K, (T *)k, (const T *)mu, sa);
-                    else
-                        fused_backward_lanes_kernel<Sys, I, T, 2, 4, 4><<<grid_for(h->p.B, 8), 96, 0, st>>>(
-                            sys, qc, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (const T *)Xc, (const T *)Uc, winner, wslot,
-                            active, iters, it, g0, g1, (T *)K, (T *)k, (const T *)mu, sa);
-                    ILQR_CHECK_LAUNCH(h);
-                    return ILQR_OK;
-                }
-            }
             const int groups = (h->p.B + 31) / 32;
             auto go = [&](auto np, auto stages, auto minb) {
                 constexpr int NP = decltype(np)::value, S = decltype(stages)::value, MB = decltype(minb)::value;
@@ -428,10 +448,26 @@ static int launch_fused(Handle *h, const void *phi, void *X, void *U, const void
                     iters, it, g0, g1, (T *)K, (T *)k, (const T *)mu, sa);
             };
             using std::integral_constant;
-            const bool big = h->env_fused_minb > 0 ? h->env_fused_minb > 1 : h->p.B > 32768;
-            if (h->env_fused_np == 3) go(integral_constant<int, 3>{}, integral_constant<int, 3>{}, integral_constant<int, 1>{});
-            else if (big) go(integral_constant<int, 2>{}, integral_constant<int, 4>{}, integral_constant<int, 5>{});
-            else go(integral_constant<int, 2>{}, integral_constant<int, 4>{}, integral_constant<int, 1>{});
+            using I1 = integral_constant<int, 1>;
+            using I2 = integral_constant<int, 2>;
+            using I3 = integral_constant<int, 3>;
+            using I4 = integral_constant<int, 4>;
+            using I5 = integral_constant<int, 5>;
+            // Shape by batch size, so that every block is resident at once (one block = 32 trajectories) and the
+            // producers keep up with the consumer:
+            //   <= 2 blocks per SM: 4 producer warps per consumer, registers uncapped -- the scan is latency bound, the SMs
+            //      are nearly empty, and 2 producers deliver a step only every ~1070 cycles against the consumer's ~800
+            //   <= 4 blocks per SM: 2 producers, registers capped for 4 blocks per SM (164, no spills)
+            //   more: 2 producers, capped for 5 blocks per SM (128 registers, 15 warps per SM for the FP64 pipe)
+            // ILQR_FUSED_NP / ILQR_FUSED_MINB override (experiments).
+            int np = h->env_fused_np, mb = h->env_fused_minb;
+            if (np == 0) np = groups <= 148 * 2 ? 4 : 2;
+            if (mb == 0) mb = groups <= 148 * 2 ? 1 : (groups <= 148 * 4 ? 4 : 5);
+            if (np == 4) go(I4{}, I4{}, I1{});
+            else if (np == 3) go(I3{}, I3{}, I1{});
+            else if (mb >= 5) go(I2{}, I4{}, I5{});
+            else if (mb == 4) go(I2{}, I4{}, I4{});
+            else go(I2{}, I4{}, I1{});
             ILQR_CHECK_LAUNCH(h);
             return ILQR_OK;
         } else {
@@ -444,7 +480,7 @@ static int launch_fused(Handle *h, const void *phi, void *X, void *U, const void
 static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const void *U, void *K, void *k,
                                const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr)
 {
-#if defined(ILQR_USER_SYS) || defined(ILQR_FAST_BUILD)
+#if defined(ILQR_FAST_BUILD)
     return ILQR_E_INVALID;
 #else
     constexpr int TPB = 16;
@@ -479,6 +515,18 @@ static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const voi
     SparseArgs sa;
     std::memset(&sa, 0, sizeof sa);
     if (sparse) sa = *sparse;
+    if (h->umod) {
+        const size_t threads = (size_t)n_alpha * (((size_t)h->p.B + 31) / 32 * 32) + (size_t)sp.cap * sp.n2;
+        int bs = h->env_rollout_bs > 0 ? h->env_rollout_bs : block_for(threads);
+        if (h->env_rollout_bs <= 0 && bs > 128) bs = 128;
+        UserSysArg us{};
+        UserCostAny qc(h);
+        int N = h->p.N, B = h->p.B;
+        AlphaList alc = al;
+        void *args[] = { &us, qc.ptr(h), &N, &B, &n_alpha, &alc, &phi, &x0, &X, &U, &k, &K, &Xc, &Uc, &cost_alpha, &active, &gate,
+                         &cost_ref, &sp, &list, &list_count, &sa };
+        return launch_user(h, ILQR_UK_ROLLOUT, grid_for(threads, bs), bs, 0, st, args);
+    }
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
         using T = decltype(tz);
         using Sys = decltype(sys);
@@ -496,14 +544,11 @@ static int launch_rollout(Handle *h, int n_alpha, const AlphaList &al, const voi
                 (const T *)k, (const T *)K, (T *)Xc, (T *)Uc, (T *)cost_alpha, active, gate, (const T *)cost_ref, sp, list,
                 list_count, sa);
         };
-#ifndef ILQR_USER_SYS
         // diagonal weights (every reference script): the compact cost keeps the kernel's constants in uniform registers
         // (n <= 4 only: with the compact cost ptxas hoists the LTV model's matrix constants into registers and feeds
         // them to the FP64 pipe through R2UR moves -- 1.75x slower than its kernel with the dense cost)
         if (Sys::N <= 4 && qc.diag) go(DiagCost<T, Sys::N, Sys::M>(qc));
-        else
-#endif
-            go(qc);
+        else go(qc);
         ILQR_CHECK_LAUNCH(h);
         return ILQR_OK;
     });
@@ -676,11 +721,7 @@ using namespace ilqr;
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
-#ifdef ILQR_USER_SYS
-const char *ilqr_version(void) { return "ilqr_b200 0.1 (sm_100a), user-defined system build"; }
-#else
-const char *ilqr_version(void) { return "ilqr_b200 0.1 (sm_100a)"; }
-#endif
+const char *ilqr_version(void) { return "ilqr_b200 0.2 (sm_100a)"; }
 
 const char *ilqr_strerror(int code)
 {
@@ -693,7 +734,54 @@ const char *ilqr_strerror(int code)
     return "unknown error";
 }
 
-int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
+static int create_handle(const ilqr_problem_t *p, UserModule *umod, ilqr_handle_t *out);
+
+int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out) { return create_handle(p, nullptr, out); }
+
+int ilqr_create_user(const ilqr_problem_t *p, ilqr_module_t mod, ilqr_handle_t *out)
+{
+    if (!mod) return ILQR_E_INVALID;
+    return create_handle(p, (UserModule *)mod, out);
+}
+
+int ilqr_module_load(const void *image, size_t bytes, const char *const *kernel_names, int n, int m, int integrator,
+                     int dtype, ilqr_module_t *out)
+{
+    if (!image || !bytes || !kernel_names || !out) return ILQR_E_INVALID;
+    *out = nullptr;
+    if (n < 1 || n > ILQR_NMAX || m < 1 || m > ILQR_MMAX || integrator < ILQR_EULER || integrator > ILQR_BACKWARD_EULER ||
+        (dtype != ILQR_F64 && dtype != ILQR_F32)) return ILQR_E_INVALID;
+    UserModule *u = new (std::nothrow) UserModule;
+    if (!u) return ILQR_E_INVALID;
+    std::memset(u, 0, sizeof *u);
+    u->n = n; u->m = m; u->integrator = integrator; u->dtype = dtype;
+    if (cudaLibraryLoadData(&u->lib, image, nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+        cudaGetLastError();
+        delete u;
+        return ILQR_E_CUDA;
+    }
+    for (int i = 0; i < ILQR_N_USER_KERNELS; ++i) {
+        if (!kernel_names[i] || cudaLibraryGetKernel(&u->k[i], u->lib, kernel_names[i]) != cudaSuccess) {
+            cudaGetLastError();
+            cudaLibraryUnload(u->lib);
+            delete u;
+            return ILQR_E_INVALID;
+        }
+    }
+    *out = (ilqr_module_t)u;
+    return ILQR_OK;
+}
+
+int ilqr_module_unload(ilqr_module_t mod)
+{
+    UserModule *u = (UserModule *)mod;
+    if (!u) return ILQR_E_INVALID;
+    cudaLibraryUnload(u->lib);
+    delete u;
+    return ILQR_OK;
+}
+
+static int create_handle(const ilqr_problem_t *p, UserModule *umod, ilqr_handle_t *out)
 {
     if (!p || !out) return ILQR_E_INVALID;
     *out = nullptr;
@@ -705,17 +793,12 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
     case ILQR_DOUBLE_PENDULUM: n = 4; m = 2; break;
     case ILQR_UA_DOUBLE_PENDULUM: n = 4; m = 1; break;
     case ILQR_LTV: n = 12; m = 4; if (p->integrator != ILQR_EULER) return ILQR_E_INVALID; break;
-#ifdef ILQR_USER_SYS
-    case ILQR_USER:
-        n = UserSys<user_t>::N; m = UserSys<user_t>::M;
-        if (p->integrator != ILQR_USER_INTEG || p->dtype != (ILQR_USER_F32 ? ILQR_F32 : ILQR_F64)) return ILQR_E_INVALID;
+    case ILQR_USER:          // kernels come from a loaded module (ilqr_create_user)
+        if (!umod || p->integrator != umod->integrator || p->dtype != umod->dtype) return ILQR_E_INVALID;
+        n = umod->n; m = umod->m;
         break;
-#endif
     default: return ILQR_E_INVALID;
     }
-#ifdef ILQR_USER_SYS
-    if (p->model != ILQR_USER) return ILQR_E_INVALID;        // this library holds one generated model only
-#endif
     if (p->n != n || p->m != m) return ILQR_E_INVALID;
     if (p->N < 1 || p->B < 1 || p->n_alpha < 1 || p->n_alpha > ILQR_MAX_ALPHAS || p->maxiter < 0) return ILQR_E_INVALID;
     if (!(p->dt > 0.0)) return ILQR_E_INVALID;
@@ -724,6 +807,7 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
     if (!h) return ILQR_E_INVALID;
     std::memset(h, 0, sizeof(Handle));
     h->p = *p;
+    h->umod = umod;
     h->prof_ev = new std::vector<cudaEvent_t>();
     h->prof_kind = new std::vector<int>();
     // alpha = 1, then *= alpha_factor per failed try; tries stop once alpha < min_alpha (:279-302)
@@ -741,7 +825,7 @@ int ilqr_create(const ilqr_problem_t *p, ilqr_handle_t *out)
         h->env_rollout_bs = (e = getenv("ILQR_ROLLOUT_BS")) && atoi(e) >= 32 ? atoi(e) / 32 * 32 : 0;
         h->env_check_every = (e = getenv("ILQR_CHECK_EVERY")) && atoi(e) > 0 ? atoi(e) : 8;
         h->env_fused = (e = getenv("ILQR_FUSED")) ? (atoi(e) != 0) : -1;
-        h->env_fused_np = (e = getenv("ILQR_FUSED_NP")) && atoi(e) >= 1 && atoi(e) <= 3 ? atoi(e) : 2;
+        h->env_fused_np = (e = getenv("ILQR_FUSED_NP")) && atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 0;
         h->env_fused_minb = (e = getenv("ILQR_FUSED_MINB")) ? atoi(e) : 0;
     }
     h->env_sparse_thresh = (e = getenv("ILQR_SPARSE_THRESH")) ? atol(e) : -1;
@@ -796,6 +880,14 @@ int ilqr_step(ilqr_handle_t hh, int t, const void *phi, const void *x, const voi
     Handle *h = (Handle *)hh;
     if (!h || !x || !u || !xn) return ILQR_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->umod) {
+        UserSysArg us{};
+        ScalarAny dt(h->p.dt);
+        int B = h->p.B;
+        const int bs = block_for(B);
+        void *args[] = { &us, dt.ptr(h), &B, &t, &phi, &x, &u, &xn };
+        return launch_user(h, ILQR_UK_STEP, grid_for(B, bs), bs, 0, st, args);
+    }
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto integ) -> int {
         using T = decltype(tz);
         using Sys = decltype(sys);
@@ -821,6 +913,12 @@ int ilqr_cost_expansion(ilqr_handle_t hh, const void *X, const void *U, void *l,
     Handle *h = (Handle *)hh;
     if (!h || !X || !U) return ILQR_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->umod) {
+        UserCostAny qc(h);
+        int N = h->p.N, B = h->p.B;
+        void *args[] = { qc.ptr(h), &N, &B, &X, &U, &l, &lx, &lu, &lxx, &luu, &lux, &lf, &lfx, &lfxx };
+        return launch_user(h, ILQR_UK_COST_EXPANSION, grid_for((size_t)(N + 1) * B, 128), 128, 0, st, args);
+    }
     return dispatch(h, [&](auto tz, auto sys, auto qc, auto) -> int {
         using T = decltype(tz);
         using Sys = decltype(sys);

@@ -224,243 +224,4 @@ fused_backward_kernel(const __grid_constant__ Sys sys, const __grid_constant__ C
     }
 }
 
-// Four-lane form for n = 4, m = 1 at small batches (the latency-bound regime of the headline benchmark).  The consumer
-// is backward_n4m1_lanes_kernel's scan -- four lanes per trajectory, eight trajectories per warp, ~760 cycles of
-// dependent latency per step instead of the ~1050 of one thread per trajectory -- fed by producer warps whose lanes are
-// (timestep-in-chunk q, trajectory slot): a producer linearizes FOUR consecutive steps of the block's eight trajectories
-// at once.  Ring stage = one chunk of four steps, [q][slot][LP]; chunk c belongs to producer c mod NP.
-template <class Sys, int INTEG, typename T, int NP, int SC, int MINB>
-__global__ void __launch_bounds__(32 * (NP + 1), MINB)
-fused_backward_lanes_kernel(const __grid_constant__ Sys sys, const __grid_constant__ QuadCost<T, 4, 1> qc, int N, int B,
-                            const T *__restrict__ phi, T *__restrict__ X, T *__restrict__ U, const T *__restrict__ Xc,
-                            const T *__restrict__ Uc, const int *__restrict__ winner, const int *__restrict__ wslot,
-                            const int *__restrict__ active, const int *__restrict__ iters, int it,
-                            const unsigned int *__restrict__ gate0, const unsigned int *__restrict__ gate1,
-                            T *__restrict__ K, T *__restrict__ k, const T *__restrict__ mu,
-                            const __grid_constant__ SparseArgs sa)
-{
-    static_assert(Sys::N == 4 && Sys::M == 1, "four-lane scan: n = 4, m = 1");
-    static_assert(SC % NP == 0, "ring stages must be a multiple of the producer count");
-    constexpr int n = 4, m = 1, LP = 26, SLOTS = 8, CH = 4;             // LP: padded slot stride (conflict-free LDS.128)
-    __shared__ __align__(16) T ring[SC][CH][SLOTS][LP];
-    __shared__ __align__(16) T pre[NP][2][n + m][32];
-    __shared__ __align__(16) T exQ[SLOTS * 4], exV[SLOTS * 20];        // Q_ux / (V_xx, V_x) exchange of the consumer
-    __shared__ __align__(8) unsigned long long full[SC], empty[SC];
-    if (gate0 && *gate0 == 0u && *gate1 == 0u) return;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const bool sparse = sparse_now(sa);
-    const int n_items = sparse ? (int)*sa.n_cur : B;
-    if (blockIdx.x * SLOTS >= n_items) return;
-    auto item = [&](int slot) -> int {
-        const int i = min(blockIdx.x * SLOTS + slot, n_items - 1);      // clamped: spare slots compute on a copy
-        return sparse ? sa.cur[i] : i;
-    };
-    // this thread's trajectory: consumer lanes are (slot, column) = (lane / 4, lane % 4), producer lanes (q, slot) =
-    // (lane / 8, lane % 8); both cover the block's eight slots, so the block-wide decisions below agree in every warp
-    const int slot = wid == 0 ? lane >> 2 : lane & 7;
-    const int b = item(slot);
-    const bool in_range = blockIdx.x * SLOTS + slot < n_items;
-    int w = (in_range && winner && !sparse) ? winner[b] : -1;           // sparse iterations: K1 committed already
-    if (iters && iters[b] != it) w = -1;
-    const bool act = in_range && (active ? active[b] != 0 : true);
-    const unsigned full_mask = 0xffffffffu;
-    const bool any_act = __any_sync(full_mask, act), any_commit = __any_sync(full_mask, w >= 0);
-    if (!any_act && !any_commit) return;
-    const size_t sB = (size_t)B;
-    if (!any_act) {
-        // only candidates to commit (the trajectories finished in the previous iteration): plain copy, 12 steps abreast
-        const int cs = threadIdx.x & 7, cb = item(cs);
-        int cw = (blockIdx.x * SLOTS + cs < n_items && winner) ? winner[cb] : -1;
-        if (iters && iters[cb] != it) cw = -1;
-        if (cw >= 0) {
-            const int ccol = wslot ? wslot[cb] : cb;
-            const T *cx = Xc + (size_t)cw * (N + 1) * n * sB + ccol, *cu = Uc + (size_t)cw * N * m * sB + ccol;
-            for (int t = threadIdx.x >> 3; t <= N; t += 4 * (NP + 1)) {
-#pragma unroll
-                for (int i = 0; i < n; ++i) X[((size_t)t * n + i) * sB + cb] = cx[((size_t)t * n + i) * sB];
-                if (t < N) U[(size_t)t * sB + cb] = cu[(size_t)t * sB];
-            }
-        }
-        return;
-    }
-    const int col = (w >= 0 && wslot) ? wslot[b] : b;
-    const T *xs = w >= 0 ? Xc + (size_t)w * (N + 1) * n * sB + col : X + col;
-    const T *us = w >= 0 ? Uc + (size_t)w * N * m * sB + col : U + col;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < SC; ++s) { mbar_init(&full[s], 32); mbar_init(&empty[s], 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (wid == 0) {
-        // ---------------- consumer: backward_n4m1_lanes_kernel's scan ----------------
-        const int s = lane >> 2, j = lane & 3;
-        const bool valid = act;
-        T qrow[n], qcol[n];
-#pragma unroll
-        for (int i = 0; i < n; ++i) { qrow[i] = qc.Qs[j][i] * qc.dt; qcol[i] = qc.Qs[i][j] * qc.dt; }
-        const T xtj[n] = { qc.xt[0], qc.xt[1], qc.xt[2], qc.xt[3] };
-        const T luu = qc.Rs[0][0] * qc.dt;
-        const T mu_b = mu ? mu[b] : T(0);
-        T Vx[n], Vxx[n][n];
-        {
-            T xN[n];
-#pragma unroll
-            for (int i = 0; i < n; ++i) xN[i] = xs[((size_t)N * n + i) * sB];
-            if (w >= 0 && j == 0) {
-#pragma unroll
-                for (int i = 0; i < n; ++i) X[((size_t)N * n + i) * sB + b] = xN[i];
-            }
-            qc.terminal_grad(xN, Vx);                                    // iLQR_class.py:136-138
-#pragma unroll
-            for (int i = 0; i < n; ++i)
-#pragma unroll
-                for (int c = 0; c < n; ++c) Vxx[i][c] = qc.Qfs[i][c];
-        }
-        struct StepIn { T Am[n][n], Bv[n], x[n], Acol[n], u; };
-        // inputs of scan step i (t = N-1-i) from the ring; the chunk's stage is handed back after its last step is read
-        auto fetch = [&](StepIn &d, int i) {
-            const int c = i >> 2, st = c % SC;
-            if ((i & 3) == 0) mbar_wait(&full[st], (unsigned)(c / SC) & 1u);
-            const T *in = &ring[st][i & 3][s][0];
-#pragma unroll
-            for (int r = 0; r < n; ++r) {
-#pragma unroll
-                for (int cc = 0; cc < n; ++cc) d.Am[r][cc] = in[r * 4 + cc];
-                d.Bv[r] = in[16 + r];
-                d.x[r] = in[20 + r];
-                d.Acol[r] = in[r * 4 + j];
-            }
-            d.u = in[24];
-            if ((i & 3) == 3 || i == N - 1) mbar_arrive(&empty[st]);
-        };
-        auto scan_step = [&](const StepIn &cur, StepIn &nxt, int i) {
-            const int t = N - 1 - i;
-            if (i + 1 < N) fetch(nxt, i + 1);                            // next step's inputs: latency hides behind this step
-            const T (&Am)[n][n] = cur.Am;
-            const T (&Bv)[n] = cur.Bv, (&x)[n] = cur.x, (&Acol)[n] = cur.Acol;
-            const T u = cur.u;
-            // Y = V_xx A[:,j] ; Q_xx[:,j] = l_xx[:,j] + A' Y ; Q_ux[j] = B' Y          (iLQR_class.py:102-103)
-            T Y[n], Qxxc[n], Quxj = T(0), Qxj = T(0), Qu = T(0), Quu = T(0);
-#pragma unroll
-            for (int r = 0; r < n; ++r) {
-                T sum = T(0);
-#pragma unroll
-                for (int l = 0; l < n; ++l) sum += Vxx[r][l] * Acol[l];
-                Y[r] = sum;
-            }
-#pragma unroll
-            for (int r = 0; r < n; ++r) {
-                T sum = T(0);
-#pragma unroll
-                for (int l = 0; l < n; ++l) sum += Am[l][r] * Y[l];
-                Qxxc[r] = qcol[r] + sum;
-                Quxj += Bv[r] * Y[r];
-            }
-            // Q_uu = l_uu + B' V_xx B, Q_u = l_u + B' V_x (redundant in the 4 lanes) ; Q_x[j]   (:100-101,104)
-#pragma unroll
-            for (int r = 0; r < n; ++r) {
-                T vb = T(0);
-#pragma unroll
-                for (int l = 0; l < n; ++l) vb += Vxx[r][l] * Bv[l];
-                Quu += Bv[r] * vb;
-                Qu += Bv[r] * Vx[r];
-                Qxj += Acol[r] * Vx[r];
-            }
-            Quu += luu;
-            Quu += mu_b;
-            Qu += luu * u;
-            T lxj = T(0);
-#pragma unroll
-            for (int r = 0; r < n; ++r) lxj += qrow[r] * (x[r] - xtj[r]);
-            Qxj += lxj;
-            const T rr = -rcp_t(Quu);                                    // (:109-110)
-            const T Kj = Quxj * rr, kk = Qu * rr;
-            const T Vxj = Qxj + Kj * Qu;                                 // (:113)
-            exQ[s * 4 + j] = Quxj;
-            __syncwarp();
-            T Quxa[n];
-#pragma unroll
-            for (int r = 0; r < n; ++r) Quxa[r] = exQ[s * 4 + r];
-#pragma unroll
-            for (int r = 0; r < n; ++r) exV[s * 20 + r * 4 + j] = Qxxc[r] + Quxa[r] * Kj;     // V_xx[:,j]   (:114)
-            exV[s * 20 + 16 + j] = Vxj;
-            if (valid) {
-                K[((size_t)t * n + j) * sB + b] = Kj;
-                if (j == 0) k[(size_t)t * sB + b] = kk;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < n; ++r) {
-#pragma unroll
-                for (int c = 0; c < n; ++c) Vxx[r][c] = exV[s * 20 + r * 4 + c];
-                Vx[r] = exV[s * 20 + 16 + r];
-            }
-        };
-        StepIn in_a, in_b;                                               // ping-pong: no register copies between steps
-        fetch(in_a, 0);
-        for (int i = 0; i < N; i += 2) {
-            scan_step(in_a, in_b, i);
-            if (i + 1 < N) scan_step(in_b, in_a, i + 1);
-        }
-        return;
-    }
-
-    // ---------------- producers: lane (q, slot) commits + linearizes step 4c + q of trajectory `slot` ----------------
-    const int p = wid - 1, q = lane >> 3;
-    const int NC = (N + CH - 1) / CH;
-    const T ph = phi ? phi[b] : T(0);
-    auto prefetch = [&](int c, int buf) {
-        const int t = N - 1 - min(CH * c + q, N - 1);                    // lanes past the horizon re-read its last step
-        const T *px = xs + (size_t)t * n * sB, *pu = us + (size_t)t * m * sB;
-        T *dst = &pre[p][buf][0][lane];
-#pragma unroll
-        for (int r = 0; r < n; ++r) cp_async<sizeof(T)>(dst + r * 32, px + (size_t)r * sB);
-        cp_async<sizeof(T)>(dst + n * 32, pu);
-    };
-    if (p < NC) prefetch(p, 0);
-    cp_async_commit();
-    int buf = 0;
-    for (int c = p; c < NC; c += NP) {
-        const int i = CH * c + q, st = c % SC;
-        const bool have = i < N;
-        const int t = N - 1 - min(i, N - 1);
-        if (c + NP < NC) prefetch(c + NP, buf ^ 1);
-        cp_async_commit();
-        cp_async_wait<1>();
-        T x[n], u[m];
-        {
-            const T *src = &pre[p][buf][0][lane];
-#pragma unroll
-            for (int r = 0; r < n; ++r) x[r] = src[r * 32];
-            u[0] = src[n * 32];
-        }
-        buf ^= 1;
-        if (have && w >= 0) {                                            // commit the accepted candidate into the nominal
-#pragma unroll
-            for (int r = 0; r < n; ++r) X[((size_t)t * n + r) * sB + b] = x[r];
-            U[(size_t)t * sB + b] = u[0];
-        }
-        mbar_wait(&empty[st], ((unsigned)(c / SC) & 1u) ^ 1u);
-        T *out = &ring[st][q][lane & 7][0];
-        if (have) {
-#pragma unroll
-            for (int r = 0; r < n; ++r) out[20 + r] = x[r];
-            out[24] = u[0];
-        }
-        T Aj[n][n], Bj[n][m];
-        step_jac<INTEG>(sys, qc.dt, x, u, Aj, Bj, sys.time_scalar(t, ph));
-        if (have) {
-#pragma unroll
-            for (int r = 0; r < n; ++r) {
-#pragma unroll
-                for (int cc = 0; cc < n; ++cc) out[r * 4 + cc] = Aj[r][cc];
-                out[16 + r] = Bj[r][0];
-            }
-        }
-        mbar_arrive(&full[st]);
-    }
-}
-
 }  // namespace ilqr

@@ -12,7 +12,9 @@
 //   QuadCost               pendulum_sys.py:77-98 and the same block in the two double-pendulum files;
 //                          derivatives system_base.py:212-219
 #pragma once
+#ifndef __CUDACC_RTC__      // NVRTC (user-defined systems, class_files/codegen.py) has the device API built in
 #include <cuda_runtime.h>
+#endif
 
 namespace ilqr {
 
@@ -814,11 +816,13 @@ struct DiagCost {
     T dt;
     T xt[n], hq[n], hr[m], hqf[n];   // halved diagonals: (0.5 d) q d == ((0.5 q) d) d bit for bit (scaling by 1/2 is exact)
     int monotone;
+#ifndef __CUDACC_RTC__     // host-side conversion (launch_rollout); NVRTC compiles device code only
     explicit DiagCost(const QuadCost<T, n, m> &c) : dt(c.dt), monotone(c.monotone)
     {
         for (int i = 0; i < n; ++i) { xt[i] = c.xt[i]; hq[i] = T(0.5) * c.Qs[i][i]; hqf[i] = T(0.5) * c.Qfs[i][i]; }
         for (int j = 0; j < m; ++j) hr[j] = T(0.5) * c.Rs[j][j];
     }
+#endif
     ILQR_DEV T stage(const T *x, const T *u) const
     {
         T cx = T(0), cu = T(0);

@@ -1,14 +1,10 @@
 #!/bin/bash
-# Round-2 experiment: fused K1+K2 kernel variants (fast builds under _variants/) against the two-kernel path.
+# Round-2 experiment: shapes of the fused K1+K2 kernel (fast build under _variants/) by batch size.
 #   gpurun --timeout 900 -- 'bash scripts/exp_fused.sh > gpurun_out/exp_fused.log 2>&1'
-export QG_SOLVE_ONLY=1 QG_ITERS=${QG_ITERS:-4}
-for B in 131072 4096; do
-  echo "=== B=$B  two-kernel path (ILQR_FUSED=0)"
-  ILQR_B200_LIB=$PWD/_variants/libfast_mb1.so ILQR_FUSED=0 python scripts/quick_gpu.py $B 500 rk4 | tail -3
-  for v in mb1 mb4 mb5; do
-    echo "=== B=$B  fused NP=2 $v"
-    ILQR_B200_LIB=$PWD/_variants/libfast_$v.so ILQR_FUSED=1 python scripts/quick_gpu.py $B 500 rk4 | tail -3
-  done
-  echo "=== B=$B  fused NP=3 mb4"
-  ILQR_B200_LIB=$PWD/_variants/libfast_mb4.so ILQR_FUSED=1 ILQR_FUSED_NP=3 python scripts/quick_gpu.py $B 500 rk4 | tail -3
-done
+export QG_SOLVE_ONLY=1 ILQR_B200_LIB=$PWD/_variants/libfast.so
+run() { echo "=== B=$1 $2"; env $2 QG_ITERS=${3:-10} python scripts/quick_gpu.py $1 500 rk4 | tail -2; }
+for np in 2 3 4; do run 4096 "ILQR_FUSED_NP=$np ILQR_FUSED_MINB=1"; done
+run 4096 "ILQR_FUSED=0"
+for cfg in "ILQR_FUSED_NP=4" "ILQR_FUSED_NP=2 ILQR_FUSED_MINB=1" "ILQR_FUSED_NP=2 ILQR_FUSED_MINB=4"; do run 8192 "$cfg"; done
+for cfg in "ILQR_FUSED_NP=2 ILQR_FUSED_MINB=1" "ILQR_FUSED_NP=2 ILQR_FUSED_MINB=4" "ILQR_FUSED_NP=2 ILQR_FUSED_MINB=5" "ILQR_FUSED=0"; do run 16384 "$cfg" 6; done
+for cfg in "ILQR_FUSED_NP=2 ILQR_FUSED_MINB=4" "ILQR_FUSED_NP=2 ILQR_FUSED_MINB=5"; do run 32768 "$cfg" 6; done

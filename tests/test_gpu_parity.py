@@ -423,13 +423,13 @@ def _solve_outputs(sol):
     return [np.array(a) for a in (X, U, cost, sol.K, sol.U_ff, sol.iterations, sol.status)]
 
 
-@pytest.mark.parametrize("kind,integ,lanes", [("ua", "rk4", "0"), ("ua", "rk4", "1"), ("ua", "backward_euler", "1"),
-                                              ("double", "rk4", "0"), ("pendulum", "midpoint", "0")])
-def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, integ, lanes):
+@pytest.mark.parametrize("kind,integ,np_", [("ua", "rk4", "0"), ("ua", "rk4", "2"), ("ua", "backward_euler", "3"),
+                                            ("double", "rk4", "0"), ("pendulum", "midpoint", "2")])
+def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, integ, np_):
     """K1+K2 as one warp-specialised kernel (csrc/ilqr_kernels_fused.cuh: producers commit + linearize into a
-    shared-memory ring, the consumer scans) against the two-kernel path with the same scan (lanes = 0: one thread per
-    trajectory, lanes = 1: four lanes per trajectory): the same operation sequence, so gains, trajectories, costs and
-    control flow must agree BIT FOR BIT -- in a solve with staggered convergence, regularisation retries and
+    shared-memory ring, the consumer scans; 4, 2 or 3 producer warps per consumer) against the two-kernel path with the
+    thread-per-trajectory scan: the same operation sequence, so gains, trajectories, costs and control flow must agree
+    BIT FOR BIT -- in a solve with staggered convergence, regularisation retries and
     warm-started re-solves (commits of finished trajectories, inactive lanes, a ragged last group), on the eager and the
     lazy schedule, and in backward_pass()."""
     from class_files.iLQR_class import iLQR
@@ -439,8 +439,9 @@ def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, in
     rng = np.random.default_rng(5)
     x0 = cfg2_x0(B, seed=5)[:, :s.n_x] if kind != "pendulum" else rng.uniform(-2, 2, (B, 2))
     out = {}
-    monkeypatch.setenv("ILQR_BACKWARD_LANES", lanes)
+    monkeypatch.setenv("ILQR_BACKWARD_LANES", "0")
     monkeypatch.setenv("ILQR_SPARSE", "0")
+    monkeypatch.setenv("ILQR_FUSED_NP", np_)
     for fused in ("0", "1"):
         monkeypatch.setenv("ILQR_FUSED", fused)
         res = []

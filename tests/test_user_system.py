@@ -64,22 +64,27 @@ def test_generated_header_derivatives_match_finite_differences():
     assert abs(H[0, 0] - CARTPOLE["Q"][0] * CARTPOLE["dt"]) > 1e-6        # the barrier makes l_xx state dependent
 
 
-def test_user_library_builds_with_the_same_c_abi():
-    from class_files import _cabi
+def test_user_kernels_compile_in_process_with_nvrtc(tmp_path, monkeypatch):
+    """The kernels of a user-defined system are built by NVRTC inside this process (no nvcc, no host compiler, no GPU
+    needed to compile): six instantiations of the library's generic templates, as a cubin for sm_100a, cached by
+    content.  With PATH emptied, so that no toolchain binary could be found."""
+    from class_files import codegen
+    monkeypatch.setenv("PATH", "")
+    monkeypatch.setattr(codegen, "CACHE", str(tmp_path))
     s = cartpole("midpoint")
-    lib = s._library()
-    hdr = open(f"{ROOT}/include/ilqr_b200.h").read()
-    for name in sorted(set(re.findall(r"\b(ilqr_[a-z0-9_]+)\s*\(", hdr))):
-        assert getattr(lib, name) is not None, name
-    assert b"user-defined system" in lib.ilqr_version()
-    # the generated library holds ONE model: anything else is rejected before any CUDA call
-    p = ua_system().make_problem(N=10, B=1)
-    h = C.c_void_p()
-    assert lib.ilqr_create(C.byref(p), C.byref(h)) == -1
-    p = s.make_problem(N=10, B=1)
-    p.integrator = _cabi.INTEGRATORS["rk4"]            # compiled for midpoint
-    assert lib.ilqr_create(C.byref(p), C.byref(h)) == -1
-    assert s._library() is lib                          # cached on the instance
+    cubin, names, n, m = codegen.compile_module(s)
+    assert (n, m) == (4, 1) and cubin[:4] == b"\x7fELF" and len(names) == 6
+    for name, frag in zip(names, ("step_kernel", "commit_linearize_kernel", "cost_expansion_kernel", "backward_kernel",
+                                  "backward_kernel", "rollout_kernel")):
+        assert frag in name and "UserSys" in name or "UserCost" in name, name
+    assert "Li1E" in names[0]                                     # midpoint = integrator 1 in the template arguments
+    files = sorted(f.name for f in tmp_path.iterdir())
+    assert len(files) == 3 and files[0].endswith(".cubin")       # cubin, lowered names, generated model
+    again = codegen.compile_module(s)                             # second call: served from the cache
+    assert again[0] == cubin and again[1] == names
+    # another integrator or element type is another module
+    assert codegen.cubin_path(codegen.generate_header(s)[0], "rk4", "float64") != codegen.cubin_path(
+        codegen.generate_header(s)[0], "midpoint", "float64")
 
 
 def test_shipped_systems_keep_their_device_models():
@@ -200,6 +205,48 @@ def test_user_ua_batched_solve_matches_shipped_model(oracle):
     report, failures = member_parity(oracle, ua_oracle_problem(oracle, N, maxiter=3), x0, np.zeros((B, 1, N)),
                                      gpu_result(sol, X, U, cost))
     write_report("user_defined_ua_B256_N100_it3", report)
+    assert not failures, (failures[:5], report)
+
+
+@pytest.mark.gpu
+def test_never_seen_user_system_builds_on_this_machine_without_nvcc(oracle, tmp_path, monkeypatch):
+    """A system nobody has compiled before -- a random constant is baked into its dynamics, so its content hash is new
+    and the cache (redirected to an empty directory) cannot serve it -- is traced, differentiated, compiled by NVRTC and
+    loaded on THIS machine with PATH emptied (no nvcc reachable), then checked against central finite differences of
+    its own step and, its dynamics being the UA double pendulum's up to the random damping, against the oracle."""
+    import secrets
+    from class_files import codegen, symbolic
+    from class_files.iLQR_class import iLQR
+    from class_files.systems.system_base import System
+    from helpers import UA_OL, ua_oracle_problem
+    from user_systems import make_user_ua_class
+    monkeypatch.setenv("PATH", "")
+    monkeypatch.setattr(codegen, "CACHE", str(tmp_path))
+    d1 = 0.05 + (secrets.randbits(40) / 2.0**40) * 0.1            # never the same twice
+    phys = dict(UA_OL["phys"], d1=d1)
+    cls = make_user_ua_class(System, symbolic)
+    s = cls(dt=0.01, x_target=np.array(UA_OL["x_target"]), Q=np.diag(UA_OL["Q"]), R=np.diag(UA_OL["R"]),
+            Q_f=np.diag(UA_OL["Q_f"]), integrator="rk4", **phys)
+    assert not any(f.name.endswith(".cubin") for f in tmp_path.iterdir())
+    rng = np.random.default_rng(5)
+    xs, us = rng.uniform(-1, 1, (16, 4)), rng.uniform(-1, 1, (16, 1))
+    A, Bm = s.f_x_fcn(xs, us), s.f_u_fcn(xs, us)                  # first use: trace -> NVRTC -> module load
+    assert sum(f.name.endswith(".cubin") for f in tmp_path.iterdir()) == 1
+    for j in range(4):
+        e = np.zeros(4); e[j] = 1e-6
+        fd = (s.f_fcn(xs + e, us) - s.f_fcn(xs - e, us)) / 2e-6
+        assert np.allclose(A[:, :, j], fd, rtol=1e-6, atol=1e-8)
+    fd = (s.f_fcn(xs, us + 1e-6) - s.f_fcn(xs, us - 1e-6)) / 2e-6
+    assert np.allclose(Bm[:, :, 0], fd, rtol=1e-6, atol=1e-8)
+    # a batched solve against the oracle of the same physical parameters
+    B, N = 64, 60
+    x0 = cfg2_x0(B, seed=6)
+    sol = iLQR(s, N * 0.01, x0, np.zeros((1, N)), maxiter=3, verbose=False)
+    sol.enable_trace()
+    X, U, cost = sol.optimize_trajectory()
+    from helpers import member_parity, gpu_result
+    p = oracle.make_problem("ua", "rk4", N, 0.01, UA_OL["Q"], UA_OL["R"], UA_OL["Q_f"], UA_OL["x_target"], phys, maxiter=3)
+    report, failures = member_parity(oracle, p, x0, np.zeros((B, 1, N)), gpu_result(sol, X, U, cost))
     assert not failures, (failures[:5], report)
 
 
