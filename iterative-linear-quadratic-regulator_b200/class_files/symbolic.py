@@ -8,7 +8,8 @@ call Python, so this package traces the same three methods ONCE, symbolically: w
 
 they receive arrays of sympy symbols and return sympy expressions, from which class_files/codegen.py derives
 the analytic Jacobians/Hessians and generates the device code.  Only what dynamics/cost definitions use is
-provided: elementwise math, array construction, @ / dot, small linear solves.
+provided: elementwise math, array construction, @ / dot, small linear solves, data-dependent selects (where / maximum /
+minimum / clip).
 """
 import numpy as np
 import sympy as sp
@@ -16,6 +17,7 @@ import sympy as sp
 pi = float(np.pi)
 float32 = np.float32
 float64 = np.float64
+ndarray = np.ndarray           # annotations in reference-style subclass files (`x: jnp.ndarray`)
 
 
 def _obj(a):
@@ -113,7 +115,34 @@ def transpose(a):
 
 
 def where(cond, a, b):
-    raise NotImplementedError("data-dependent branches cannot be traced symbolically; use smooth expressions")
+    """jnp.where on traced values: a data-dependent SELECT becomes a Piecewise expression, which differentiates branch by
+    branch and is generated as a conditional expression in the device code (the select form of lax.cond; loops with a
+    data-dependent trip count, lax.while_loop, cannot be traced)."""
+    def one(c, x, y):
+        return sp.Piecewise((sp.sympify(x), c), (sp.sympify(y), True))
+    if isinstance(cond, np.ndarray) or isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        c, x, y = np.broadcast_arrays(_obj(cond), _obj(a), _obj(b))
+        return np.frompyfunc(one, 3, 1)(c, x, y)
+    return one(cond, a, b)
+
+
+def maximum(a, b):
+    return where(_gt(a, b), a, b)
+
+
+def minimum(a, b):
+    return where(_gt(a, b), b, a)
+
+
+def clip(a, lo, hi):
+    return minimum(maximum(a, lo), hi)
+
+
+def _gt(a, b):
+    if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        x, y = np.broadcast_arrays(_obj(a), _obj(b))
+        return np.frompyfunc(lambda u, v: sp.StrictGreaterThan(sp.sympify(u), sp.sympify(v)), 2, 1)(x, y)
+    return sp.StrictGreaterThan(sp.sympify(a), sp.sympify(b))
 
 
 class linalg:

@@ -87,6 +87,27 @@ def test_user_kernels_compile_in_process_with_nvrtc(tmp_path, monkeypatch):
         codegen.generate_header(s)[0], "midpoint", "float64")
 
 
+def _saturated(integ="rk4"):
+    from class_files import symbolic
+    from class_files.systems.system_base import System
+    from user_systems import make_saturated_pendulum_class
+    cls = make_saturated_pendulum_class(System, symbolic)
+    return cls(dt=0.01, x_target=np.array([np.pi, 0.0]), Q=np.diag([1.0, 0.1]), R=np.diag([0.5]), Q_f=np.diag([50.0, 5.0]),
+               integrator=integ)
+
+
+def test_data_dependent_selects_are_traced_as_conditionals(tmp_path, monkeypatch):
+    """jnp.where / clip in user methods: traced as Piecewise, differentiated branch by branch, generated as conditional
+    expressions, compiled by NVRTC"""
+    from class_files import codegen
+    monkeypatch.setattr(codegen, "CACHE", str(tmp_path))
+    s = _saturated()
+    text, n, m = codegen.generate_header(s)
+    assert (n, m) == (2, 1) and text.count("?") >= 4            # saturation in f and B_c, wall in l, l_x, l_xx
+    cubin, names, _, _ = codegen.compile_module(s)
+    assert cubin[:4] == b"\x7fELF"
+
+
 def test_shipped_systems_keep_their_device_models():
     s = ua_system()
     assert not s._is_user_defined() and s._device_model()[0] == "ua_double_pendulum"
@@ -248,6 +269,36 @@ def test_never_seen_user_system_builds_on_this_machine_without_nvcc(oracle, tmp_
     p = oracle.make_problem("ua", "rk4", N, 0.01, UA_OL["Q"], UA_OL["R"], UA_OL["Q_f"], UA_OL["x_target"], phys, maxiter=3)
     report, failures = member_parity(oracle, p, x0, np.zeros((B, 1, N)), gpu_result(sol, X, U, cost))
     assert not failures, (failures[:5], report)
+
+
+@pytest.mark.gpu
+def test_user_system_with_data_dependent_selects_vs_finite_differences():
+    """saturated torque (clip) and a one-sided cost wall (where): every branch of the generated derivatives against
+    central finite differences of the generated step / cost, and a batched solve that improves every member"""
+    from class_files.iLQR_class import iLQR
+    s = _saturated()
+    rng = np.random.default_rng(9)
+    xs = rng.uniform(-2.5, 2.5, (64, 2))
+    us = rng.uniform(-4.0, 4.0, (64, 1))                              # half of them beyond the saturation
+    keep = (np.abs(np.abs(us[:, 0]) - 2.0) > 1e-3) & (np.abs(xs[:, 1] - 1.0) > 1e-3)   # away from the kinks
+    xs, us = xs[keep], us[keep]
+    assert (np.abs(us[:, 0]) > 2).any() and (np.abs(us[:, 0]) < 2).any() and (xs[:, 1] > 1).any() and (xs[:, 1] < 1).any()
+    A, Bm, lx, lxx = s.f_x_fcn(xs, us), s.f_u_fcn(xs, us), s.l_x_fcn(xs, us), s.l_xx_fcn(xs, us)
+    h = 1e-6
+    for j in range(2):
+        e = np.zeros(2); e[j] = h
+        assert np.allclose(A[:, :, j], (s.f_fcn(xs + e, us) - s.f_fcn(xs - e, us)) / (2 * h), rtol=1e-6, atol=1e-8)
+        assert np.allclose(lx[:, j], (s.l_fcn(xs + e, us) - s.l_fcn(xs - e, us)) / (2 * h), rtol=1e-5, atol=1e-9)
+        assert np.allclose(lxx[:, :, j], (s.l_x_fcn(xs + e, us) - s.l_x_fcn(xs - e, us)) / (2 * h), rtol=1e-5, atol=1e-9)
+    fd = (s.f_fcn(xs, us + h) - s.f_fcn(xs, us - h)) / (2 * h)
+    assert np.allclose(Bm[:, :, 0], fd, rtol=1e-6, atol=1e-8)
+    assert np.all(Bm[np.abs(us[:, 0]) > 2, :, 0] == 0.0)                # saturated: the control has no effect
+    B, N = 128, 80
+    x0 = rng.uniform(-1.0, 1.0, (B, 2))
+    sol = iLQR(s, N * 0.01, x0, np.zeros((1, N)), maxiter=10, verbose=False)
+    c0 = sol.forward_pass(x0, 0.0, np.zeros((B, 2, N + 1)), np.zeros((B, 1, N)), np.zeros((B, 1, N)), np.zeros((B, N, 1, 2)))[2]
+    X, U, cost = sol.optimize_trajectory()
+    assert np.all(cost <= c0) and np.all(np.isfinite(cost))
 
 
 @pytest.mark.gpu

@@ -81,3 +81,28 @@ def make_user_ua_class(System, jnp):
             return 0.5 * dx.T @ self.Q_f @ dx
 
     return UserUADoublePendulum
+
+
+def make_saturated_pendulum_class(System, jnp):
+    class SaturatedPendulum(System):
+        """A pendulum with data-dependent selects in BOTH user methods: the torque saturates (jnp.clip) and the cost has
+        a one-sided quadratic wall (jnp.where) -- what the reference would write with jnp.where / lax.cond."""
+
+        def __init__(self, dt, x_target, Q, R, Q_f, u_max=2.0, wall=1.0, use_jit=True, integrator="rk4", **kw):
+            self.x_target, self.Q, self.R, self.Q_f, self.u_max, self.wall = x_target, Q, R, Q_f, u_max, wall
+            super().__init__(n_x=2, n_u=1, dt=dt, use_jit=use_jit, integrator=integrator, **kw)
+
+        def _f_cont_fcn(self, x, u):
+            tau = jnp.clip(u[0], -self.u_max, self.u_max)
+            return jnp.array([x[1], tau - 0.05 * x[1] - 9.81 * jnp.sin(x[0])])
+
+        def _l_fcn(self, x, u):
+            dx = x - self.x_target
+            over = jnp.where(x[1] > self.wall, (x[1] - self.wall) ** 2, 0.0)
+            return (0.5 * dx.T @ self.Q @ dx + 0.5 * u.T @ self.R @ u + 10.0 * over) * self.dt
+
+        def _l_f_fcn(self, x):
+            dx = x - self.x_target
+            return 0.5 * dx.T @ self.Q_f @ dx
+
+    return SaturatedPendulum
