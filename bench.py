@@ -301,11 +301,25 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE line, the JSON: everything else written to fd 1 while the bench runs (NCCL's version
+    # banner, library chatter) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, in front of the one JSON line this prints
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # The path's only exchange is a 64 KB all-gather per step, issued asynchronously.  An NCCL kernel that waits for
+        # a peer spins on the SMs it occupies; capped to ONE CTA it cannot take more than one SM from the latency-bound
+        # solve kernels it runs beside (default channel counts cost 14 % of the step at N=2).
+        os.environ.setdefault("NCCL_MAX_CTAS", "1")
+        os.environ.setdefault("NCCL_MIN_CTAS", "1")
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = 1
+            opts.config.min_ctas = 1
+        except Exception:
+            opts = None
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     from class_files.iLQR_class import iLQR
     from class_files.systems.UA_double_pendulum_sys import MyUADoublePendulum
     from class_files import _cabi
@@ -522,7 +536,7 @@ def main():
            "traj_iterations_per_step": units / args.steps, "e2e": e2e,
            "gpu_launches": int(launches), "roofline": roof, "roofline_backward": roof_b, "kernels": kern,
            "large_batch": large, "cpu_baseline": cpu, "clocks": clocks}
-    print(json.dumps(out))
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
