@@ -134,7 +134,6 @@ struct Handle {
     int env_rollout_bs;       // ILQR_ROLLOUT_BS: 0 [auto] or a block size
     int env_fused;            // ILQR_FUSED: -1 [auto: fused K1+K2 inside ilqr_solve where it is the faster form], 0 never,
                               // 1 wherever the model allows (also ilqr_backward_pass)
-    int env_fused_np;         // ILQR_FUSED_NP: producer warps per consumer warp: 0 [auto: by batch size], 2, 3, 4
     int env_fused_minb;       // ILQR_FUSED_MINB: 0 [auto: by batch size], 1 = uncapped registers, 4 / 5 = capped for 4 / 5 blocks per SM
     int env_check_every;      // ILQR_CHECK_EVERY: iterations enqueued between host polls of the active count [8]
     long env_sparse_thresh;   // ILQR_SPARSE_THRESH / ILQR_SPARSE_ALL: -1 [auto] or the thresholds of SparseArgs
@@ -450,22 +449,19 @@ static int launch_fused(Handle *h, const void *phi, void *X, void *U, const void
             using std::integral_constant;
             using I1 = integral_constant<int, 1>;
             using I2 = integral_constant<int, 2>;
-            using I3 = integral_constant<int, 3>;
             using I4 = integral_constant<int, 4>;
             using I5 = integral_constant<int, 5>;
-            // Shape by batch size, so that every block is resident at once (one block = 32 trajectories) and the
-            // producers keep up with the consumer:
-            //   <= 2 blocks per SM: 4 producer warps per consumer, registers uncapped -- the scan is latency bound, the SMs
-            //      are nearly empty, and 2 producers deliver a step only every ~1070 cycles against the consumer's ~800
-            //   <= 4 blocks per SM: 2 producers, registers capped for 4 blocks per SM (164, no spills)
-            //   more: 2 producers, capped for 5 blocks per SM (128 registers, 15 warps per SM for the FP64 pipe)
-            // ILQR_FUSED_NP / ILQR_FUSED_MINB override (experiments).
-            int np = h->env_fused_np, mb = h->env_fused_minb;
-            if (np == 0) np = groups <= 148 * 2 ? 4 : 2;
-            if (mb == 0) mb = groups <= 148 * 2 ? 1 : (groups <= 148 * 4 ? 4 : 5);
-            if (np == 4) go(I4{}, I4{}, I1{});
-            else if (np == 3) go(I3{}, I3{}, I1{});
-            else if (mb >= 5) go(I2{}, I4{}, I5{});
+            // Two producer warps per consumer (three or four gain nothing: at small batches the kernel runs at the speed
+            // of the consumer's dependent chain, 0.273 ms at B=4096 = the thread-per-trajectory scan alone, with the
+            // linearization hidden completely; 4 producers on single ring stages: 0.352 ms).  The register cap follows
+            // the batch so that every block is resident at once (one block = 32 trajectories = 96 threads):
+            //   <= 3 blocks per SM: uncapped (194 registers)            B=8192: 0.475 vs 0.490 ms capped for 4
+            //   <= 4 blocks per SM: capped for 4 (164, no spills)       B=16384: 0.861 vs 0.925 ms uncapped
+            //   more: capped for 5 (128 registers, 15 warps per SM)     B=131072: 5.37 vs 5.50 (4) vs 6.16 ms (uncapped)
+            // ILQR_FUSED_MINB overrides (experiments).
+            int mb = h->env_fused_minb;
+            if (mb == 0) mb = groups <= 148 * 3 ? 1 : (groups <= 148 * 4 ? 4 : 5);
+            if (mb >= 5) go(I2{}, I4{}, I5{});
             else if (mb == 4) go(I2{}, I4{}, I4{});
             else go(I2{}, I4{}, I1{});
             ILQR_CHECK_LAUNCH(h);
@@ -825,7 +821,6 @@ static int create_handle(const ilqr_problem_t *p, UserModule *umod, ilqr_handle_
         h->env_rollout_bs = (e = getenv("ILQR_ROLLOUT_BS")) && atoi(e) >= 32 ? atoi(e) / 32 * 32 : 0;
         h->env_check_every = (e = getenv("ILQR_CHECK_EVERY")) && atoi(e) > 0 ? atoi(e) : 8;
         h->env_fused = (e = getenv("ILQR_FUSED")) ? (atoi(e) != 0) : -1;
-        h->env_fused_np = (e = getenv("ILQR_FUSED_NP")) && atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 0;
         h->env_fused_minb = (e = getenv("ILQR_FUSED_MINB")) ? atoi(e) : 0;
     }
     h->env_sparse_thresh = (e = getenv("ILQR_SPARSE_THRESH")) ? atol(e) : -1;
@@ -1149,7 +1144,11 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
                 unsigned int *n_spec = &ctl->n_active[2 * (p.maxiter + 2)];
                 sp.cap = h->spec_cap;
                 sp.n2 = n2;
-                sp.threshold = n1 - 4 > 1 ? n1 - 4 : 1;
+                // listed for the next iteration: accepted try index >= n1 - 5 this time.  On config 2 (10 tries, n1 = 9)
+                // that is ~17 % of the batch, within the ~1000 spare slots, and it catches the trajectories that will need
+                // the deferred try all but once per ten iterations (n1 - 4: 6 %, twice as many misses; every miss costs a
+                // latency-bound second wave, 0.37 ms at N = 500)
+                sp.threshold = n1 - 5 > 1 ? n1 - 5 : 1;
                 sp.list_cur = lists + (size_t)(it & 1) * B;
                 sp.list_next = lists + (size_t)((it + 1) & 1) * B;
                 sp.count_cur = n_spec + it;

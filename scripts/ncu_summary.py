@@ -25,6 +25,15 @@ KEYS = [
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    # shared memory: wavefronts (bank-conflict replays included), their share of the LSU data pipe, bank conflicts
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
+    "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
 ]
 
 
@@ -57,12 +66,14 @@ def traffic(rep, key, out):
         tot = 0.0
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(r[idx[k]].replace(",", "")) * scale[units[idx[k]]]
-        if cls == "linearize":
+        # an iteration opens with K1, or -- K1 fused into the scan -- with the fused backward kernel
+        if cls == "linearize" or (cls == "backward" and "fused" in name):
             buckets.append({})
         if buckets:
             buckets[-1][cls] = buckets[-1].get(cls, 0.0) + tot
-    full = [b for b in buckets if {"linearize", "backward", "rollout"} <= set(b)]
-    acc = {c: [b[c] for b in full] for c in ("linearize", "backward", "rollout")} if full else {}
+    full = [b for b in buckets if {"backward", "rollout"} <= set(b)]
+    classes = [c for c in ("linearize", "backward", "rollout") if full and all(c in b for b in full)]
+    acc = {c: [b[c] for b in full] for c in classes}
     d = json.load(open(out)) if os.path.exists(out) else {}
     d[key] = {c: sum(v) / len(v) for c, v in acc.items()}
     # duration-weighted FP64 pipe utilisation per kernel class (a utilisation read under the profiler, not a timing)

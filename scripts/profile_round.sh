@@ -1,10 +1,10 @@
 #!/bin/bash
-# One GPU call that refreshes the evidence under profiles/ for a round tag (default r01f):
-#   gpurun --timeout 1500 -- 'bash scripts/profile_round.sh r01f'
+# One GPU call that refreshes the evidence under profiles/ for a round tag (default r02):
+#   gpurun --timeout 1500 -- 'bash scripts/profile_round.sh r02'
 # bench line, reference arm, ncu launch list, ncu --set full captures at B=4096 (kept: source view) and
 # B=131072 (summarised on the box, the 60 MB report is not brought back), other configurations.
 # PROFILE_SHORT=1 skips the reference arm and the other configurations.
-tag=${1:-r01f}
+tag=${1:-r02}
 out=gpurun_out
 set -x
 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err
@@ -16,5 +16,8 @@ python scripts/ncu_summary.py $out/prof_$tag.ncu-rep --traffic B4096 $out/traffi
 QG_SOLVE_ONLY=1 QG_NO_REPS=1 QG_ITERS=2 ncu --set full --clock-control none -k regex:"rollout|linearize|backward" -c 14 -o /tmp/prof_${tag}_large -f python scripts/quick_gpu.py 131072 500 rk4 > $out/ncu3_$tag.log 2>&1
 python scripts/ncu_summary.py /tmp/prof_${tag}_large.ncu-rep > $out/${tag}_ncu_full_B131072.txt
 python scripts/ncu_summary.py /tmp/prof_${tag}_large.ncu-rep --traffic B131072 $out/traffic_$tag.json
+# config 4 (LTV, n=12, m=4): the sixteen-lane Riccati kernel and the n=12 rollout, incl. the shared-memory counters
+QG_SOLVE_ONLY=1 QG_NO_REPS=1 QG_ITERS=1 QG_ALPHAS=4 ncu --set full --clock-control none --import-source on -k regex:"backward_ltv|rollout" -c 4 -o $out/prof_${tag}_ltv -f python scripts/quick_gpu.py 32768 1000 ltv > $out/ncu4_$tag.log 2>&1
+python scripts/ncu_summary.py $out/prof_${tag}_ltv.ncu-rep > $out/${tag}_ncu_full_ltv_B32768.txt
 [ -n "$PROFILE_SHORT" ] || python scripts/bench_configs.py > $out/configs_$tag.json 2> $out/configs_$tag.err
 ls -la $out/*$tag*

@@ -42,6 +42,9 @@ def main():
     else:
         n, m = 4, 1
         x0 = cfg2_x0(B)
+        if os.environ.get("QG_SHARD"):          # "r,w": rank r's shard of the w*B batch bench.py uses at --gpus w
+            r, w = (int(v) for v in os.environ["QG_SHARD"].split(","))
+            x0 = cfg2_x0(B * w)[r * B:(r + 1) * B]
         sol = iLQR(ua_system(integ), N * 0.01, x0, np.zeros((1, N)), tol=0.0, maxiter=iters, verbose=False, n_alpha=n_alpha)
         bytes_k = {"linearize": 240, "backward": 240, "rollout": 120}
     phi_p = D.ptr(sol._phi)

@@ -423,11 +423,11 @@ def _solve_outputs(sol):
     return [np.array(a) for a in (X, U, cost, sol.K, sol.U_ff, sol.iterations, sol.status)]
 
 
-@pytest.mark.parametrize("kind,integ,np_", [("ua", "rk4", "0"), ("ua", "rk4", "2"), ("ua", "backward_euler", "3"),
-                                            ("double", "rk4", "0"), ("pendulum", "midpoint", "2")])
-def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, integ, np_):
+@pytest.mark.parametrize("kind,integ,minb", [("ua", "rk4", "0"), ("ua", "rk4", "5"), ("ua", "backward_euler", "4"),
+                                             ("double", "rk4", "0"), ("pendulum", "midpoint", "5")])
+def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, integ, minb):
     """K1+K2 as one warp-specialised kernel (csrc/ilqr_kernels_fused.cuh: producers commit + linearize into a
-    shared-memory ring, the consumer scans; 4, 2 or 3 producer warps per consumer) against the two-kernel path with the
+    shared-memory ring, the consumer scans; in each of its register-capped builds) against the two-kernel path with the
     thread-per-trajectory scan: the same operation sequence, so gains, trajectories, costs and control flow must agree
     BIT FOR BIT -- in a solve with staggered convergence, regularisation retries and
     warm-started re-solves (commits of finished trajectories, inactive lanes, a ragged last group), on the eager and the
@@ -441,7 +441,7 @@ def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, in
     out = {}
     monkeypatch.setenv("ILQR_BACKWARD_LANES", "0")
     monkeypatch.setenv("ILQR_SPARSE", "0")
-    monkeypatch.setenv("ILQR_FUSED_NP", np_)
+    monkeypatch.setenv("ILQR_FUSED_MINB", minb)
     for fused in ("0", "1"):
         monkeypatch.setenv("ILQR_FUSED", fused)
         res = []
