@@ -17,7 +17,8 @@ QG_SOLVE_ONLY=1 QG_NO_REPS=1 QG_ITERS=2 ncu --set full --clock-control none -k r
 python scripts/ncu_summary.py /tmp/prof_${tag}_large.ncu-rep > $out/${tag}_ncu_full_B131072.txt
 python scripts/ncu_summary.py /tmp/prof_${tag}_large.ncu-rep --traffic B131072 $out/traffic_$tag.json
 # config 4 (LTV, n=12, m=4): the sixteen-lane Riccati kernel and the n=12 rollout, incl. the shared-memory counters
-QG_SOLVE_ONLY=1 QG_NO_REPS=1 QG_ITERS=1 QG_ALPHAS=4 ncu --set full --clock-control none --import-source on -k regex:"backward_ltv|rollout" -c 4 -o $out/prof_${tag}_ltv -f python scripts/quick_gpu.py 32768 1000 ltv > $out/ncu4_$tag.log 2>&1
-python scripts/ncu_summary.py $out/prof_${tag}_ltv.ncu-rep > $out/${tag}_ncu_full_ltv_B32768.txt
+QG_SOLVE_ONLY=1 QG_NO_REPS=1 QG_ITERS=1 QG_ALPHAS=4 ncu --set full --clock-control none --import-source on -k regex:"backward_ltv|rollout" -c 4 -o /tmp/prof_${tag}_ltv -f python scripts/quick_gpu.py 32768 1000 ltv > $out/ncu4_$tag.log 2>&1
+python scripts/ncu_summary.py /tmp/prof_${tag}_ltv.ncu-rep > $out/${tag}_ncu_full_ltv_B32768.txt
 [ -n "$PROFILE_SHORT" ] || python scripts/bench_configs.py > $out/configs_$tag.json 2> $out/configs_$tag.err
-ls -la $out/*$tag*
+# only the B=4096 report (source view of the hot kernels) travels back: gpurun_out/ is limited to 64 MiB
+ls -la $out/*$tag*; du -sh $out
