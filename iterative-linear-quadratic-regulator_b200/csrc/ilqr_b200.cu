@@ -135,6 +135,7 @@ struct Handle {
     int env_fused;            // ILQR_FUSED: -1 [auto: fused K1+K2 inside ilqr_solve where it is the faster form], 0 never,
                               // 1 wherever the model allows (also ilqr_backward_pass)
     int env_fused_minb;       // ILQR_FUSED_MINB: 0 [auto: by batch size], 1 = uncapped registers, 4 / 5 = capped for 4 / 5 blocks per SM
+    int env_ltv_lanes;        // ILQR_LTV_LANES: 0 [auto: by batch size], 4 (register-tiled kernel) or 16 (one column per lane)
     int env_check_every;      // ILQR_CHECK_EVERY: iterations enqueued between host polls of the active count [8]
     long env_sparse_thresh;   // ILQR_SPARSE_THRESH / ILQR_SPARSE_ALL: -1 [auto] or the thresholds of SparseArgs
     long env_sparse_all;
@@ -266,7 +267,14 @@ template <typename T, class Sys, class F> static int dispatch_integ(const Handle
 
 template <typename T, class F> static int dispatch_model(const Handle *h, F &&f)
 {
-#ifdef ILQR_FAST_BUILD
+#if defined(ILQR_FAST_BUILD) && ILQR_FAST_BUILD == 2     // LTV model only
+    if (h->p.model == ILQR_LTV) {
+        auto sys = make_ltv<T>(h->p);
+        auto qc = make_cost<T, 12, 4>(h->p);
+        return f(T(0), sys, qc, std::integral_constant<int, EULER>{});
+    }
+    return ILQR_E_INVALID;
+#elif defined(ILQR_FAST_BUILD)
     if (h->p.model == ILQR_UA_DOUBLE_PENDULUM) return dispatch_integ<T>(h, make_double<T, 1>(h->p), f);
     return ILQR_E_INVALID;
 #else
@@ -476,20 +484,37 @@ static int launch_fused(Handle *h, const void *phi, void *X, void *U, const void
 static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const void *U, void *K, void *k,
                                const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr)
 {
-#if defined(ILQR_FAST_BUILD)
+#if defined(ILQR_FAST_BUILD) && ILQR_FAST_BUILD != 2
     return ILQR_E_INVALID;
 #else
     constexpr int TPB = 16;
     auto go = [&](auto tz) -> int {
         using T = decltype(tz);
-        const size_t smem = sizeof(T) * (size_t)(504 * TPB + 48 + 144 + 16 + 288);
+        // sixteen lanes per trajectory, one column each: the latency-bound regime of small batches (B=2048, N=1000: 4.0 vs
+        // 7.5 ms per pass); four lanes x four columns, register tiled: large batches (B=32768: 39.6 vs 47.1 ms)
+        const bool lanes16 = h->env_ltv_lanes ? h->env_ltv_lanes == 16 : h->p.B < 8192;
+        if (lanes16) {
+            const size_t smem = sizeof(T) * (size_t)(504 * TPB + 48 + 144 + 16 + 288);
+            if (!h->smem_ltv) {
+                cudaError_t e = cudaFuncSetAttribute(backward_ltv_kernel<T, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)smem);
+                if (e != cudaSuccess) { h->last_cuda = (int)e; return ILQR_E_CUDA; }
+                h->smem_ltv = 1;
+            }
+            backward_ltv_kernel<T, TPB><<<grid_for(h->p.B, TPB), TPB * 16, smem, st>>>(
+                make_ltv<T>(h->p), make_cost<T, 12, 4>(h->p), h->p.N, h->p.B, (const T *)phi, (const T *)X, (const T *)U,
+                (T *)K, (T *)k, active, gate, (const T *)mu);
+            ILQR_CHECK_LAUNCH(h);
+            return ILQR_OK;
+        }
+        const size_t smem = sizeof(T) * (size_t)(Ltv4Layout::PER_TRAJ * TPB + Ltv4Layout::CONST);
         if (!h->smem_ltv) {
-            cudaError_t e = cudaFuncSetAttribute(backward_ltv_kernel<T, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaError_t e = cudaFuncSetAttribute(backward_ltv4_kernel<T, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)smem);
             if (e != cudaSuccess) { h->last_cuda = (int)e; return ILQR_E_CUDA; }
             h->smem_ltv = 1;
         }
-        backward_ltv_kernel<T, TPB><<<grid_for(h->p.B, TPB), TPB * 16, smem, st>>>(
+        backward_ltv4_kernel<T, TPB><<<grid_for(h->p.B, TPB), TPB * 4, smem, st>>>(
             make_ltv<T>(h->p), make_cost<T, 12, 4>(h->p), h->p.N, h->p.B, (const T *)phi, (const T *)X, (const T *)U,
             (T *)K, (T *)k, active, gate, (const T *)mu);
         ILQR_CHECK_LAUNCH(h);
@@ -821,6 +846,7 @@ static int create_handle(const ilqr_problem_t *p, UserModule *umod, ilqr_handle_
         h->env_rollout_bs = (e = getenv("ILQR_ROLLOUT_BS")) && atoi(e) >= 32 ? atoi(e) / 32 * 32 : 0;
         h->env_check_every = (e = getenv("ILQR_CHECK_EVERY")) && atoi(e) > 0 ? atoi(e) : 8;
         h->env_fused = (e = getenv("ILQR_FUSED")) ? (atoi(e) != 0) : -1;
+        h->env_ltv_lanes = (e = getenv("ILQR_LTV_LANES")) && (atoi(e) == 16 || atoi(e) == 4) ? atoi(e) : 0;
         h->env_fused_minb = (e = getenv("ILQR_FUSED_MINB")) ? atoi(e) : 0;
     }
     h->env_sparse_thresh = (e = getenv("ILQR_SPARSE_THRESH")) ? atol(e) : -1;

@@ -670,4 +670,346 @@ backward_ltv_kernel(const __grid_constant__ LtvSys<T> sys, const __grid_constant
     }
 }
 
+// K2 for the LTV model, register-tiled (round 2).  The sixteen-lane kernel above is bound by shared-memory bandwidth:
+// every lane re-reads all of V_xx and all of [A_t|B_t]' for ONE column (ncu: the LSU data pipe, not the FP64 pipe).
+// Here FOUR lanes share a trajectory and lane c owns FOUR columns of [A_t | B_t]: 4c .. 4c+3 (lanes 0-2: columns of
+// A_t, lane 3: the four columns of B_t), so every value read from shared memory feeds four FMAs instead of one:
+//   A  build the own columns of A_t = I + dt (Ac + w_t E) pairwise from the block's constant tables, publish them as
+//      rows of MT = [A_t|B_t]' ; q = own columns' dot with V_x                             (iLQR_class.py:100-101)
+//   B  W[:, own] = V_xx M[:, own]            two passes over V_xx, 2 columns x 12 rows of accumulators each
+//   C  G[r][own] = MT[r][:] W[:, own]  r = 0..15: rows < 12 give Q_xx[:, own] (written over V_xx[:, own], which nobody
+//      reads any more), rows >= 12 give Q_ux[:, own] -- or, in lane 3, Q_uu                          (:102-104)
+//   D  exchange Q_ux, Q_uu, Q_u through shared memory; every lane factors the 4x4 Q_uu (LU with partial pivoting, as
+//      the reference's solve) and solves for its own four right-hand sides: K[:, own] (lane 3: k)    (:109-110)
+//   E  V_xx[:, own] += Q_ux' K[:, own],  V_x[own] = Q_x[own] + K[:, own]' Q_u                       (:113-114)
+// Lanes of a trajectory sit in one warp (__syncwarp between the phases); one block barrier per step for the staged,
+// coalesced gain stores and the x_t, u_t prefetch, as in the sixteen-lane kernel.
+#ifndef ILQR_LTV4_MINBLOCKS
+#define ILQR_LTV4_MINBLOCKS 1
+#endif
+// Shared-memory layout of the register-tiled LTV kernel.  A 128-bit shared load is served eight lanes at a time, i.e. two
+// trajectories (four lanes each) per phase: the per-trajectory strides are == 16 bytes (mod 128) so that the two never
+// meet in a bank, and the tables whose rows are owned by different lanes (MT, AcdT, EdT: rows 4c..4c+3 belong to lane c)
+// skew each group of four rows by 16 bytes for the same reason.
+struct Ltv4Layout {
+    static constexpr int VXX = 146;        // [12][12] + 2
+    static constexpr int MT = 162;         // 12 rows of 12, group of four rows skewed by 2: row r at r*12 + 2*(r/4); 150 + 12
+    static constexpr int VX = 14, QUX = 66 /* [12][4] transposed, each lane's four rows skewed by 2 */, QUU = 18, QU = 6, XS = 18;
+    static constexpr int KROW = 17;        // gain stage [52][KROW >= TPB]: rows 4 apart (lanes c, c+1) land 32 bytes apart
+    static constexpr int PER_TRAJ = VXX + MT + VX + QUX + QUU + QU + 2 * XS;
+    static constexpr int KSTAGE = 2 * 52 * KROW;
+    static constexpr int TAB = 150;        // AcdT / EdT: 12 skewed rows
+    static constexpr int CONST = KSTAGE + 48 + 2 * TAB + 144 + 16;
+    __host__ __device__ static constexpr int row(int r) { return r * 12 + 2 * (r >> 2); }
+};
+
+template <typename T, int TPB>
+__global__ void __launch_bounds__(TPB * 4, ILQR_LTV4_MINBLOCKS)
+backward_ltv4_kernel(const __grid_constant__ LtvSys<T> sys, const __grid_constant__ QuadCost<T, 12, 4> qc, int N, int B,
+                     const T *__restrict__ phi, const T *__restrict__ X, const T *__restrict__ U, T *__restrict__ K,
+                     T *__restrict__ k, const int *__restrict__ active, const unsigned int *__restrict__ gate,
+                     const T *__restrict__ mu)
+{
+    constexpr int n = 12, m = 4, NT = TPB * 4, ROWS = n * m + m;     // 52 gain rows per step
+    using V2 = typename Vec2<T>::type;
+    using LY = Ltv4Layout;
+    static_assert(TPB <= LY::KROW, "gain stage rows hold TPB trajectories");
+    extern __shared__ __align__(16) unsigned char ltv4_raw[];
+    T *sm = reinterpret_cast<T *>(ltv4_raw);
+    T *VxxS = sm;                               // [TPB] row-major V_xx (Q_xx during a step)
+    T *MTS = VxxS + TPB * LY::VXX;              // [TPB] MT[r][l] = A_t[l][r], r < 12 (skewed rows)
+    T *VxS = MTS + TPB * LY::MT;                // [TPB][12]
+    T *QuxS = VxS + TPB * LY::VX;               // [TPB][12][4]   Q_ux transposed: QuxT[i][u]
+    T *QuuS = QuxS + TPB * LY::QUX;             // [TPB][4][4]
+    T *QuS = QuuS + TPB * LY::QUU;              // [TPB][4]
+    T *xsS = QuS + TPB * LY::QU;                // [2][TPB][16]   x_t (12), u_t (4), double buffered
+    T *KS = xsS + 2 * TPB * LY::XS;             // [2][52][KROW]  gain stage, double buffered
+    T *BdT = KS + LY::KSTAGE;               // [4][12]        rows 12..15 of MT: BdT[j][l] = dt Bc[l][j]   (constant)
+    T *AcdT = BdT + 48;                         // skewed rows    AcdT[c][l] = delta(l,c) + dt Ac[l][c]
+    T *EdT = AcdT + LY::TAB;                    // skewed rows    EdT[c][l]  = dt E[l][c]
+    T *QsS = EdT + LY::TAB;                     // [12][12]       symmetrised Q times dt
+    T *RsS = QsS + 144;                         // [4][4]         symmetrised R times dt
+    __shared__ int vflag[TPB];
+    if (gate && *gate == 0u) return;
+    const int tid = threadIdx.x, s = tid >> 2, c = tid & 3;
+    const int b0 = blockIdx.x * TPB;
+    const int b_raw = b0 + s;
+    const bool valid = b_raw < B && (!active || active[b_raw] != 0);
+    if (__syncthreads_or(valid) == 0) return;
+    const int b = b_raw < B ? b_raw : B - 1;        // out-of-range / inactive slots compute on a copy, never store
+    if (c == 0) vflag[s] = valid;
+    for (int e = tid; e < 48; e += NT) BdT[e] = qc.dt * sys.Bc[e % 12][e / 12];
+    for (int e = tid; e < 144; e += NT) {
+        const int cc = e / 12, l = e % 12;
+        QsS[e] = qc.Qs[cc][l] * qc.dt;
+        AcdT[LY::row(cc) + l] = (cc == l ? T(1) : T(0)) + qc.dt * sys.Ac[l][cc];
+        EdT[LY::row(cc) + l] = qc.dt * sys.E[l][cc];
+    }
+    if (tid < 16) RsS[tid] = qc.Rs[tid >> 2][tid & 3] * qc.dt;
+    // staged loads: element e = row * TPB + bb -> row (x_0..x_11, u_0..u_3) of trajectory b0 + bb
+    auto fetch = [&](int t, int e) -> T {
+        const int row = e / TPB, bb = e % TPB;
+        const int lb = min(b0 + bb, B - 1);
+        if (row < n) return X[((size_t)t * n + row) * B + lb];
+        return t < N ? U[((size_t)t * m + (row - n)) * B + lb] : T(0);
+    };
+    // 16 TPB values per step over 4 TPB threads: four per thread, fetched at the top of a step into registers and put
+    // into the other staging buffer just before the step's block barrier (the global latency hides behind the step)
+    T pre[4];
+    auto fetch_pre = [&](int t) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pre[i] = fetch(t, tid + i * NT);
+    };
+    auto store_pre = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * NT;
+            xsS[(buf * TPB + e % TPB) * LY::XS + e / TPB] = pre[i];
+        }
+    };
+    const T ph = phi ? phi[b] : T(0);
+    const T mu_b = mu ? mu[b] : T(0);                                    // regularisation (RegArgs), 0 in the reference
+    T *Vxx = VxxS + s * LY::VXX, *MT = MTS + s * LY::MT, *Vx = VxS + s * LY::VX, *QuxT = QuxS + s * LY::QUX,
+      *Quu = QuuS + s * LY::QUU, *Qu = QuS + s * LY::QU;
+    // terminal condition (iLQR_class.py:136-138): V_x = Q_f (x_N - x_target), V_xx = Q_f ; lane c fills rows 3c..3c+2
+    fetch_pre(N);
+    store_pre(0);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int i = 3 * c + r;
+        T g = T(0);
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            g += qc.Qfs[i][j] * (xsS[s * LY::XS + j] - qc.xt[j]);
+            Vxx[i * 12 + j] = qc.Qfs[i][j];
+        }
+        Vx[i] = g;
+    }
+    __syncthreads();
+    fetch_pre(N - 1);
+    store_pre(1);                        // buffer index of step t = (N - t) & 1
+    __syncthreads();
+    for (int t = N - 1; t >= 0; --t) {
+        const int buf = (N - t) & 1;
+        const T *xs = xsS + (buf * TPB + s) * LY::XS;
+        const T w = sys.time_scalar(t, ph);
+        if (t > 0) fetch_pre(t - 1);
+        // ---- A + B: own columns of [A_t|B_t] two at a time; W[:, own] = V_xx M[:, own]; q = M[:, own]' V_x ----
+        T Wc[4][n], q[4];
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+            T Mc[2][n];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = 2 * pr + jj;
+                if (c < 3) {
+                    const int ro = LY::row(4 * c + j);
+                    const T *ar = AcdT + ro, *er = EdT + ro;
+#pragma unroll
+                    for (int l = 0; l < n; l += 2) {
+                        const V2 a = *reinterpret_cast<const V2 *>(ar + l), e = *reinterpret_cast<const V2 *>(er + l);
+                        Mc[jj][l] = fma_t(w, e.x, a.x);
+                        Mc[jj][l + 1] = fma_t(w, e.y, a.y);
+                        *reinterpret_cast<V2 *>(MT + ro + l) = V2{Mc[jj][l], Mc[jj][l + 1]};
+                    }
+                } else {
+#pragma unroll
+                    for (int l = 0; l < n; l += 2) {
+                        const V2 v = *reinterpret_cast<const V2 *>(BdT + j * 12 + l);
+                        Mc[jj][l] = v.x;
+                        Mc[jj][l + 1] = v.y;
+                    }
+                }
+            }
+            {
+                T q0 = T(0), q1 = T(0), q2 = T(0), q3 = T(0);     // two chains per column
+#pragma unroll
+                for (int l = 0; l < n; l += 2) {
+                    const V2 v = *reinterpret_cast<const V2 *>(Vx + l);
+                    q0 += Mc[0][l] * v.x;
+                    q1 += Mc[1][l] * v.x;
+                    q2 += Mc[0][l + 1] * v.y;
+                    q3 += Mc[1][l + 1] * v.y;
+                }
+                q[2 * pr] = q0 + q2;
+                q[2 * pr + 1] = q1 + q3;
+            }
+            // four rows of V_xx at a time: eight independent accumulation chains keep the FP64 pipe fed from one or two
+            // warps per sub-partition
+#pragma unroll
+            for (int i0 = 0; i0 < n; i0 += 4) {
+                T acc[4][2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = T(0);
+#pragma unroll
+                for (int l = 0; l < n; l += 2) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const V2 v = *reinterpret_cast<const V2 *>(Vxx + (i0 + r) * 12 + l);
+                        acc[r][0] += v.x * Mc[0][l];
+                        acc[r][1] += v.x * Mc[1][l];
+                        acc[r][0] += v.y * Mc[0][l + 1];
+                        acc[r][1] += v.y * Mc[1][l + 1];
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    Wc[2 * pr][i0 + r] = acc[r][0];
+                    Wc[2 * pr + 1][i0 + r] = acc[r][1];
+                }
+                asm volatile("" ::: "memory");       // keep ptxas from hoisting every row's loads (it spills W otherwise)
+            }
+        }
+        __syncwarp();                    // every lane's MT rows are published; nobody reads V_xx any more
+        // ---- C: G[r][own] = MT[r][:] W[:, own] ----
+        // rows < 12: Q_xx[r][own] = l_xx[r][own] + G (lane 3's block, f_x' V_xx f_u, is not used by the reference).  Two
+        // rows per trip (eight chains), not unrolled further: the 48 values of W stay in registers, MT passes through
+#pragma unroll 1
+        for (int r = 0; r < n; r += 2) {
+            const T *row = MT + LY::row(r);
+            T g[2][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[0][j] = g[1][j] = T(0);
+#pragma unroll
+            for (int l = 0; l < n; l += 2) {
+                const V2 v0 = *reinterpret_cast<const V2 *>(row + l), v1 = *reinterpret_cast<const V2 *>(row + 12 + l);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    g[0][j] += v0.x * Wc[j][l];
+                    g[1][j] += v1.x * Wc[j][l];
+                    g[0][j] += v0.y * Wc[j][l + 1];
+                    g[1][j] += v1.y * Wc[j][l + 1];
+                }
+            }
+            if (c < 3) {
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int j = 0; j < 4; j += 2) {
+                        const V2 lq = *reinterpret_cast<const V2 *>(QsS + (r + rr) * 12 + 4 * c + j);
+                        *reinterpret_cast<V2 *>(Vxx + (r + rr) * 12 + 4 * c + j) = V2{lq.x + g[rr][j], lq.y + g[rr][j + 1]};
+                    }
+            }
+        }
+        T Gu[m][4];                      // rows 12..15: Q_ux[:, own] (lanes 0-2) or Q_uu (lane 3), without l_uu
+#pragma unroll
+        for (int u = 0; u < m; ++u) {
+            const T *row = BdT + u * 12;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Gu[u][j] = T(0);
+#pragma unroll
+            for (int l = 0; l < n; l += 2) {
+                const V2 v = *reinterpret_cast<const V2 *>(row + l);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    Gu[u][j] += v.x * Wc[j][l];
+                    Gu[u][j] += v.y * Wc[j][l + 1];
+                }
+            }
+        }
+        // cost gradient of the own entries and Q_x / Q_u  (QsS, RsS already carry dt)      (:100-101)
+        T Qc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            T g = T(0);
+            if (c < 3) {
+                const int i = 4 * c + j;
+                if (qc.diag) g = QsS[i * 12 + i] * (xs[i] - qc.xt[i]);
+                else {
+#pragma unroll
+                    for (int jj = 0; jj < n; ++jj) g += QsS[i * 12 + jj] * (xs[jj] - qc.xt[jj]);
+                }
+            } else {
+                if (qc.diag) g = RsS[j * 4 + j] * xs[n + j];
+                else {
+#pragma unroll
+                    for (int jj = 0; jj < m; ++jj) g += RsS[j * 4 + jj] * xs[n + jj];
+                }
+            }
+            Qc[j] = g + q[j];
+        }
+        // ---- D: exchange, 4x4 solve ----
+        if (c < 3) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {               // QuxT[i][u], i = 4c + j
+                *reinterpret_cast<V2 *>(QuxT + (4 * c + j) * 4 + 2 * c) = V2{Gu[0][j], Gu[1][j]};
+                *reinterpret_cast<V2 *>(QuxT + (4 * c + j) * 4 + 2 * c + 2) = V2{Gu[2][j], Gu[3][j]};
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < m; ++u) {
+                const V2 r0 = *reinterpret_cast<const V2 *>(RsS + u * 4), r1 = *reinterpret_cast<const V2 *>(RsS + u * 4 + 2);
+                *reinterpret_cast<V2 *>(Quu + u * 4) = V2{(r0.x + Gu[u][0]) + (u == 0 ? mu_b : T(0)), (r0.y + Gu[u][1]) + (u == 1 ? mu_b : T(0))};
+                *reinterpret_cast<V2 *>(Quu + u * 4 + 2) = V2{(r1.x + Gu[u][2]) + (u == 2 ? mu_b : T(0)), (r1.y + Gu[u][3]) + (u == 3 ? mu_b : T(0))};
+            }
+            *reinterpret_cast<V2 *>(Qu) = V2{Qc[0], Qc[1]};
+            *reinterpret_cast<V2 *>(Qu + 2) = V2{Qc[2], Qc[3]};
+        }
+        __syncwarp();
+        T Lm[m][m], rhs[m][4], Quv[m];
+        {
+            const V2 a = *reinterpret_cast<const V2 *>(Qu), bq = *reinterpret_cast<const V2 *>(Qu + 2);
+            Quv[0] = a.x; Quv[1] = a.y; Quv[2] = bq.x; Quv[3] = bq.y;
+        }
+#pragma unroll
+        for (int u = 0; u < m; ++u) {
+            const V2 a = *reinterpret_cast<const V2 *>(Quu + u * 4), bq = *reinterpret_cast<const V2 *>(Quu + u * 4 + 2);
+            Lm[u][0] = a.x; Lm[u][1] = a.y; Lm[u][2] = bq.x; Lm[u][3] = bq.y;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rhs[u][j] = c < 3 ? Gu[u][j] : (j == 0 ? Quv[u] : T(0));
+        }
+        lu_solve_inplace<m, 4, T, true>(Lm, rhs);
+        T *ks = KS + ((N - t) & 1) * ROWS * LY::KROW;
+        if (c < 3) {
+            // ---- E: V_xx[:, own] = Q_xx[:, own] + Q_ux' K[:, own] ; V_x[own] = Q_x[own] + K[:, own]' Q_u ----
+            T Kc[m][4];
+#pragma unroll
+            for (int u = 0; u < m; ++u)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) Kc[u][j] = -rhs[u][j];
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const V2 qa = *reinterpret_cast<const V2 *>(QuxT + i * 4 + 2 * (i >> 2)), qb = *reinterpret_cast<const V2 *>(QuxT + i * 4 + 2 * (i >> 2) + 2);
+                const T qx[m] = { qa.x, qa.y, qb.x, qb.y };
+#pragma unroll
+                for (int j = 0; j < 4; j += 2) {
+                    V2 v = *reinterpret_cast<const V2 *>(Vxx + i * 12 + 4 * c + j);
+                    T a0 = T(0), a1 = T(0);
+#pragma unroll
+                    for (int u = 0; u < m; ++u) { a0 += qx[u] * Kc[u][j]; a1 += qx[u] * Kc[u][j + 1]; }
+                    v.x += a0;
+                    v.y += a1;
+                    *reinterpret_cast<V2 *>(Vxx + i * 12 + 4 * c + j) = v;
+                }
+            }
+            T vxn[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                T vx = T(0);
+#pragma unroll
+                for (int u = 0; u < m; ++u) vx += Kc[u][j] * Quv[u];
+                vxn[j] = Qc[j] + vx;
+#pragma unroll
+                for (int u = 0; u < m; ++u) ks[(u * n + 4 * c + j) * LY::KROW + s] = Kc[u][j];
+            }
+            *reinterpret_cast<V2 *>(Vx + 4 * c) = V2{vxn[0], vxn[1]};
+            *reinterpret_cast<V2 *>(Vx + 4 * c + 2) = V2{vxn[2], vxn[3]};
+        } else {
+#pragma unroll
+            for (int u = 0; u < m; ++u) ks[(n * m + u) * LY::KROW + s] = -rhs[u][0];
+        }
+        if (t > 0) store_pre(buf ^ 1);
+        __syncthreads();
+        // coalesced store of the step's gains: rows of TPB consecutive trajectories
+        for (int e = tid; e < ROWS * TPB; e += NT) {
+            const int row = e / TPB, bb = e % TPB;
+            if (vflag[bb]) {
+                if (row < n * m) K[((size_t)t * n * m + row) * B + b0 + bb] = ks[row * LY::KROW + bb];
+                else k[((size_t)t * m + (row - n * m)) * B + b0 + bb] = ks[row * LY::KROW + bb];
+            }
+        }
+    }
+}
+
 }  // namespace ilqr
