@@ -137,7 +137,7 @@ def workload_config(args, world):
                         f"N={N_H} rk4, B={args.batch} seeded initial states per GPU",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world, "horizon": N_H,
             "iterations_per_step": ITERS, "line_search_alphas": N_ALPHA, "tol": 0.0, "sharding": f"batch x{world}",
-            "l2_policy": "working set per step (A,B,X,U,K,k + 10 candidate slabs = 1.3 GB) exceeds the 126 MB L2; "
+            "l2_policy": "working set per step (X,U,K,k + 10 candidate slabs = 1.0 GB) exceeds the 126 MB L2; "
                          "no explicit flush"}
 
 

@@ -164,6 +164,12 @@ struct Handle {
     cudaEvent_t ev[2];
 };
 
+// does this handle's ilqr_solve / ilqr_backward_pass materialise A_t, B_t in the workspace?  (see ws_layout)
+static bool stores_linearization(const Handle *h)
+{
+    return h->p.model != ILQR_LTV && (h->p.model == ILQR_USER || h->env_fused == 0);
+}
+
 static inline int grid_for(size_t threads, int bs) { return (int)((threads + bs - 1) / bs); }
 
 // pick a block size that still spreads small batches over all 148 SMs
@@ -183,7 +189,7 @@ static size_t ctl_bytes(int maxiter)
     return sizeof(Control) + sizeof(unsigned int) * (3 + ILQR_MAX_WAVES) * (size_t)(maxiter + 2);
 }
 
-static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
+static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha, bool store_linearization)
 {
     const size_t w = p.dtype == ILQR_F64 ? 8 : 4;
     const size_t B = p.B, N = p.N, n = p.n, m = p.m;
@@ -194,8 +200,10 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha)
     // per-iteration speculation-list counters [maxiter + 2], then the lazy-wave list counters
     // [maxiter + 2][ILQR_MAX_WAVES]
     L.ctl = off; off = al(off + ctl_bytes(p.maxiter));
-    // the LTV model generates A_t, B_t inside its kernels: no per-trajectory linearization is stored
-    const size_t lin = p.model == ILQR_LTV ? 0 : 1;
+    // A_t, B_t are stored only where K1 and K2 run as two kernels (user-defined models, ILQR_FUSED=0): the fused kernel
+    // hands them over in shared memory and the LTV model generates them inside its kernels.  Config 5's shard
+    // (B=131072, N=500): 36.8 -> 26.3 GB of workspace
+    const size_t lin = store_linearization ? 1 : 0;
     // sized for the batch padded to whole groups of 32 columns: ilqr_solve keeps A and Bd as ONE blocked array
     // starting at L.A (ab_off); the two sizes are multiples of 256 bytes, so the regions are contiguous
     const size_t Bpad = (B + 31) / 32 * 32;
@@ -890,7 +898,7 @@ size_t ilqr_workspace_bytes(ilqr_handle_t hh)
 {
     Handle *h = (Handle *)hh;
     if (!h) return 0;
-    return ws_layout(h->p, h->n_alpha_eff).total;
+    return ws_layout(h->p, h->n_alpha_eff, stores_linearization(h)).total;
 }
 
 int64_t ilqr_launch_count(ilqr_handle_t hh) { return hh ? ((Handle *)hh)->launches : 0; }
@@ -975,12 +983,12 @@ int ilqr_backward_pass(ilqr_handle_t hh, const void *phi, const void *X, const v
 {
     Handle *h = (Handle *)hh;
     if (!h || !ws) return ILQR_E_INVALID;
-    const WsLayout L = ws_layout(h->p, h->n_alpha_eff);
+    const WsLayout L = ws_layout(h->p, h->n_alpha_eff, stores_linearization(h));
     if (ws_bytes < L.total) return ILQR_E_WORKSPACE;
     char *w = (char *)ws;
     if (!X || !U || !K || !k) return ILQR_E_INVALID;
     if (h->p.model == ILQR_LTV) return launch_backward_ltv(h, phi, X, U, K, k, nullptr, nullptr, (cudaStream_t)stream);
-    if (h->env_fused == 1 && fused_available(h))            // opt-in: the fused kernel, nothing to commit
+    if (fused_available(h))                                  // the fused kernel, nothing to commit
         return launch_fused(h, phi, (void *)X, (void *)U, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr,
                             nullptr, K, k, nullptr, (cudaStream_t)stream);
     int rc = ilqr_linearize(hh, phi, X, U, w + L.A, w + L.Bd, stream);
@@ -1025,7 +1033,7 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
     Handle *h = (Handle *)hh;
     if (!h || !x0 || !X || !U || !K || !k || !cost || !iters || !status || !ws) return ILQR_E_INVALID;
     const ilqr_problem_t &p = h->p;
-    const WsLayout L = ws_layout(p, h->n_alpha_eff);
+    const WsLayout L = ws_layout(p, h->n_alpha_eff, stores_linearization(h));
     if (ws_bytes < L.total) return ILQR_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     char *w = (char *)ws;

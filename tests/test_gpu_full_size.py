@@ -28,7 +28,7 @@ def test_cfg5_shard_131072_trajectories(oracle):
     x0 = cfg2_x0(1 << 20, seed=0)[5 * B:6 * B]           # rank 5's contiguous shard of the 1M batch
     sol = iLQR(ua_system(), 5.0, torch.as_tensor(x0).cuda(), torch.zeros((1, N), dtype=torch.float64, device="cuda"),
                tol=0.0, maxiter=iters, verbose=False)
-    assert sol._handle.workspace().numel() > 30e9         # lazy schedule, 10 candidate slabs
+    assert sol._handle.workspace().numel() > 20e9         # lazy schedule: 10 candidate slabs (no A_t, B_t: fused K1+K2)
     sol.enable_trace()
     X, U, cost = sol.optimize_trajectory()
     torch.cuda.synchronize()

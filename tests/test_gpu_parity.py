@@ -250,11 +250,13 @@ def test_two_wave_line_search_is_exact(monkeypatch):
 
 
 def test_backward_variants_agree(monkeypatch):
-    """four-lanes-per-trajectory and one-thread-per-trajectory Riccati kernels on the same inputs"""
+    """four-lanes-per-trajectory and one-thread-per-trajectory Riccati kernels of the two-kernel path (ILQR_FUSED=0) on
+    the same inputs"""
     from class_files.iLQR_class import iLQR
     g = load_golden("solve_cfg2_ua_rk4_b0")
     s = system_from_golden(g)
     res = {}
+    monkeypatch.setenv("ILQR_FUSED", "0")
     for lanes in ("1", "0"):
         monkeypatch.setenv("ILQR_BACKWARD_LANES", lanes)
         sol = iLQR(s, float(g["T"]), g["x0"], np.zeros((1, int(g["N"]))), verbose=False)
