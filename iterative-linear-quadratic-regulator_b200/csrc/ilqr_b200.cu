@@ -181,12 +181,12 @@ static inline int block_for(size_t threads)
 }
 
 struct WsLayout {
-    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, wslot, active, defer, mark, lists, alists, apos, mu, total;
+    size_t ctl, A, Bd, Xc, Uc, cost_alpha, winner, wslot, active, defer, mark, hist, lists, lists2, alists, apos, mu, total;
 };
 
 static size_t ctl_bytes(int maxiter)
 {
-    return sizeof(Control) + sizeof(unsigned int) * (3 + ILQR_MAX_WAVES) * (size_t)(maxiter + 2);
+    return sizeof(Control) + sizeof(unsigned int) * (5 + ILQR_MAX_WAVES) * (size_t)(maxiter + 2);
 }
 
 static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha, bool store_linearization)
@@ -198,7 +198,7 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha, bool store_linea
     size_t off = 0;
     // n_active[maxiter + 2], then the per-iteration deferred (second-wave) counters [maxiter + 2], then the
     // per-iteration speculation-list counters [maxiter + 2], then the lazy-wave list counters
-    // [maxiter + 2][ILQR_MAX_WAVES]
+    // [maxiter + 2][ILQR_MAX_WAVES], then the tier-2 speculation counters and the select tickets [maxiter + 2] each
     L.ctl = off; off = al(off + ctl_bytes(p.maxiter));
     // A_t, B_t are stored only where K1 and K2 run as two kernels (user-defined models, ILQR_FUSED=0): the fused kernel
     // hands them over in shared memory and the LTV model generates them inside its kernels.  Config 5's shard
@@ -217,7 +217,9 @@ static WsLayout ws_layout(const ilqr_problem_t &p, int n_alpha, bool store_linea
     L.active = off; off = al(off + 4 * B);
     L.defer = off; off = al(off + 4 * B);
     L.mark = off; off = al(off + 4 * B);
+    L.hist = off; off = al(off + 4 * B);          // try index accepted in the previous iteration (SpecArgs)
     L.lists = off; off = al(off + 4 * 2 * B);     // two speculation lists (capacity <= B each)
+    L.lists2 = off; off = al(off + 4 * B);        // tier-2 candidates of the next iteration
     L.alists = off; off = al(off + 4 * 2 * B);    // active lists of the current / next iteration (SparseArgs)
     L.apos = off; off = al(off + 4 * B);          // position of each trajectory in its active list
     L.mu = off; off = al(off + w * B);
@@ -1081,7 +1083,7 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { h->last_cuda = (int)e_; return ILQR_E_CUDA; } } while (0)
     CU(cudaMemsetAsync(ctl, 0, ctl_bytes(p.maxiter), st));
     CU(cudaMemsetAsync(defer, 0, sizeof(int) * (size_t)B, st));
-    CU(cudaMemsetAsync(mark, 0, sizeof(int) * (size_t)B, st));
+    CU(cudaMemsetAsync(mark, 0, L.lists - L.mark, st));                 // mark and hist (adjacent regions)
     // initial rollout, alpha = 0, with the incoming X,K,k (iLQR_class.py:257-259) into candidate slab 0
     AlphaList a0;
     std::memset(&a0, 0, sizeof a0);
@@ -1178,16 +1180,22 @@ int ilqr_solve(ilqr_handle_t hh, const void *phi, const void *x0, void *X, void 
                 unsigned int *n_spec = &ctl->n_active[2 * (p.maxiter + 2)];
                 sp.cap = h->spec_cap;
                 sp.n2 = n2;
-                // listed for the next iteration: accepted try index >= n1 - 5 this time.  On config 2 (10 tries, n1 = 9)
-                // that is ~17 % of the batch, within the ~1000 spare slots, and it catches the trajectories that will need
-                // the deferred try all but once per ten iterations (n1 - 4: 6 %, twice as many misses; every miss costs a
-                // latency-bound second wave, 0.37 ms at N = 500)
+                // listed for the next iteration (tier 1): accepted try index >= n1 - 5 this time, or this and the previous
+                // index adding up to >= n1 - 2; tier 2 (sum >= n1 - 3) fills what capacity is left.  On config 2 (10 tries,
+                // n1 = 9) tier 1 is ~20 % of the batch, within the ~1000 spare slots; every miss costs a latency-bound second
+                // wave, 0.37 ms at N = 500 (oracle traces of eleven shards: 1 miss per 11 solves, 5 with the single threshold;
+                // measured on 2 GPUs: 8.76 -> 8.48 ms per step on the slower shard)
                 sp.threshold = n1 - 5 > 1 ? n1 - 5 : 1;
                 sp.list_cur = lists + (size_t)(it & 1) * B;
                 sp.list_next = lists + (size_t)((it + 1) & 1) * B;
                 sp.count_cur = n_spec + it;
                 sp.count_next = n_spec + it + 1;
                 sp.mark = mark;
+                sp.hist = (int *)(w + L.hist);
+                sp.list2_next = (int *)(w + L.lists2);
+                unsigned int *extra = &ctl->n_active[(3 + ILQR_MAX_WAVES) * (p.maxiter + 2)];
+                sp.count2_next = extra + it + 1;
+                sp.ticket = extra + (p.maxiter + 2) + it;
             }
             if ((rc = launch_rollout(h, n1, h->alphas, phi, x0, X, U, k, K, Xc, Uc, ca, active, g, nullptr, st, &sp))) return rc;
             prof_mark(h, ILQR_KC_ROLLOUT, st);

@@ -25,13 +25,21 @@ struct Control {
 // sub-partitions) that roll out the deferred step sizes for the listed trajectories, so that the
 // separate, latency-bound second wave is almost never needed.  Which rollouts are evaluated never
 // changes which one is accepted.
+// Two tiers (round 2): a trajectory is listed at once when its accepted try index w, or w plus the index it accepted
+// the iteration before, is high (tier 1); the milder cases (tier 2) are collected apart and fill whatever capacity
+// tier 1 leaves, merged by the last block of select_kernel to finish.  On config 2 (offline, oracle traces of eleven
+// shards of 4096): single threshold 5 missed second waves per 11 solves, two tiers 1.
 struct SpecArgs {
     int cap;                              // list capacity; 0 switches speculation off
     int n2;                               // deferred step sizes per trajectory
-    int threshold;                        // accepted try index from which a trajectory is listed
+    int threshold;                        // tier 1: w >= threshold or w + previous w >= threshold + 3; tier 2: sum >= threshold + 2
     int *list_cur, *list_next;            // [cap]
     unsigned int *count_cur, *count_next; // entries appended this / next iteration (may exceed cap)
     int *mark;                            // [B]: mark[b] == it + 1 <=> b is on the list of iteration it
+    int *hist;                            // [B]: try index accepted in the previous iteration
+    int *list2_next;                      // [cap] tier-2 candidates for the next iteration
+    unsigned int *count2_next;            // tier-2 candidates appended (may exceed cap)
+    unsigned int *ticket;                 // blocks of this iteration's first select that have finished
 };
 
 // Levenberg-Marquardt regularisation of Q_uu, kept per trajectory on the device (an EXTENSION: the

@@ -300,9 +300,16 @@ __global__ void select_kernel(int B, int a_lo, int a_hi, int wave, const T *__re
                     if (it + 1 >= maxiter) { status[b] = ILQR_ST_MAXITER; active[b] = 0; }
                     else if (abs_t(cw - c0) <= tol) { status[b] = ILQR_ST_CONVERGED; active[b] = 0; }
                     else still = true;
-                    if (still && sp.cap > 0 && w >= sp.threshold) {      // small step needed: list it for next time
-                        const unsigned int pos = atomicAdd(sp.count_next, 1u);
-                        if (pos < (unsigned int)sp.cap) { sp.list_next[pos] = b; sp.mark[b] = it + 2; }
+                    if (sp.cap > 0) {
+                        const int sum = w + sp.hist[b];
+                        sp.hist[b] = w;
+                        if (still && (w >= sp.threshold || sum >= sp.threshold + 3)) {   // small steps: list it for next time
+                            const unsigned int pos = atomicAdd(sp.count_next, 1u);
+                            if (pos < (unsigned int)sp.cap) { sp.list_next[pos] = b; sp.mark[b] = it + 2; }
+                        } else if (still && sum >= sp.threshold + 2) {                   // tier 2: if room is left
+                            const unsigned int pos = atomicAdd(sp.count2_next, 1u);
+                            if (pos < (unsigned int)sp.cap) sp.list2_next[pos] = b;
+                        }
                     }
                 }
             }
@@ -315,6 +322,28 @@ __global__ void select_kernel(int B, int a_lo, int a_hi, int wave, const T *__re
         if (ns) atomicAdd(&ctl->n_active[it + 1], ns);
         if (nr) atomicAdd(&ctl->total_iters, (unsigned long long)nr);
         if (nd) atomicAdd(n2_count, nd);
+    }
+    // the last block of the first wave's select appends tier 2 behind tier 1 while capacity lasts (a second wave, if
+    // one runs, lists only trajectories that accepted a deferred step size: tier 1, appended behind these)
+    if (wave == 0 && sp.cap > 0) {
+        __shared__ bool last_block;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last_block = atomicAdd(sp.ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (last_block) {
+            __threadfence();
+            const unsigned int c1 = min(*(volatile unsigned int *)sp.count_next, (unsigned int)sp.cap);
+            const unsigned int c2 = min(*(volatile unsigned int *)sp.count2_next, (unsigned int)sp.cap);
+            const unsigned int nc = min(c2, (unsigned int)sp.cap - c1);
+            for (unsigned int j = threadIdx.x; j < nc; j += blockDim.x) {
+                const int bj = ((volatile int *)sp.list2_next)[j];
+                sp.list_next[c1 + j] = bj;
+                sp.mark[bj] = it + 2;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0 && nc) atomicAdd(sp.count_next, nc);
+        }
     }
 }
 
