@@ -17,6 +17,7 @@
 //   ilqr_kernels_common.cuh     structures shared by the kernels (control block, speculation / regularisation args)
 //   ilqr_kernels_linearize.cuh  step_kernel, K1, materialised cost expansion, MPC shift
 //   ilqr_kernels_backward.cuh   K2 in its three forms
+//   ilqr_kernels_ltv_mma.cuh    K2 of the LTV model on the FP64 tensor cores (DMMA), one warp per trajectory
 //   ilqr_kernels_fused.cuh      K1 + K2 as one warp-specialised kernel (producers linearize, consumer scans)
 //   ilqr_kernels_rollout.cuh    K3 and K4 (eager and lazy line-search schedules)
 //   ilqr_b200.cu (this file)    handle, workspace layout, launch configuration, ilqr_solve, the C ABI
@@ -37,6 +38,7 @@
 #include "ilqr_kernels_common.cuh"
 #include "ilqr_kernels_linearize.cuh"
 #include "ilqr_kernels_backward.cuh"
+#include "ilqr_kernels_ltv_mma.cuh"
 #include "ilqr_kernels_fused.cuh"
 #include "ilqr_kernels_rollout.cuh"
 
@@ -135,7 +137,9 @@ struct Handle {
     int env_fused;            // ILQR_FUSED: -1 [auto: fused K1+K2 inside ilqr_solve where it is the faster form], 0 never,
                               // 1 wherever the model allows (also ilqr_backward_pass)
     int env_fused_minb;       // ILQR_FUSED_MINB: 0 [auto: by batch size], 1 = uncapped registers, 4 / 5 = capped for 4 / 5 blocks per SM
-    int env_ltv_lanes;        // ILQR_LTV_LANES: 0 [auto: by batch size], 4 (register-tiled kernel) or 16 (one column per lane)
+    int env_ltv_lanes;        // ILQR_LTV_LANES: 0 [auto: by batch size and precision], 4 (register-tiled kernel), 16 (one column
+                              // per lane) or 32 (FP64 tensor-core kernel, one warp per trajectory)
+    int env_ltv_wpb;          // ILQR_LTV_MMA_WPB: trajectories per block of the tensor-core kernel (4 [default] or 8)
     int env_check_every;      // ILQR_CHECK_EVERY: iterations enqueued between host polls of the active count [8]
     long env_sparse_thresh;   // ILQR_SPARSE_THRESH / ILQR_SPARSE_ALL: -1 [auto] or the thresholds of SparseArgs
     long env_sparse_all;
@@ -491,6 +495,9 @@ static int launch_fused(Handle *h, const void *phi, void *X, void *U, const void
 }
 
 // K2 of the LTV model: A_t, B_t generated in the kernel (no linearization buffers)
+#ifndef ILQR_LTV_MMA_MIN_BATCH
+#define ILQR_LTV_MMA_MIN_BATCH 1
+#endif
 static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const void *U, void *K, void *k,
                                const int *active, const unsigned int *gate, cudaStream_t st, const void *mu = nullptr)
 {
@@ -500,8 +507,26 @@ static int launch_backward_ltv(Handle *h, const void *phi, const void *X, const 
     constexpr int TPB = 16;
     auto go = [&](auto tz) -> int {
         using T = decltype(tz);
-        // sixteen lanes per trajectory, one column each: the latency-bound regime of small batches (B=2048, N=1000: 4.0 vs
-        // 7.5 ms per pass); four lanes x four columns, register tiled: large batches (B=32768: 39.6 vs 47.1 ms)
+        // FP64: the tensor-core kernel (ilqr_kernels_ltv_mma.cuh), one warp per trajectory, at every batch size (N=1000,
+        // ms per pass, sixteen-lane / four-lane / tensor-core kernel: B=256 3.94 / 6.90 / 1.54, B=1024 4.00 / 7.16 / 1.92,
+        // B=4096 6.85 / 7.60 / 5.15, B=32768 47.1 / 39.6 / 33.0; profiles/r02_exp_ltv_sizes.log)
+        if constexpr (std::is_same_v<T, double>) {
+            if (h->env_ltv_lanes ? h->env_ltv_lanes == 32 : h->p.B >= ILQR_LTV_MMA_MIN_BATCH) {
+                auto run = [&](auto wz) -> int {
+                    constexpr int WPB = decltype(wz)::value;
+                    backward_ltv_mma_kernel<WPB><<<grid_for(h->p.B, WPB), WPB * 32, 0, st>>>(
+                        make_ltv<double>(h->p), make_cost<double, 12, 4>(h->p), h->p.N, h->p.B, (const double *)phi,
+                        (const double *)X, (const double *)U, (double *)K, (double *)k, active, gate, (const double *)mu);
+                    ILQR_CHECK_LAUNCH(h);
+                    return ILQR_OK;
+                };
+                if (h->env_ltv_wpb == 8) return run(std::integral_constant<int, 8>());
+                return run(std::integral_constant<int, 4>());
+            }
+        }
+        // FP32 (and ILQR_LTV_LANES): sixteen lanes per trajectory, one column each: the latency-bound regime of small
+        // batches (B=2048, N=1000: 4.0 vs 7.5 ms per pass); four lanes x four columns, register tiled: large batches
+        // (B=32768: 39.6 vs 47.1 ms)
         const bool lanes16 = h->env_ltv_lanes ? h->env_ltv_lanes == 16 : h->p.B < 8192;
         if (lanes16) {
             const size_t smem = sizeof(T) * (size_t)(504 * TPB + 48 + 144 + 16 + 288);
@@ -856,7 +881,8 @@ static int create_handle(const ilqr_problem_t *p, UserModule *umod, ilqr_handle_
         h->env_rollout_bs = (e = getenv("ILQR_ROLLOUT_BS")) && atoi(e) >= 32 ? atoi(e) / 32 * 32 : 0;
         h->env_check_every = (e = getenv("ILQR_CHECK_EVERY")) && atoi(e) > 0 ? atoi(e) : 8;
         h->env_fused = (e = getenv("ILQR_FUSED")) ? (atoi(e) != 0) : -1;
-        h->env_ltv_lanes = (e = getenv("ILQR_LTV_LANES")) && (atoi(e) == 16 || atoi(e) == 4) ? atoi(e) : 0;
+        h->env_ltv_lanes = (e = getenv("ILQR_LTV_LANES")) && (atoi(e) == 32 || atoi(e) == 16 || atoi(e) == 4) ? atoi(e) : 0;
+        h->env_ltv_wpb = (e = getenv("ILQR_LTV_MMA_WPB")) && atoi(e) == 8 ? 8 : 4;
         h->env_fused_minb = (e = getenv("ILQR_FUSED_MINB")) ? atoi(e) : 0;
     }
     h->env_sparse_thresh = (e = getenv("ILQR_SPARSE_THRESH")) ? atol(e) : -1;

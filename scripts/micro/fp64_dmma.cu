@@ -36,6 +36,136 @@ __global__ void k(double *out, int iters, double a0, double b0)
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// like the LTV kernel: 4 accumulator tiles, 4 k-steps each, every DMMA with its own A and B registers (8 + 8 operands)
+__global__ void k16(double *out, int iters, double a0, double b0)
+{
+    double c[4][2], a[2][4], b[2][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i][0] = c[i][1] = i;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i / 4][i % 4] = a0 + (threadIdx.x + i) * 1e-9; b[i / 4][i % 4] = b0 - (threadIdx.x + 3 * i) * 1e-9; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) dmma(c[mt * 2 + nt][0], c[mt * 2 + nt][1], a[mt][ks], b[nt][ks]);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+void run16(int warps_per_smsp, double *out)
+{
+    const int iters = 4000, blocks = 148 * 4 * warps_per_smsp;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k16<<<blocks, 32>>>(out, 50, 1e-3, 1e-3);
+    cudaEventRecord(e0);
+    k16<<<blocks, 32>>>(out, iters, 1e-3, 1e-3);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double cyc_trip = ms * 1e-3 * 1.965e9 / iters;
+    printf("warps/SMSP %d  16 DMMAs (4 tiles x 4 k-steps, distinct operands): %8.1f cycles per trip, %6.2f cycles per DMMA per sub-partition\n",
+           warps_per_smsp, cyc_trip, cyc_trip / (16.0 * warps_per_smsp));
+}
+
+// the LTV step in caricature: 32 DMMAs (two products, 4 tiles x 4 k-steps, the second reading the first's accumulators)
+// followed by ONE dependent chain of L scalar FP64 instructions (the 4 x 4 LU) whose result feeds the next trip's operands
+template <int L>
+__global__ void kstep(double *out, int iters, double a0, double b0)
+{
+    double c[4][2], d[4][2], a[2][4];
+    double x = a0 + threadIdx.x * 1e-9;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i / 4][i % 4] = a0 + (threadIdx.x + i) * 1e-9;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i][0] = d[i][1] = b0 + i * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) dmma(c[mt * 2 + nt][0], c[mt * 2 + nt][1], a[mt][ks], d[nt * 2 + (ks >> 1)][ks & 1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i][0] = d[i][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) dmma(d[mt * 2 + nt][0], d[mt * 2 + nt][1], a[mt][ks], c[nt * 2 + (ks >> 1)][ks & 1]);
+        x = d[3][1] * 1e-30 + x;
+#pragma unroll
+        for (int i = 0; i < L; ++i) x = fma(x, 0.999999, 1e-9);
+        d[0][0] += x * 1e-30;
+    }
+    double s = x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1] + d[i][0] + d[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int L>
+void runstep(int warps_per_smsp, double *out)
+{
+    const int iters = 2000, blocks = 148 * 4 * warps_per_smsp;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    kstep<L><<<blocks, 32>>>(out, 50, 1e-3, 1e-3);
+    cudaEventRecord(e0);
+    kstep<L><<<blocks, 32>>>(out, iters, 1e-3, 1e-3);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double cyc = ms * 1e-3 * 1.965e9 / iters / warps_per_smsp;
+    printf("warps/SMSP %d  32 DMMA + chain of %3d DFMA: %7.1f cycles per step per sub-partition (pipe work %d)\n",
+           warps_per_smsp, L, cyc, 32 * 16 + (L + 2) * 2);
+}
+
+// do integer / select instructions issue while a DMMA occupies the FP64 pipe?  4 DMMAs + NI LOP3/IMADs per trip
+template <int NI>
+__global__ void kint(double *out, int *iout, int iters, double a0, double b0, int ia)
+{
+    double c[4][2];
+    int y[8];
+    const double a = a0 + threadIdx.x * 1e-9, b = b0 - threadIdx.x * 1e-9;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i][0] = c[i][1] = i;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = threadIdx.x + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            dmma(c[i][0], c[i][1], a, b);
+#pragma unroll
+            for (int j = 0; j < NI / 4; ++j) y[(i * (NI / 4) + j) % 8] = (y[(i * (NI / 4) + j) % 8] ^ ia) + (int)threadIdx.x;
+        }
+    }
+    double s = 0; int t = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += y[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    iout[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+template <int NI>
+void runint(int warps_per_smsp, double *out)
+{
+    const int iters = 4000, blocks = 148 * 4 * warps_per_smsp;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    kint<NI><<<blocks, 32>>>(out, (int *)(out + 148 * 4 * 8 * 32), 50, 1e-3, 1e-3, 5);
+    cudaEventRecord(e0);
+    kint<NI><<<blocks, 32>>>(out, (int *)(out + 148 * 4 * 8 * 32), iters, 1e-3, 1e-3, 5);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double cyc = ms * 1e-3 * 1.965e9 / iters / warps_per_smsp;
+    printf("warps/SMSP %d  4 DMMA + %3d integer ops (2 SASS instructions each): %7.1f cycles per trip per warp  (DMMA alone: 64)\n",
+           warps_per_smsp, NI, cyc);
+}
+
 template <int CH, int NF>
 void run(int warps_per_smsp, double *out)
 {
@@ -63,6 +193,12 @@ int main()
     run<4, 0>(1, out);
     run<8, 0>(1, out);
     for (int w : {2, 4, 8}) { run<1, 0>(w, out); run<4, 0>(w, out); run<8, 0>(w, out); }
+    printf("# the LTV kernel's pattern\n");
+    for (int w : {1, 2, 4, 6}) run16(w, out);
+    printf("# products + dependent scalar chain per step\n");
+    for (int w : {1, 2, 3, 4, 6, 8}) { runstep<60>(w, out); runstep<120>(w, out); }
+    printf("# DMMA + integer instructions\n");
+    for (int w : {2, 4}) { runint<0>(w, out); runint<16>(w, out); runint<32>(w, out); runint<64>(w, out); runint<128>(w, out); }
     printf("# DMMA + DFMA mixed (do they share the pipe?)\n");
     run<4, 8>(2, out);
     run<4, 32>(2, out);

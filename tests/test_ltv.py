@@ -55,10 +55,11 @@ def test_oracle_ltv_is_lqr(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("lanes", ["16", "4"])
+@pytest.mark.parametrize("lanes", ["16", "4", "32"])
 def test_ltv_point_functions_and_passes_vs_oracle(oracle, monkeypatch, lanes):
-    """both Riccati kernels of the LTV model: sixteen lanes per trajectory (small batches) and the register-tiled
-    four-lane kernel (large batches; forced here by ILQR_LTV_LANES)"""
+    """the three Riccati kernels of the LTV model: sixteen lanes per trajectory (small batches), the register-tiled
+    four-lane kernel (FP32, large batches) and the FP64 tensor-core kernel, one warp per trajectory (FP64, large
+    batches); forced here by ILQR_LTV_LANES"""
     from class_files.iLQR_class import iLQR
     monkeypatch.setenv("ILQR_LTV_LANES", lanes)
     O = oracle
@@ -89,7 +90,7 @@ def test_ltv_point_functions_and_passes_vs_oracle(oracle, monkeypatch, lanes):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("lanes,B", [("16", 64), ("4", 64), ("4", 37)])
+@pytest.mark.parametrize("lanes,B", [("16", 64), ("4", 64), ("4", 37), ("32", 64), ("32", 37)])
 def test_ltv_solve_reaches_lqr_optimum(oracle, monkeypatch, lanes, B):
     from class_files.iLQR_class import iLQR
     monkeypatch.setenv("ILQR_LTV_LANES", lanes)
@@ -109,8 +110,9 @@ def test_ltv_solve_reaches_lqr_optimum(oracle, monkeypatch, lanes, B):
 
 @pytest.mark.gpu
 def test_ltv_riccati_kernels_agree_incl_fp32_and_ragged_batches(monkeypatch):
-    """the two LTV Riccati kernels on the same nominal: FP64 gains to 1e-12, FP32 gains to 1e-4 of the FP64 ones, on a
-    batch that fills neither kernel's last block"""
+    """the LTV Riccati kernels on the same nominal: FP64 gains of the lane-tiled kernels to 1e-12, of the tensor-core
+    kernel (every block size) to 1e-11 (DMMA sums in another order), FP32 gains to 1e-4 of the FP64 ones, on a batch that
+    fills no kernel's last block"""
     from class_files.iLQR_class import iLQR
     from class_files.systems.ltv_sys import MyLTVSystem
     B, N = 203, 90
@@ -120,13 +122,18 @@ def test_ltv_riccati_kernels_agree_incl_fp32_and_ragged_batches(monkeypatch):
     out = {}
     for dtype in ("float64", "float32"):
         s = MyLTVSystem.synthetic(seed=2, dtype=dtype)
-        for lanes in ("16", "4"):
+        for lanes, wpb in (("16", ""), ("4", ""), ("32", "4"), ("32", "8")):
+            if dtype == "float32" and lanes == "32":
+                continue                      # FP64 only: the FP32 mode keeps the lane-tiled kernels
             monkeypatch.setenv("ILQR_LTV_LANES", lanes)
+            monkeypatch.setenv("ILQR_LTV_MMA_WPB", wpb)
             sol = iLQR(s, N * s.dt, x0, np.zeros((4, N)), verbose=False, phi=phi)
             X_nom, _, _ = sol.forward_pass(x0, 0.0, sol.X, U_nom, sol.U_ff, sol.K)
             U_ff, K = sol.backward_pass(X_nom, U_nom)
-            out[dtype, lanes] = (np.asarray(K, dtype=np.float64), np.asarray(U_ff, dtype=np.float64))
+            out[dtype, lanes + wpb] = (np.asarray(K, dtype=np.float64), np.asarray(U_ff, dtype=np.float64))
     for j in range(2):
         assert rel_err(out["float64", "4"][j], out["float64", "16"][j]) < 1e-12
+        for wpb in ("4", "8"):
+            assert rel_err(out["float64", "32" + wpb][j], out["float64", "16"][j]) < 1e-11
         assert rel_err(out["float32", "4"][j], out["float64", "16"][j], floor=1e-3) < 1e-4
         assert rel_err(out["float32", "16"][j], out["float64", "16"][j], floor=1e-3) < 1e-4
