@@ -147,6 +147,8 @@ struct Handle {
     // lives on one device), never in function statics
     size_t smem_backward;     // largest size configured for this handle's backward_kernel instantiation
     int smem_ltv;             // backward_ltv_kernel configured
+    int smem_fsplit;          // fused_backward_split_kernel configured (dynamic shared memory above 48 KB)
+    int env_fused_split;      // ILQR_FUSED_SPLIT: -1 [auto: at most two blocks per SM, n = 4], 0 never, 1 whenever n = 4
     void *mu_user;            // optional caller buffer for the per-trajectory regularisation (ilqr_set_mu_buffer)
     int ab_blocked;           // ilqr_solve stores the linearization blocked by groups of 32 trajectories (ab_off)
     int sparse;               // lazy schedule: late iterations index the batch through the active list (SparseArgs)
@@ -468,6 +470,26 @@ static int launch_fused(Handle *h, const void *phi, void *X, void *U, const void
                     sys, qc, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U, (const T *)Xc, (const T *)Uc, winner, wslot, active,
                     iters, it, g0, g1, (T *)K, (T *)k, (const T *)mu, sa);
             };
+            // Small batches (at most two rounds of one block per SM): two consumer warps, each half the columns, four
+            // producers (ms per pass, one consumer / split: B=1024 0.273 / 0.226, B=4096 0.272 / 0.226, B=8192 0.474 / 0.448;
+            // profiles/r02_exp_fused_split.log)
+            if constexpr (Sys::N == 4) {
+                if (h->env_fused_split != 0 && (h->env_fused_split == 1 || groups <= 2 * 148)) {
+                    constexpr int NP = 4, S = 4;
+                    constexpr size_t smem = fused_split_smem_bytes<Sys, Cost, NP, S, T>();
+                    auto kern = fused_backward_split_kernel<Sys, Cost, I, T, NP, S>;
+                    if (!h->smem_fsplit) {
+                        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        if (e != cudaSuccess) { h->last_cuda = (int)e; return ILQR_E_CUDA; }
+                        h->smem_fsplit = 1;
+                    }
+                    kern<<<groups, 32 * (NP + 2), smem, st>>>(sys, qc, h->p.N, h->p.B, (const T *)phi, (T *)X, (T *)U,
+                                                              (const T *)Xc, (const T *)Uc, winner, wslot, active, iters, it, g0,
+                                                              g1, (T *)K, (T *)k, (const T *)mu, sa);
+                    ILQR_CHECK_LAUNCH(h);
+                    return ILQR_OK;
+                }
+            }
             using std::integral_constant;
             using I1 = integral_constant<int, 1>;
             using I2 = integral_constant<int, 2>;
@@ -884,6 +906,7 @@ static int create_handle(const ilqr_problem_t *p, UserModule *umod, ilqr_handle_
         h->env_ltv_lanes = (e = getenv("ILQR_LTV_LANES")) && (atoi(e) == 32 || atoi(e) == 16 || atoi(e) == 4) ? atoi(e) : 0;
         h->env_ltv_wpb = (e = getenv("ILQR_LTV_MMA_WPB")) && atoi(e) == 8 ? 8 : 4;
         h->env_fused_minb = (e = getenv("ILQR_FUSED_MINB")) ? atoi(e) : 0;
+        h->env_fused_split = (e = getenv("ILQR_FUSED_SPLIT")) ? (atoi(e) != 0) : -1;
     }
     h->env_sparse_thresh = (e = getenv("ILQR_SPARSE_THRESH")) ? atol(e) : -1;
     h->env_sparse_all = (e = getenv("ILQR_SPARSE_ALL")) ? atol(e) : -1;

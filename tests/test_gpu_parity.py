@@ -425,11 +425,14 @@ def _solve_outputs(sol):
     return [np.array(a) for a in (X, U, cost, sol.K, sol.U_ff, sol.iterations, sol.status)]
 
 
-@pytest.mark.parametrize("kind,integ,minb", [("ua", "rk4", "0"), ("ua", "rk4", "5"), ("ua", "backward_euler", "4"),
-                                             ("double", "rk4", "0"), ("pendulum", "midpoint", "5")])
-def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, integ, minb):
+@pytest.mark.parametrize("kind,integ,minb,split", [("ua", "rk4", "0", "1"), ("ua", "rk4", "0", "0"), ("ua", "rk4", "5", "0"),
+                                                   ("ua", "backward_euler", "4", "0"), ("ua", "euler", "0", "1"),
+                                                   ("double", "rk4", "0", "1"), ("double", "rk4", "0", "0"),
+                                                   ("double", "midpoint", "0", "1"), ("pendulum", "midpoint", "5", "0")])
+def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, integ, minb, split):
     """K1+K2 as one warp-specialised kernel (csrc/ilqr_kernels_fused.cuh: producers commit + linearize into a
-    shared-memory ring, the consumer scans; in each of its register-capped builds) against the two-kernel path with the
+    shared-memory ring, the consumer scans; in each of its register-capped builds, and in the small-batch form whose
+    recursion is split over two consumer warps, `split`) against the two-kernel path with the
     thread-per-trajectory scan: the same operation sequence, so gains, trajectories, costs and control flow must agree
     BIT FOR BIT -- in a solve with staggered convergence, regularisation retries and
     warm-started re-solves (commits of finished trajectories, inactive lanes, a ragged last group), on the eager and the
@@ -444,6 +447,7 @@ def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, in
     monkeypatch.setenv("ILQR_BACKWARD_LANES", "0")
     monkeypatch.setenv("ILQR_SPARSE", "0")
     monkeypatch.setenv("ILQR_FUSED_MINB", minb)
+    monkeypatch.setenv("ILQR_FUSED_SPLIT", split)
     for fused in ("0", "1"):
         monkeypatch.setenv("ILQR_FUSED", fused)
         res = []
