@@ -236,8 +236,9 @@ fused_backward_kernel(const __grid_constant__ Sys sys, const __grid_constant__ C
 // roles follow the hardware's warp -> sub-partition map (warp w runs on sub-partition w mod 4, scripts/micro/
 // warp_smsp_map.cu): warps 2 and 3 are the consumers, each alone on its sub-partition, warps 0, 4 and 1, 5 the producers.
 // Measured at B=4096, N=500 (profiles/r02_exp_fused_split.log): one consumer + 2 producers 0.273 ms; split + 2 producers
-// 0.262 (producer bound: 2 060 cycles per linearization from a lone warp); split + 4 producers 0.226 (producer bound: the
-// two sub-partitions that linearize are pipe bound); six producers, two of them on the consumers' sub-partitions: 0.273-
+// 0.262 (producer bound: 2 060 cycles per linearization from a lone warp); split + 4 producers 0.226 (with Euler steps,
+// whose linearization is almost free, 0.208: what remains is the halves' per-step latency -- ring hand-off, exchange
+// barrier, reciprocal chain); six producers, two of them on the consumers' sub-partitions: 0.273-
 // 0.281 (a consumer half that shares its sub-partition is as slow as the unsplit consumer); both halves on one
 // sub-partition and six producers on the other three: 0.29; three producers per sub-partition: 0.224.
 // ------------------------------------------------------------------------------------------------------------------
