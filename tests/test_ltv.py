@@ -137,3 +137,45 @@ def test_ltv_riccati_kernels_agree_incl_fp32_and_ragged_batches(monkeypatch):
             assert rel_err(out["float64", "32" + wpb][j], out["float64", "16"][j]) < 1e-11
         assert rel_err(out["float32", "4"][j], out["float64", "16"][j], floor=1e-3) < 1e-4
         assert rel_err(out["float32", "16"][j], out["float64", "16"][j], floor=1e-3) < 1e-4
+
+
+@pytest.mark.gpu
+def test_ltv_dense_weights_target_and_regularisation_across_kernels(oracle, monkeypatch):
+    """the paths of the LTV Riccati kernels that the diagonal-weight cases above never take: dense non-symmetric Q, R, Q_f
+    with a non-zero target (general cost gradient), on all three kernels against the oracle; and a regularised solve
+    (mu on the diagonal of Q_uu) on the tensor-core kernel against the sixteen-lane one"""
+    from class_files.iLQR_class import iLQR
+    from class_files.systems.ltv_sys import MyLTVSystem
+    O = oracle
+    B, N = 21, 70
+    base = MyLTVSystem.synthetic(seed=4)
+    rng = np.random.default_rng(11)
+    Q = np.eye(12) + 0.2 * rng.standard_normal((12, 12))
+    R = 0.1 * np.eye(4) + 0.02 * rng.standard_normal((4, 4))
+    Qf = 10.0 * np.eye(12) + rng.standard_normal((12, 12))
+    xt = 0.3 * rng.standard_normal(12)
+    s = MyLTVSystem(base.dt, xt, Q, R, Qf, base.Ac, base.E, base.Bc, amp=base.amp)
+    x0, phi = rng.standard_normal((B, 12)), rng.uniform(0, 2 * np.pi, B)
+    U_nom = 0.3 * rng.standard_normal((B, 4, N))
+    p = O.make_problem("ltv", "euler", N, s.dt, Q, R, Qf, xt, ltv=dict(Ac=s.Ac, E=s.E, Bc=s.Bc, amp=s.amp))
+    got = {}
+    for lanes in ("16", "4", "32"):
+        monkeypatch.setenv("ILQR_LTV_LANES", lanes)
+        sol = iLQR(s, N * s.dt, x0, np.zeros((4, N)), verbose=False, phi=phi)
+        X_nom, _, _ = sol.forward_pass(x0, 0.0, sol.X, U_nom, sol.U_ff, sol.K)
+        U_ff, K = sol.backward_pass(X_nom, U_nom)
+        got[lanes] = (np.asarray(X_nom), np.asarray(U_ff), np.asarray(K))
+    for b in range(0, B, 5):
+        Uff_o, K_o = O.backward_pass(p, got["16"][0][b], U_nom[b], phi=float(phi[b]))
+        for lanes in got:
+            assert rel_err(got[lanes][2][b], K_o) < 1e-9 and rel_err(got[lanes][1][b], Uff_o) < 1e-9, lanes
+    # regularised solves: the mu schedule lives in the select kernels, the kernels only add mu to Q_uu's diagonal
+    res = {}
+    for lanes in ("16", "32"):
+        monkeypatch.setenv("ILQR_LTV_LANES", lanes)
+        sol = iLQR(s, N * s.dt, x0, np.zeros((4, N)), verbose=False, phi=phi, maxiter=3, reg_init=0.05, reg_factor=4.0)
+        X, U, cost = sol.optimize_trajectory()
+        res[lanes] = (np.asarray(X), np.asarray(U), np.asarray(cost), np.asarray(sol.K), np.asarray(sol.iterations))
+    assert np.array_equal(res["16"][4], res["32"][4])
+    for j in range(4):
+        assert rel_err(res["32"][j], res["16"][j]) < 1e-9
