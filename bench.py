@@ -43,6 +43,14 @@ BYTES = {"linearize": 240, "backward": 240, "rollout": 120, "fused_backward": 12
 # f64 / rk4 / UA-double-pendulum kernels by scripts/sass_flops.py: step_jac 485+150+59, riccati_step 246+10+26,
 # rollout step 229+61+24 instructions
 FLOPS = {"linearize": 1179, "backward": 528, "rollout": 543}
+# the same counts for the kernels of batches of TRIG_TABLE_MIN trajectories or more, whose sines and cosines come from the
+# shared-memory table (sincos_tab, csrc/ilqr_systems.cuh): step_jac 421+174+75, rollout step 165+85+40 instructions
+FLOPS_TABLE = {"linearize": 1091, "backward": 528, "rollout": 455}
+TRIG_TABLE_MIN = int(os.environ.get("ILQR_TRIG_TABLE_MIN", "8192"))
+
+
+def flops_for(B):
+    return FLOPS_TABLE if B >= TRIG_TABLE_MIN else FLOPS
 
 
 def cfg2_x0(count, seed=0):
@@ -188,6 +196,7 @@ def kernel_report(sol, torch, B, steps, peak_hbm, peak_fp64, fused):
     nit = max(1, kt["backward"][1] if fused else kt["linearize"][1])         # iLQR iterations profiled
     per_it_rollouts = rollouts / nit
     kern = {}
+    FLOPS = flops_for(B)
     for name in ("linearize", "backward", "rollout"):
         tot, cnt = kt[name]
         if fused and name == "linearize":
@@ -474,7 +483,7 @@ def main():
             "hbm": {"achieved": kd["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": kd["hbm_frac"]},
             "fp64": {"achieved": kd["achieved_TFLOPs"], "peak": peak_fp64, "unit": "TFLOP/s", "frac": kd["fp64_frac"],
                      "peak_source": "ilqr_fp64_peak(): DFMA chains on every SM, measured in this run",
-                     "flop_per_rollout_step": FLOPS["rollout"]},
+                     "flop_per_rollout_step": flops_for(B)["rollout"]},
             "pipe_active_pct_from_profiles": tB.get("fp64_pipe_active_pct", {}).get(dom),
             "note": "the rollout is bound by the FP64 pipe, not by HBM (DESIGN.md section 4): frac = FP64 flop/s (DFMA = 2, "
                     "counted from the kernel's SASS, x rollouts the schedule evaluated) / measured DFMA peak; the HBM figures "

@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, "csrc", "ilqr_b200.cu")]
-HEADERS = ["ilqr_systems.cuh", "ilqr_kernels_common.cuh", "ilqr_kernels_linearize.cuh", "ilqr_kernels_backward.cuh", "ilqr_kernels_ltv_mma.cuh",
+HEADERS = ["ilqr_systems.cuh", "ilqr_trig_table.cuh", "ilqr_kernels_common.cuh", "ilqr_kernels_linearize.cuh", "ilqr_kernels_backward.cuh", "ilqr_kernels_ltv_mma.cuh",
            "ilqr_kernels_fused.cuh", "ilqr_kernels_rollout.cuh"]
 DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in HEADERS] + [os.path.join(ROOT, "include", "ilqr_b200.h")]
 OUT = os.path.join(HERE, "libilqr_b200.so")

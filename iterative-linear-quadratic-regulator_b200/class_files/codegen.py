@@ -112,7 +112,7 @@ namespace ilqr {{
 template <typename T>
 struct UserSys {{
     static constexpr int NQ = 0, N = {n}, M = {m};
-    static constexpr bool FIRST_ORDER = false, GENERIC = true;
+    static constexpr bool FIRST_ORDER = false, GENERIC = true, TRIG_TABLE = false;
     ILQR_DEV T time_scalar(int, T) const {{ return T(0); }}
     ILQR_DEV void f(const T *x, const T *u, T *xd) const
     {{

@@ -56,11 +56,11 @@ template <typename T> PendulumSys<T> make_pendulum(const ilqr_problem_t &p)
     return s;
 }
 
-template <typename T, int M> DoublePendulumSys<T, M> make_double(const ilqr_problem_t &p)
+template <typename T, int M, bool TAB = false> DoublePendulumSys<T, M, TAB> make_double(const ilqr_problem_t &p)
 {
     const double g = p.phys[0], m1 = p.phys[1], m2 = p.phys[2], l1 = p.phys[3], l2 = p.phys[4];
     const double d1 = p.phys[5], d2 = p.phys[6], th1 = p.phys[7], th2 = p.phys[8];
-    DoublePendulumSys<T, M> s;
+    DoublePendulumSys<T, M, TAB> s;
     s.c = (T)(m2 * l1 * l2);
     s.m11_0 = (T)((m1 * l1 * l1) / 4 + m2 * l1 * l1 + (m2 * l2 * l2) / 4 + th1 + th2);
     s.m12_0 = (T)((m2 * l2 * l2) / 4 + th2);
@@ -148,6 +148,8 @@ struct Handle {
     size_t smem_backward;     // largest size configured for this handle's backward_kernel instantiation
     int smem_ltv;             // backward_ltv_kernel configured
     int smem_fsplit;          // fused_backward_split_kernel configured (dynamic shared memory above 48 KB)
+    int trig_table;           // the double pendulums' FP64 kernels take sin/cos from the shared-memory table: batches of
+                              // ILQR_TRIG_TABLE_MIN [8192] trajectories or more (pipe-bound kernels)
     int env_fused_split;      // ILQR_FUSED_SPLIT: -1 [auto: at most two blocks per SM, n = 4], 0 never, 1 whenever n = 4
     void *mu_user;            // optional caller buffer for the per-trajectory regularisation (ilqr_set_mu_buffer)
     int ab_blocked;           // ilqr_solve stores the linearization blocked by groups of 32 trajectories (ab_off)
@@ -291,13 +293,27 @@ template <typename T, class F> static int dispatch_model(const Handle *h, F &&f)
     }
     return ILQR_E_INVALID;
 #elif defined(ILQR_FAST_BUILD)
-    if (h->p.model == ILQR_UA_DOUBLE_PENDULUM) return dispatch_integ<T>(h, make_double<T, 1>(h->p), f);
+    if (h->p.model == ILQR_UA_DOUBLE_PENDULUM) {
+        if constexpr (std::is_same_v<T, double>) {
+            if (h->trig_table) return dispatch_integ<T>(h, make_double<T, 1, true>(h->p), f);
+        }
+        return dispatch_integ<T>(h, make_double<T, 1>(h->p), f);
+    }
     return ILQR_E_INVALID;
 #else
     switch (h->p.model) {
     case ILQR_PENDULUM: return dispatch_integ<T>(h, make_pendulum<T>(h->p), f);
-    case ILQR_DOUBLE_PENDULUM: return dispatch_integ<T>(h, make_double<T, 2>(h->p), f);
-    case ILQR_UA_DOUBLE_PENDULUM: return dispatch_integ<T>(h, make_double<T, 1>(h->p), f);
+    // large FP64 batches: the double pendulums' sines and cosines through the shared-memory table (a separate model type)
+    case ILQR_DOUBLE_PENDULUM:
+        if constexpr (std::is_same_v<T, double>) {
+            if (h->trig_table) return dispatch_integ<T>(h, make_double<T, 2, true>(h->p), f);
+        }
+        return dispatch_integ<T>(h, make_double<T, 2>(h->p), f);
+    case ILQR_UA_DOUBLE_PENDULUM:
+        if constexpr (std::is_same_v<T, double>) {
+            if (h->trig_table) return dispatch_integ<T>(h, make_double<T, 1, true>(h->p), f);
+        }
+        return dispatch_integ<T>(h, make_double<T, 1>(h->p), f);
     case ILQR_LTV: {   // forward Euler only (validated in ilqr_create)
         auto sys = make_ltv<T>(h->p);
         auto qc = make_cost<T, 12, 4>(h->p);
@@ -907,6 +923,7 @@ static int create_handle(const ilqr_problem_t *p, UserModule *umod, ilqr_handle_
         h->env_ltv_wpb = (e = getenv("ILQR_LTV_MMA_WPB")) && atoi(e) == 8 ? 8 : 4;
         h->env_fused_minb = (e = getenv("ILQR_FUSED_MINB")) ? atoi(e) : 0;
         h->env_fused_split = (e = getenv("ILQR_FUSED_SPLIT")) ? (atoi(e) != 0) : -1;
+        h->trig_table = p->B >= ((e = getenv("ILQR_TRIG_TABLE_MIN")) ? atol(e) : 8192L);
     }
     h->env_sparse_thresh = (e = getenv("ILQR_SPARSE_THRESH")) ? atol(e) : -1;
     h->env_sparse_all = (e = getenv("ILQR_SPARSE_ALL")) ? atol(e) : -1;

@@ -100,6 +100,9 @@ fused_backward_kernel(const __grid_constant__ Sys sys, const __grid_constant__ C
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 32); mbar_init(&empty[s], 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+#if ILQR_TRIG_TABLE
+    if constexpr (Sys::TRIG_TABLE) trig_table_init();
+#endif
     __syncthreads();
 
     if (wid == 0) {
@@ -455,6 +458,9 @@ fused_backward_split_kernel(const __grid_constant__ Sys sys, const __grid_consta
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 32); mbar_init(&empty[s], 64); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+#if ILQR_TRIG_TABLE
+    if constexpr (Sys::TRIG_TABLE) trig_table_init();
+#endif
     __syncthreads();
 
     if (wid == 2 || wid == 3) {

@@ -12,6 +12,9 @@ __global__ void step_kernel(const __grid_constant__ Sys sys, T dt, int B, int t,
                             const T *__restrict__ x, const T *__restrict__ u, T *__restrict__ xn)
 {
     constexpr int n = Sys::N, m = Sys::M;
+#if ILQR_TRIG_TABLE
+    if constexpr (Sys::TRIG_TABLE) trig_table_init();
+#endif
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     T xv[n], uv[m], out[n];
@@ -102,6 +105,9 @@ __global__ void __launch_bounds__(128, Sys::N <= 4 ? 4 : 1) commit_linearize_ker
 {
     if (gate0 && *gate0 == 0u && *gate1 == 0u) return;   // nobody active now or in the previous iteration
     if (sparse_only && !sparse_now(sa)) return;          // dense iterations: the fused kernel commits and linearizes
+#if ILQR_TRIG_TABLE
+    if constexpr (Sys::TRIG_TABLE) { if (do_linearize) trig_table_init(); }
+#endif
     const int *pos = sparse_now(sa) ? sa.pos : nullptr;  // where K2 will look for A_t, B_t in this iteration
     if (sparse_prev(sa)) {
         // few trajectories ran the previous iteration: the first blocks stride over (t, list entry) pairs, the

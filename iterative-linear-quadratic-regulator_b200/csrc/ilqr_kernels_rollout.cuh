@@ -72,6 +72,9 @@ __global__ void ILQR_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ Sys s
 {
     constexpr int n = Sys::N, m = Sys::M;
     if (gate && *gate == 0u) return;
+#if ILQR_TRIG_TABLE
+    if constexpr (Sys::TRIG_TABLE) trig_table_init();
+#endif
     // Warp w of the grid handles step size (w % n_alpha) of trajectory group (w / n_alpha): the warps that
     // re-read the same nominal trajectory and gains run next to each other, so at large batches those
     // reads come from L1/L2 instead of once per step size from HBM.

@@ -15,6 +15,7 @@
 #ifndef __CUDACC_RTC__      // NVRTC (user-defined systems, class_files/codegen.py) has the device API built in
 #include <cuda_runtime.h>
 #endif
+#include "ilqr_trig_table.cuh"
 
 namespace ilqr {
 
@@ -65,6 +66,46 @@ ILQR_DEV void sincos_t(double x, double *s, double *c)
     // pipe slots per sincos on DADDs)
     *s = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));
     *c = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
+}
+// Table form for the hand-written models' FP64 kernels (ILQR_TRIG_TABLE): x = k pi/256 + r, |r| <= pi/512, with
+// sin, cos of k pi/256 from a 512-entry table in SHARED memory (trig_table_init; the table is exact to half an ulp, the
+// reduction exact as above) and sin r, cos r - 1 from two-term fits: 16 FP64 instructions instead of 22 and no quadrant
+// selects; absolute error 1.1e-16 (scripts/gen_trig_table.py), i.e. the same as sincos_t.  The per-lane table read is an
+// LDS.128 that runs beside the polynomials.
+#ifndef ILQR_TRIG_TABLE
+#define ILQR_TRIG_TABLE 1
+#endif
+#if ILQR_TRIG_TABLE
+__shared__ double2 s_trig_table[ILQR_TRIG_N];
+// every thread of the block, before the first sincos_tab
+ILQR_DEV void trig_table_init()
+{
+    for (int i = threadIdx.x; i < ILQR_TRIG_N; i += blockDim.x) s_trig_table[i] = g_trig_table[i];
+    __syncthreads();
+}
+ILQR_DEV void sincos_tab(double x, double *s, double *c)
+{
+    const double magic = 6755399441055744.0;                 // 1.5 * 2^52: rounds to nearest integer
+    const double t = fma(x, ILQR_TRIG_INV_H, magic);
+    const double2 sc = s_trig_table[__double2loint(t) & (ILQR_TRIG_N - 1)];
+    const double kd = t - magic;
+    double r = fma(-kd, ILQR_TRIG_H_HI, x);
+    r = fma(-kd, ILQR_TRIG_H_LO, r);
+    const double z = r * r;
+    const double sr = fma(r * z, fma(z, ILQR_TRIG_S2, ILQR_TRIG_S1), r);        // sin r
+    const double cm = z * fma(z, ILQR_TRIG_C2, ILQR_TRIG_C1);                   // cos r - 1
+    *s = sc.x + fma(sc.x, cm, sc.y * sr);
+    *c = sc.y + fma(sc.y, cm, -(sc.x * sr));
+}
+#endif
+// the sincos of a model's dynamics: the table form where the kernel has set the table up (FP64, hand-written models)
+template <bool TAB> ILQR_DEV void sincos_m(double x, double *s, double *c)
+{
+#if ILQR_TRIG_TABLE
+    if constexpr (TAB) sincos_tab(x, s, c);
+    else
+#endif
+        sincos_t(x, s, c);
 }
 // FP32 counterpart (optional 1e-4 mode): three-constant Cody-Waite reduction and the cephes sinf/cosf
 // polynomials on [-pi/4, pi/4]; ~2e-7 absolute error for |x| up to ~1e5, no slow path.
@@ -139,6 +180,7 @@ ILQR_DEV float atan2_t(float y, float x) { return atan2f(y, x); }
 
 template <typename T>
 struct PendulumSys {
+    static constexpr bool TRIG_TABLE = false;
     static constexpr int NQ = 1, N = 2, M = 1;
     static constexpr bool FIRST_ORDER = false, GENERIC = false;
     T gl, d;   // g/l, damping
@@ -158,10 +200,20 @@ struct PendulumSys {
     }
 };
 
-template <typename T, int M_>
+// TAB_: sines and cosines through the shared-memory table (FP64 only; the kernels call trig_table_init).  Faster where the
+// kernels are bound by the FP64 pipe (B=131072: rollouts 7.08 -> 6.50 ms, fused backward 5.64 -> 5.48 ms per iteration),
+// slower where one or two warps per sub-partition wait on the table read's latency (B=4096: rollouts 0.502 -> 0.522 ms):
+// a handle uses it from ILQR_TRIG_TABLE_MIN trajectories up (ilqr_b200.cu), in ALL its kernels.
+template <typename T, int M_, bool TAB_ = false>
 struct DoublePendulumSys {
     static constexpr int NQ = 2, N = 4, M = M_;
     static constexpr bool FIRST_ORDER = false, GENERIC = false;
+    static constexpr bool TRIG_TABLE = ILQR_TRIG_TABLE && TAB_ && sizeof(T) == 8;
+    ILQR_DEV static void sc(T x, T *s, T *c)
+    {
+        if constexpr (sizeof(T) == 8) sincos_m<TRIG_TABLE>(x, s, c);
+        else sincos_t(x, s, c);
+    }
     ILQR_DEV T time_scalar(int, T) const { return T(0); }
     // derived constants (host, double precision):
     //   c = m2 l1 l2, m11_0 = m1 l1^2/4 + m2 l1^2 + m2 l2^2/4 + th1 + th2, m12_0 = m22 = m2 l2^2/4 + th2,
@@ -172,8 +224,8 @@ struct DoublePendulumSys {
     {
         const T q1d = x[2], q2d = x[3];
         T s1, c1, s2, c2;
-        sincos_t(x[0], &s1, &c1);
-        sincos_t(x[1], &s2, &c2);
+        sc(x[0], &s1, &c1);
+        sc(x[1], &s2, &c2);
         const T s12 = s1 * c2 + c1 * s2;
         const T m11 = m11_0 + c * c2, m12 = m12_0 + T(0.5) * c * c2, m22 = m12_0;
         const T inv = rcp_t(m11 * m22 - m12 * m12);
@@ -195,8 +247,8 @@ struct DoublePendulumSys {
     {
         const T q1d = x[2], q2d = x[3];
         T s1, c1, s2, c2;
-        sincos_t(x[0], &s1, &c1);
-        sincos_t(x[1], &s2, &c2);
+        sc(x[0], &s1, &c1);
+        sc(x[1], &s2, &c2);
         const T s12 = s1 * c2 + c1 * s2, c12 = c1 * c2 - s1 * s2;
         const T m11 = m11_0 + c * c2, m12 = m12_0 + T(0.5) * c * c2, m22 = m12_0;
         const T inv = rcp_t(m11 * m22 - m12 * m12);
@@ -237,6 +289,7 @@ struct DoublePendulumSys {
 // ------------------------------------------------------------------------------------------
 template <typename T>
 struct LtvSys {
+    static constexpr bool TRIG_TABLE = false;
     static constexpr int NQ = 0, N = 12, M = 4;
     static constexpr bool FIRST_ORDER = true, GENERIC = false;
     T Ac[N][N], E[N][N], Bc[N][M];

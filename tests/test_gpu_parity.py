@@ -55,6 +55,19 @@ def test_backward_forward_pass_vs_reference(name):
         assert rel_err(c, g["cost_a" + tag]) < TOL
 
 
+@pytest.mark.parametrize("name", [n for n in golden_names("derivs_") + golden_names("passes_") if "ua_" in n or "double_" in n])
+def test_table_sincos_variant_vs_reference(monkeypatch, name):
+    """From 8192 trajectories up the double pendulums' FP64 kernels take sin/cos from a 512-entry shared-memory table plus
+    two-term fits (sincos_tab, csrc/ilqr_systems.cuh) -- a separate instantiation of every kernel.  Forced here for the
+    small golden cases: point functions and single passes against the unmodified reference's vectors at the same bounds
+    as the polynomial form."""
+    monkeypatch.setenv("ILQR_TRIG_TABLE_MIN", "1")
+    if name.startswith("derivs_"):
+        test_point_functions_vs_reference(name)
+    else:
+        test_backward_forward_pass_vs_reference(name)
+
+
 def _solve_case(name):
     from class_files.iLQR_class import iLQR
     g = load_golden(name)
@@ -448,6 +461,8 @@ def test_fused_linearize_backward_is_bit_identical(monkeypatch, oracle, kind, in
     monkeypatch.setenv("ILQR_SPARSE", "0")
     monkeypatch.setenv("ILQR_FUSED_MINB", minb)
     monkeypatch.setenv("ILQR_FUSED_SPLIT", split)
+    if minb in ("4", "5"):                                        # the large-batch forms run with the table sincos
+        monkeypatch.setenv("ILQR_TRIG_TABLE_MIN", "1")
     for fused in ("0", "1"):
         monkeypatch.setenv("ILQR_FUSED", fused)
         res = []
