@@ -113,3 +113,35 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "ilqr_oracle" not in txt and "jaxshim" not in txt, os.path.join(dirpath, f)
+
+
+def test_trig_table_header_is_reproducible_and_accurate(tmp_path):
+    """csrc/ilqr_trig_table.cuh (the table and constants of sincos_tab, the sincos of the large-batch FP64 kernels) is what
+    scripts/gen_trig_table.py writes, and the algorithm it parameterises -- restated here in numpy without FMA -- is
+    within 2.5e-16 of sin and cos for arguments up to 1e3 (the device code, with FMA, measures 1.1e-16)."""
+    import subprocess
+    import sys
+    mp = pytest.importorskip("mpmath")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "iterative-linear-quadratic-regulator_b200", "csrc", "ilqr_trig_table.cuh")
+    committed = open(hdr).read()
+    again = str(tmp_path / "ilqr_trig_table.cuh")
+    subprocess.run([sys.executable, os.path.join(root, "scripts", "gen_trig_table.py"), again], check=True, capture_output=True)
+    assert open(again).read() == committed
+    const = {k: float(v) for k, v in re.findall(r"#define ILQR_TRIG_(\w+) (\S+)", committed)}
+    tab = np.array([[float(a), float(b)] for a, b in re.findall(r"\{(\S+), (\S+)\},", committed)])
+    n = int(const["N"])
+    assert tab.shape == (n, 2) and n == 512
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-40, 40, 20000), rng.uniform(-1e3, 1e3, 5000)])
+    k = np.rint(x * const["INV_H"])
+    r = (x - k * const["H_HI"]) - k * const["H_LO"]
+    z = r * r
+    sr = r + (r * z) * (const["S1"] + z * const["S2"])
+    cm = z * (const["C1"] + z * const["C2"])
+    S, C = tab[k.astype(np.int64) & (n - 1)].T
+    s, c = S + (S * cm + C * sr), C + (C * cm - S * sr)
+    mp.mp.dps = 40
+    es = max(abs(mp.mpf(float(a)) - mp.sin(mp.mpf(float(b)))) for a, b in zip(s, x))
+    ec = max(abs(mp.mpf(float(a)) - mp.cos(mp.mpf(float(b)))) for a, b in zip(c, x))
+    assert es < 2.5e-16 and ec < 2.5e-16, (float(es), float(ec))
