@@ -1,6 +1,7 @@
 // ilqr_systems.cuh -- device-side system definitions (continuous dynamics, analytic Jacobians,
-// integrators, quadratic cost) for the batched iLQR kernels.  sm_100a, CUDA cores only: the
-// per-step matrices are n<=12, m<=4, far below a tensor-core tile (BASELINE.json north_star).
+// integrators, quadratic cost) for the batched iLQR kernels.  sm_100a; FP64 on the CUDA cores -- the per-step matrices
+// are n<=12, m<=4 (BASELINE.json north_star) -- except the n=12 LTV recursion, which runs on FP64 DMMA
+// (ilqr_kernels_ltv_mma.cuh).
 //
 // What each piece replaces in the reference (paths relative to /root/reference/python/):
 //   PendulumSys            class_files/systems/pendulum_sys.py:60-75
