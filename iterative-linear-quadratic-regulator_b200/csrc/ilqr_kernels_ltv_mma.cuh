@@ -18,8 +18,9 @@
 //              product are the B-operands of the next WITHOUT any shuffle:
 //   phase 1   Wt[mt][nt] += MA[mt][ct][e] x V[nt][ct][e]        Wt = (Vaug M)' (16 x 16), 16 DMMAs
 //   phase 2   G[mr][mt]  += MA[mr][nt][e] x Wt[mt][nt][e]       G  = M' V_xx M (16 x 16), 16 DMMAs
-//   phase 3   Q_uu, Q_u, Q_ux, Q_x through the warp's shared-memory patch; every lane factors the 4 x 4 Q_uu (LU with
-//             partial pivoting, as the reference's solve) and lane c solves for column c of K (lane 12: k)   (:109-110)
+//   phase 3   Q_uu, Q_u, Q_ux, Q_x through the warp's shared-memory patch; every lane factors the 4 x 4 Q_uu (the
+//             reference's LU: swap-free fast path, the pivoting routine when a pivot is not its column's largest) and
+//             lane c solves for column c of K (lane 12: k)                                                  (:109-110)
 //   phase 4   Vaug' = [Q_xx ; Q_x'] + [Q_ux' ; Q_u'] K          4 DMMAs straight into the next step's V fragments (:113-114)
 // 36 DMMAs = 9 216 FMA slots for the step's ~6 000 useful FMAs (padding 12 -> 16).  Gains are staged through shared memory
 // and stored as rows of WPB consecutive trajectories, one block barrier per step.  FP64 only (the FP32 mode keeps the
@@ -41,8 +42,7 @@ ILQR_DEV void dmma884(double &c0, double &c1, double a, double b)
 // swap is due, and the return value says whether one was (some |a[i][j]| > |a[j][j]| below a pivot: the caller then
 // repeats the solve with the pivoting routine).  Q_uu = R dt + B' V_xx B is symmetric positive definite up to rounding,
 // so swaps are rare, and ptxas turns the swaps of the general routine -- selects or, written as branches, predicated
-// moves -- into ~120 instructions that issue every step whether or not a swap happens.  While a DMMA occupies the
-// sub-partition nothing else issues (scripts/micro/fp64_dmma.cu), so every instruction removed from the step is time.
+// moves -- into ~120 instructions that issue every step whether or not a swap happens.
 ILQR_DEV bool lu4_solve_nopivot(double (*a)[4], double *b)
 {
     bool swap_due = false;
@@ -70,8 +70,8 @@ ILQR_DEV bool lu4_solve_nopivot(double (*a)[4], double *b)
     return swap_due;
 }
 
-// register cap: ILQR_LTV_MMA_WARPS warps per SM whatever the block size (20: 102 registers, no spills; measured
-// 36.7 / 35.1 / 35.5 / 38.6 ms per pass at B=32768, N=1000 for 16 / 20 / 24 / 32)
+// register cap: ILQR_LTV_MMA_WARPS warps per SM whatever the block size (20: 96 registers and ~120 bytes of spills, still
+// the fastest: 36.1 / 33.0 / 34.9 ms per pass at B=32768, N=1000 for 16 (128 registers, no spills) / 20 / 24)
 #ifndef ILQR_LTV_MMA_WARPS
 #define ILQR_LTV_MMA_WARPS 20
 #endif
@@ -143,9 +143,8 @@ backward_ltv_mma_kernel(const __grid_constant__ LtvSys<double> sys, const __grid
                 }
     }
     // loop invariants of the lane.  Everything a lane does differently from its neighbours is an address or an addend
-    // fixed here, so that the step below is straight-line code: while a DMMA occupies the sub-partition's FP64 pipe (16
-    // cycles) no other instruction issues (scripts/micro/fp64_dmma.cu: DMMAs + integer instructions take the SUM of
-    // their issue times), hence every branch, select and address computation removed from the step is time
+    // fixed here, so that the step below is straight-line code (scripts/micro/fp64_dmma.cu: DMMAs and integer
+    // instructions add up rather than overlap; in this kernel 653 -> 415 instructions per step bought 6 %)
     //   x_t, u_t of the own trajectory: lanes 0..15 fetch one value each, one step ahead, and store x - x_target
     const double *fsrc = lane < n ? X + (size_t)lane * B + b : U + (size_t)((lane - n) & 3) * B + b;
     const size_t fstride = (size_t)(lane < n ? n : m) * B;
