@@ -13,6 +13,7 @@ Cubins are cached under _user_cache/ by content hash.
 import ctypes as C
 import hashlib
 import os
+import re
 
 import numpy as np
 import sympy as sp
@@ -20,6 +21,7 @@ from sympy.printing.c import C99CodePrinter
 
 from . import _cabi
 from . import _nvrtc
+from . import symbolic
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _ROOT = os.path.dirname(_PKG)
@@ -33,6 +35,20 @@ class _Printer(C99CodePrinter):
 
     def __init__(self):
         super().__init__({"user_functions": dict(_FUNCS)})
+        self.loop_local = {}                 # process-wide loop id (symbolic._ALL_LOOPS) -> number within this system
+
+    def _loop(self, gid):
+        return self.loop_local.setdefault(int(gid), len(self.loop_local))
+
+    def _print_Symbol(self, e):
+        m = re.fullmatch(r"wl(\d+)_([ctn])(\w+)", e.name)        # carry / tangent variables of a staged while_loop
+        return f"wl{self._loop(m.group(1))}_{m.group(2)}{m.group(3)}" if m else super()._print_Symbol(e)
+
+    def _print_LoopLeaf(self, e):
+        return f"wl{self._loop(e.args[0])}_c{int(e.args[1])}"
+
+    def _print_LoopTangent(self, e):
+        return f"wl{self._loop(e.args[0])}_t{int(e.args[1])}_{int(e.args[2])}"
 
     def _print_Float(self, e):
         return f"T({float(e)!r})"
@@ -57,32 +73,82 @@ class _Printer(C99CodePrinter):
         return f"pow_t({self._print(b)}, {self._print(p)})"
 
 
-def _trace(system):
+def _trace(system, loops=None):
+    """the three user methods evaluated once on sympy symbols; `loops` (a dict) receives the staged lax.while_loops each
+    method contains (symbolic._Loop), keyed "f" / "l" / "lf"""
     n, m = int(system.n_x), int(system.n_u)
     xs = [sp.Symbol(f"x[{i}]", real=True) for i in range(n)]
     us = [sp.Symbol(f"u[{j}]", real=True) for j in range(m)]
     x, u = np.array(xs, dtype=object), np.array(us, dtype=object)
-    f = np.asarray(system._f_cont_fcn(x, u), dtype=object).reshape(-1)
-    if f.shape[0] != n:
-        raise ValueError(f"_f_cont_fcn must return {n} state derivatives, got {f.shape[0]}")
-    f = [sp.sympify(v) for v in f]
-    l = sp.sympify(np.asarray(system._l_fcn(x, u), dtype=object).reshape(-1)[0])
-    lf = sp.sympify(np.asarray(system._l_f_fcn(x), dtype=object).reshape(-1)[0])
+    loops = {} if loops is None else loops
+    try:
+        symbolic.begin_trace(xs + us)
+        f = np.asarray(system._f_cont_fcn(x, u), dtype=object).reshape(-1)
+        loops["f"] = symbolic.end_trace()
+        if f.shape[0] != n:
+            raise ValueError(f"_f_cont_fcn must return {n} state derivatives, got {f.shape[0]}")
+        f = [sp.sympify(v) for v in f]
+        symbolic.begin_trace(xs + us)
+        l = sp.sympify(np.asarray(system._l_fcn(x, u), dtype=object).reshape(-1)[0])
+        loops["l"] = symbolic.end_trace()
+        symbolic.begin_trace(xs)
+        lf = sp.sympify(np.asarray(system._l_f_fcn(x), dtype=object).reshape(-1)[0])
+        loops["lf"] = symbolic.end_trace()
+    finally:
+        symbolic.end_trace()
     return n, m, xs, us, f, l, lf
 
 
-def _body(pr, assigns, indent="        "):
-    """C statements computing `assigns` = [(lhs, expr)] with shared subexpressions hoisted"""
+def _loop_code(pr, lp, tangents, indent):
+    """One staged lax.while_loop as device code: the carry (and, for the Jacobian functions, its tangents with respect to
+    the base symbols -- forward mode, as jax.jacfwd treats a while_loop) in function-scope variables, advanced by a real
+    loop whose trip count is decided per trajectory by the traced condition."""
+    g, base = lp.id, lp.base
+    act = [i for i in range(len(lp.carry)) if lp.active[i]] if tangents else []
+    tan = {(i, v): sp.Symbol(f"wl{g}_t{i}_{v}", real=True) for i in act for v in range(len(base))}
+    nxt = [sp.Symbol(f"wl{g}_n{i}", real=True) for i in range(len(lp.carry))]
+    ntan = {k: sp.Symbol(f"wl{g}_n{k[0]}_{k[1]}", real=True) for k in tan}
+    names = [pr.doprint(c) for c in lp.carry] + [pr.doprint(t) for t in tan.values()]
+    init = [(pr.doprint(c), e) for c, e in zip(lp.carry, lp.init)]
+    init += [(pr.doprint(tan[i, v]), sp.diff(lp.init[i], base[v])) for (i, v) in tan]
+    step = [(f"const T {pr.doprint(nxt[i])}", b) for i, b in enumerate(lp.body)]
+    for (i, v) in tan:
+        e = sp.diff(lp.body[i], base[v])
+        for j in act:
+            e += sp.diff(lp.body[i], lp.carry[j]) * tan[j, v]
+        step.append((f"const T {pr.doprint(ntan[i, v])}", e))
+    trip = f"wl{pr._loop(g)}_trip"
+    inner = indent + "    "
+    out = [f"{indent}T {', '.join(names)};",
+           f"{indent}{{", _body(pr, init, inner), f"{indent}}}",
+           f"{indent}int {trip} = 0;",
+           f"{indent}for (; {trip} < ILQR_WHILE_MAX && ({pr.doprint(lp.cond)}); ++{trip}) {{",
+           _body(pr, step, inner)]
+    out += [f"{inner}{pr.doprint(c)} = {pr.doprint(nx)};" for c, nx in zip(lp.carry, nxt)]
+    out += [f"{inner}{pr.doprint(tan[k])} = {pr.doprint(ntan[k])};" for k in tan]
+    out += [f"{indent}}}",
+            # a loop that never ends on the device would hang the GPU: past the cap the results are NaN, which no line
+            # search accepts
+            f"{indent}if ({trip} >= ILQR_WHILE_MAX) {{ " + " ".join(f"{nm} = T(__int_as_float(0x7fffffff));" for nm in names)
+            + " }"]
+    return "\n".join(out)
+
+
+def _body(pr, assigns, indent="        ", loops=(), tangents=False):
+    """C statements computing `assigns` = [(lhs, expr)] with shared subexpressions hoisted; `loops`: the staged
+    while_loops the expressions read, emitted first"""
     exprs = [e for _, e in assigns]
     repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("w_"), optimizations="basic") if exprs else ([], [])
-    out = [f"{indent}const T {pr.doprint(s)} = {pr.doprint(e)};" for s, e in repl]
+    out = [_loop_code(pr, lp, tangents, indent) for lp in loops]
+    out += [f"{indent}const T {pr.doprint(s)} = {pr.doprint(e)};" for s, e in repl]
     out += [f"{indent}{lhs} = {pr.doprint(e)};" for (lhs, _), e in zip(assigns, red)]
     return "\n".join(out)
 
 
 def generate_header(system):
     """-> (header text, n, m).  See csrc/ilqr_systems.cuh for how UserSys/UserCost are used."""
-    n, m, xs, us, f, l, lf = _trace(system)
+    loops = {}
+    n, m, xs, us, f, l, lf = _trace(system, loops)
     pr = _Printer()
     Ac = [[sp.diff(f[i], xs[j]) for j in range(n)] for i in range(n)]
     Bc = [[sp.diff(f[i], us[j]) for j in range(m)] for i in range(n)]
@@ -93,21 +159,25 @@ def generate_header(system):
     lux = [[sp.diff(lu[i], xs[j]) for j in range(n)] for i in range(m)]          # jacfwd(grad_u l)_x, system_base.py:216
     lfx = [sp.diff(lf, v) for v in xs]
     lfxx = [[sp.diff(lfx[i], xs[j]) for j in range(n)] for i in range(n)]
-    f_only = _body(pr, [(f"xd[{i}]", f[i]) for i in range(n)])
+    f_only = _body(pr, [(f"xd[{i}]", f[i]) for i in range(n)], loops=loops["f"])
     f_jac = _body(pr, [(f"xd[{i}]", f[i]) for i in range(n)] +
                   [(f"Ac[{i}][{j}]", Ac[i][j]) for i in range(n) for j in range(n)] +
-                  [(f"Bc[{i}][{j}]", Bc[i][j]) for i in range(n) for j in range(m)])
+                  [(f"Bc[{i}][{j}]", Bc[i][j]) for i in range(n) for j in range(m)], loops=loops["f"], tangents=True)
+    # (a while_loop inside a cost would need second derivatives through the loop: symbolic.LoopTangent.fdiff raises)
     expand = _body(pr, [(f"lx[{i}]", lx[i]) for i in range(n)] + [(f"lu[{j}]", lu[j]) for j in range(m)] +
                    [(f"lxx[{i}][{j}]", lxx[i][j]) for i in range(n) for j in range(n)] +
                    [(f"luu[{i}][{j}]", luu[i][j]) for i in range(m) for j in range(m)] +
-                   [(f"lux[{i}][{j}]", lux[i][j]) for i in range(m) for j in range(n)])
+                   [(f"lux[{i}][{j}]", lux[i][j]) for i in range(m) for j in range(n)], loops=loops["l"], tangents=True)
     term = _body(pr, [(f"g[{i}]", lfx[i]) for i in range(n)] +
-                 [(f"H[{i}][{j}]", lfxx[i][j]) for i in range(n) for j in range(n)])
-    stage = _body(pr, [("const T value", l)])
-    terminal = _body(pr, [("const T value", lf)])
+                 [(f"H[{i}][{j}]", lfxx[i][j]) for i in range(n) for j in range(n)], loops=loops["lf"], tangents=True)
+    stage = _body(pr, [("const T value", l)], loops=loops["l"])
+    terminal = _body(pr, [("const T value", lf)], loops=loops["lf"])
     name = type(system).__name__
     text = f"""// generated by class_files/codegen.py from {name}._f_cont_fcn/_l_fcn/_l_f_fcn -- do not edit
 #pragma once
+#ifndef ILQR_WHILE_MAX
+#define ILQR_WHILE_MAX 65536      // trip cap of a generated lax.while_loop (results are NaN beyond it)
+#endif
 namespace ilqr {{
 template <typename T>
 struct UserSys {{

@@ -9,7 +9,8 @@ call Python, so this package traces the same three methods ONCE, symbolically: w
 they receive arrays of sympy symbols and return sympy expressions, from which class_files/codegen.py derives
 the analytic Jacobians/Hessians and generates the device code.  Only what dynamics/cost definitions use is
 provided: elementwise math, array construction, @ / dot, small linear solves, data-dependent selects (where / maximum /
-minimum / clip).
+minimum / clip) and the structured control flow of `jax.lax` (`lax.cond`, `select`, `switch`, `fori_loop`, `scan`, and
+`while_loop` with a data-dependent trip count, which becomes a real loop in the device code -- see `lax` below).
 """
 import numpy as np
 import sympy as sp
@@ -116,8 +117,7 @@ def transpose(a):
 
 def where(cond, a, b):
     """jnp.where on traced values: a data-dependent SELECT becomes a Piecewise expression, which differentiates branch by
-    branch and is generated as a conditional expression in the device code (the select form of lax.cond; loops with a
-    data-dependent trip count, lax.while_loop, cannot be traced)."""
+    branch and is generated as a conditional expression in the device code (the select form of lax.cond)."""
     def one(c, x, y):
         return sp.Piecewise((sp.sympify(x), c), (sp.sympify(y), True))
     if isinstance(cond, np.ndarray) or isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
@@ -164,3 +164,210 @@ class linalg:
     def norm(a):
         a = _obj(a).reshape(-1)
         return sp.sqrt(np.sum(a * a))
+
+
+def logical_and(a, b):
+    return sp.And(a, b)
+
+
+def logical_or(a, b):
+    return sp.Or(a, b)
+
+
+def logical_not(a):
+    return sp.Not(a)
+
+
+# ------------------------------------------------------------------------------------------ jax.lax
+# The reference's own integrator uses lax.while_loop (system_base.py:139) and a user may write one inside a dynamics
+# function (a Newton or fixed-point iteration with a data-dependent trip count).  Unrolling such a loop into nested
+# selects is exponential for a symbolic tracer, so a while_loop is STAGED instead: cond_fun and body_fun are traced once
+# with fresh symbols for the carry, the loop's results enter the surrounding expressions as opaque leaves (LoopLeaf),
+# and class_files/codegen.py emits a genuine `while` loop in the device code that carries, beside the values, their
+# tangents with respect to x and u (forward mode: T <- (d body / d carry) T + d body / d(x,u)) -- what jax.jacfwd does
+# with a while_loop.  Derivatives of a leaf are the loop's final tangents (LoopTangent).
+class LoopLeaf(sp.Function):
+    """leaf `i` of the final carry of loop `id`, as a function of the trace's base symbols (x..., u...)"""
+
+    @classmethod
+    def eval(cls, *args):
+        return None
+
+    def _eval_is_real(self):
+        return True
+
+    def fdiff(self, argindex=1):
+        lp = _loop_by_id(int(self.args[0]))
+        i, v = int(self.args[1]), argindex - 3
+        if v < 0:
+            raise sp.function.ArgumentIndexError(self, argindex)
+        if not lp.active[i]:
+            return sp.Integer(0)              # a leaf that does not depend on x, u (a trip counter)
+        return LoopTangent(*self.args[:2], sp.Integer(v), *self.args[2:])
+
+
+class LoopTangent(sp.Function):
+    """d LoopLeaf(id, i) / d base symbol v"""
+
+    @classmethod
+    def eval(cls, *args):
+        return None
+
+    def _eval_is_real(self):
+        return True
+
+    def fdiff(self, argindex=1):
+        raise NotImplementedError(
+            "second derivatives through lax.while_loop are not generated: a data-dependent loop may appear in "
+            "_f_cont_fcn (first derivatives) but not inside _l_fcn / _l_f_fcn, whose Hessians the backward pass needs")
+
+
+class _Loop:
+    def __init__(self, ident, base, carry, init, cond, body, rebuild):
+        self.id, self.base, self.carry, self.init, self.cond, self.body = ident, base, carry, init, cond, body
+        # leaves that depend on x, u (directly, through earlier loops, or through another such leaf): fixed point
+        dep = lambda e: bool(e.free_symbols & set(base)) or bool(e.atoms(LoopLeaf))
+        act = [dep(e) for e in init]
+        changed = True
+        while changed:
+            changed = False
+            for i, b in enumerate(body):
+                if not act[i] and (dep(b) or any(act[j] and b.has(c) for j, c in enumerate(carry))):
+                    act[i] = changed = True
+        self.active = act
+        self.leaves = [LoopLeaf(sp.Integer(ident), sp.Integer(i), *base) for i in range(len(carry))]
+        self.result = rebuild(self.leaves)
+
+
+class _Trace:
+    def __init__(self, base):
+        self.base, self.loops, self.depth = list(base), [], 0
+
+
+_TRACE = None
+_ALL_LOOPS = {}          # by a process-wide id (sympy caches derivatives by expression, so ids are never reused);
+                         # the generated code numbers the loops of one system from 0 (codegen._Printer)
+
+
+def _loop_by_id(ident):
+    return _ALL_LOOPS[ident]
+
+
+def begin_trace(base_symbols):
+    """codegen: the symbols every traced expression is a function of; loops met until end_trace() are collected"""
+    global _TRACE
+    _TRACE = _Trace(base_symbols)
+
+
+def end_trace():
+    global _TRACE
+    t, _TRACE = _TRACE, None
+    return t.loops if t is not None else []
+
+
+def _flatten(tree):
+    """-> (leaves, rebuild): tuples / lists / dicts / object arrays of scalars"""
+    if isinstance(tree, (tuple, list)):
+        parts = [_flatten(t) for t in tree]
+        sizes = [len(p[0]) for p in parts]
+
+        def rebuild(leaves, kind=type(tree)):
+            out, o = [], 0
+            for (_, rb), k in zip(parts, sizes):
+                out.append(rb(leaves[o:o + k]))
+                o += k
+            return kind(out)
+        return [l for p in parts for l in p[0]], rebuild
+    if isinstance(tree, dict):
+        keys = list(tree)
+        leaves, rb = _flatten([tree[k] for k in keys])
+        return leaves, lambda lv: dict(zip(keys, rb(lv)))
+    if isinstance(tree, np.ndarray):
+        shape = tree.shape
+
+        def rebuild_arr(leaves):
+            out = np.empty(len(leaves), dtype=object)
+            for i, l in enumerate(leaves):
+                out[i] = l
+            return out.reshape(shape)
+        return [sp.sympify(v) for v in tree.reshape(-1)], rebuild_arr
+    return [sp.sympify(tree)], lambda lv: lv[0]
+
+
+def _select_tree(c, a, b):
+    la, rb = _flatten(a)
+    lb, _ = _flatten(b)
+    if len(la) != len(lb):
+        raise TypeError("lax.cond / select: both branches must return the same structure")
+    return rb([where(c, x, y) for x, y in zip(la, lb)])
+
+
+class lax:
+    """`jax.lax` for traced user methods"""
+
+    @staticmethod
+    def select(pred, on_true, on_false):
+        return where(pred, on_true, on_false)
+
+    @staticmethod
+    def cond(pred, true_fun, false_fun, *operands):
+        """both branches are traced and the results selected leaf by leaf (what lax.cond becomes under vmap as well)"""
+        if isinstance(pred, (bool, np.bool_)):
+            return true_fun(*operands) if pred else false_fun(*operands)
+        return _select_tree(pred, true_fun(*operands), false_fun(*operands))
+
+    @staticmethod
+    def switch(index, branches, *operands):
+        if isinstance(index, (int, np.integer)):
+            return branches[min(max(int(index), 0), len(branches) - 1)](*operands)
+        out = branches[-1](*operands)
+        for i in range(len(branches) - 2, -1, -1):
+            c = sp.Le(sp.sympify(index), i) if i == 0 else sp.Eq(sp.sympify(index), i)
+            out = _select_tree(c, branches[i](*operands), out)
+        return out
+
+    @staticmethod
+    def fori_loop(lower, upper, body_fun, init_val):
+        """static bounds: unrolled at trace time; traced bounds: a while_loop over (i, value)"""
+        if isinstance(lower, (int, np.integer)) and isinstance(upper, (int, np.integer)):
+            val = init_val
+            for i in range(int(lower), int(upper)):
+                val = body_fun(i, val)
+            return val
+        return lax.while_loop(lambda c: c[0] < upper, lambda c: (c[0] + 1, body_fun(c[0], c[1])), (lower, init_val))[1]
+
+    @staticmethod
+    def scan(f, init, xs=None, length=None):
+        """unrolled over the leading axis (trace-time length); -> (carry, stacked ys)"""
+        n = int(length) if xs is None else len(xs)
+        carry, ys = init, []
+        for i in range(n):
+            carry, y = f(carry, None if xs is None else xs[i])
+            ys.append(y)
+        if not ys or ys[0] is None:
+            return carry, None
+        return carry, np.stack([_obj(y) for y in ys])
+
+    @staticmethod
+    def while_loop(cond_fun, body_fun, init_val):
+        """a loop whose trip count depends on the data: staged (see above), a real `while` in the generated code"""
+        t = _TRACE
+        if t is None:
+            raise RuntimeError("lax.while_loop outside a traced System method")
+        if t.depth:
+            raise NotImplementedError("nested lax.while_loop")
+        init, rebuild = _flatten(init_val)
+        ident = len(_ALL_LOOPS)
+        carry = [sp.Symbol(f"wl{ident}_c{i}", real=True) for i in range(len(init))]
+        t.depth += 1
+        try:
+            cond = sp.sympify(cond_fun(rebuild(carry)))
+            body, _ = _flatten(body_fun(rebuild(carry)))
+        finally:
+            t.depth -= 1
+        if len(body) != len(init):
+            raise TypeError("lax.while_loop: body_fun must return the structure of init_val")
+        lp = _Loop(ident, t.base, carry, init, cond, body, rebuild)
+        _ALL_LOOPS[ident] = lp
+        t.loops.append(lp)
+        return lp.result

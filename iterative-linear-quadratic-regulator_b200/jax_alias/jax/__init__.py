@@ -31,14 +31,7 @@ def _no_autodiff(*a, **k):
 grad = jacfwd = jacrev = hessian = _no_autodiff
 
 
-class _Lax:
-    """importable (`from jax import lax`) so that files using it in demo / __main__ code load; loops with data-dependent
-    trip counts cannot be traced symbolically"""
-
-    def __getattr__(self, name):
-        def _untraceable(*a, **k):
-            raise NotImplementedError(f"jax.lax.{name} cannot be traced symbolically; use jnp.where for data-dependent selects")
-        return _untraceable
-
-
-lax = _Lax()
+# jax.lax: cond / select / switch / fori_loop / scan are traced through; while_loop is staged and becomes a real loop in
+# the generated device code (class_files/symbolic.py)
+lax = numpy.lax
+sys.modules[__name__ + ".lax"] = lax

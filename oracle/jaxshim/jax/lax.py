@@ -28,3 +28,11 @@ def while_loop(cond_fun, body_fun, init_val):
     while bool(cond_fun(val)):
         val = body_fun(val)
     return val
+
+
+def cond(pred, true_fun, false_fun, *operands):
+    return true_fun(*operands) if bool(pred) else false_fun(*operands)
+
+
+def select(pred, on_true, on_false):
+    return torch.where(torch.as_tensor(pred), torch.as_tensor(on_true), torch.as_tensor(on_false))

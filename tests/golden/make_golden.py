@@ -81,6 +81,14 @@ def make_system(p, integrator):
         from user_systems import make_cartpole_class
         extra = {k: p[k] for k in ("mc", "mp", "l", "g", "b", "p_max", "w_bar")}
         return make_cartpole_class(System, jnp)(**extra, **common)
+    if p["kind"] == "user_spring":
+        # a user-defined subclass with a lax.while_loop (data-dependent trip count) and a lax.cond in its dynamics: the
+        # reference's jacfwd differentiates THROUGH the loop (system_base.py:204-205)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from jax import lax
+        from class_files.systems.system_base import System
+        from user_systems import make_implicit_spring_class
+        return make_implicit_spring_class(System, jnp, lax)(a=p["a"], ks=p["ks"], **common)
     if p["kind"] == "pendulum":
         from class_files.systems.pendulum_sys import MyPendulum
         return MyPendulum(g=p["g"], l=p["l"], d=p["d"], **common)
@@ -270,6 +278,14 @@ def build_cases():
     cases["user_cartpole_solve_rk4_T1"] = (case_solve, (p_cp, "rk4", 1.0, [0.0, 0.3, 0.0, 0.0], 30, 1e-5))
     cases["user_cartpole_solve_be_T1"] = (case_solve, (p_cp, "backward_euler", 1.0, [0.2, -0.2, 0.0, 0.5], 20, 1e-5))
     cases["user_cartpole_mpc_T0p5"] = (case_mpc, (p_cp, "rk4", "midpoint", 0.5, 4, [0.1, 2.9, 0.0, 0.0], 20, 1e-5))
+    # user-defined subclass with lax.while_loop + lax.cond in the dynamics (tests/user_systems.py)
+    from user_systems import SPRING
+    p_sp = dict(SPRING, kind="user_spring")
+    for i, integ in enumerate(integs):
+        cases[f"user_spring_derivs_{integ}"] = (case_derivs, (p_sp, integ, 320 + i))
+    cases["user_spring_passes_rk4"] = (case_passes, (p_sp, "rk4", 0.6, 330))
+    cases["user_spring_solve_rk4_T1"] = (case_solve, (p_sp, "rk4", 1.0, [0.4, -0.3], 30, 1e-5))
+    cases["user_spring_solve_midpoint_T1"] = (case_solve, (p_sp, "midpoint", 1.0, [-1.0, 0.8], 30, 1e-5))
     for tag, p in (("pend", P_PEND_D), ("double", P_DP_OL), ("ua", P_UA_OL)):
         for i, integ in enumerate(integs):
             cases[f"derivs_{tag}_{integ}"] = (case_derivs, (p, integ, 100 + i))

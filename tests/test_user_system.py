@@ -12,7 +12,7 @@ import pytest
 
 from conftest import ROOT, load_golden, rel_err
 from helpers import UA_OL, cfg2_x0, golden_flow, ua_system
-from user_systems import CARTPOLE, make_cartpole_class, make_user_ua_class
+from user_systems import CARTPOLE, SPRING, make_cartpole_class, make_implicit_spring_class, make_user_ua_class
 
 INTEGRATORS = ("euler", "midpoint", "rk4", "backward_euler")
 TOL = 1e-9
@@ -106,6 +106,72 @@ def test_data_dependent_selects_are_traced_as_conditionals(tmp_path, monkeypatch
     assert (n, m) == (2, 1) and text.count("?") >= 4            # saturation in f and B_c, wall in l, l_x, l_xx
     cubin, names, _, _ = codegen.compile_module(s)
     assert cubin[:4] == b"\x7fELF"
+
+
+def spring(integrator="rk4", dtype="float64"):
+    from class_files import symbolic as jnp
+    from class_files.systems.system_base import System
+    p = SPRING
+    cls = make_implicit_spring_class(System, jnp, jnp.lax)
+    return cls(dt=p["dt"], x_target=np.array(p["x_target"]), Q=np.diag(p["Q"]), R=np.diag(p["R"]), Q_f=np.diag(p["Q_f"]),
+               a=p["a"], ks=p["ks"], integrator=integrator, dtype=dtype)
+
+
+def test_while_loop_is_staged_as_a_device_loop(tmp_path, monkeypatch):
+    """lax.while_loop with a data-dependent trip count (the construct the reference's own integrator uses,
+    system_base.py:139) inside a user's dynamics: one traced body, a real loop in the generated code that carries the
+    forward-mode tangents beside the values, compiled by NVRTC; loop numbering is per system, so the text (and with it
+    the cache key) is reproducible"""
+    from class_files import codegen
+    monkeypatch.setattr(codegen, "CACHE", str(tmp_path))
+    s = spring()
+    text, n, m = codegen.generate_header(s)
+    assert (n, m) == (2, 1)
+    f_only, f_jac = text.split("void f_jac")[0], text.split("void f_jac")[1].split("struct UserCost")[0]
+    assert f_only.count("for (; wl0_trip < ILQR_WHILE_MAX") == 1 and "wl0_t0_0" not in f_only     # values only
+    assert f_jac.count("for (; wl0_trip < ILQR_WHILE_MAX") == 1 and "wl0_t0_0 = wl0_n0_0;" in f_jac
+    assert "wl0_t1_" not in text                                   # the trip counter does not depend on x, u: no tangents
+    assert "?" in f_jac                                            # the lax.cond became a select
+    assert codegen.generate_header(spring())[0] == text            # a second trace prints the same text
+    cubin, names, _, _ = codegen.compile_module(s)
+    assert cubin[:4] == b"\x7fELF" and len(names) == 6
+
+
+def test_lax_control_flow_is_traced():
+    """cond / select / switch / fori_loop / scan of jax.lax on traced values; a while_loop inside a cost is refused
+    with a message (its Hessian would need second derivatives through the loop)"""
+    import sympy as sp
+    from class_files import codegen, symbolic as jnp
+    from class_files.systems.system_base import System
+    lax = jnp.lax
+    x = sp.Symbol("x", real=True)
+    assert lax.fori_loop(0, 3, lambda i, v: v * x + i, 1.0) == ((1.0 * x + 0) * x + 1) * x + 2
+    carry, ys = lax.scan(lambda c, e: (c + e * x, c), 0, jnp.array([1.0, 2.0, 3.0]))
+    assert sp.simplify(carry - 6.0 * x) == 0 and ys.shape == (3,) and sp.simplify(ys[2] - 3.0 * x) == 0
+    both = lax.cond(x > 0, lambda v: (v, jnp.array([v, 2 * v])), lambda v: (-v, jnp.array([0.0, v])), x)
+    assert both[0] == sp.Piecewise((x, x > 0), (-x, True)) and both[1].shape == (2,)
+    assert lax.cond(True, lambda v: v + 1, lambda v: v - 1, x) == x + 1
+    sw = lax.switch(sp.Symbol("k"), [lambda v: v, lambda v: 2 * v, lambda v: 3 * v], x)
+    assert sw.subs(sp.Symbol("k"), 1) == 2 * x and sw.subs(sp.Symbol("k"), 0) == x and sw.subs(sp.Symbol("k"), 2) == 3 * x
+    assert lax.select(x > 1, x, 1.0) == sp.Piecewise((x, x > 1), (1.0, True))
+
+    class LoopInCost(System):
+        def __init__(self):
+            super().__init__(n_x=1, n_u=1, dt=0.01)
+
+        def _f_cont_fcn(self, x, u):
+            return jnp.array([u[0] - x[0]])
+
+        def _l_fcn(self, x, u):
+            y, _ = lax.while_loop(lambda c: (jnp.abs(c[0] * c[0] - x[0]) > 1e-12) & (c[1] < 9),
+                                  lambda c: (0.5 * (c[0] + x[0] / c[0]), c[1] + 1), (x[0], 0))
+            return y + u[0] * u[0]
+
+        def _l_f_fcn(self, x):
+            return x[0] * x[0]
+
+    with pytest.raises(NotImplementedError, match="second derivatives through lax.while_loop"):
+        codegen.generate_header(LoopInCost())
 
 
 def test_shipped_systems_keep_their_device_models():
@@ -320,3 +386,86 @@ def test_user_cartpole_batch_properties_and_fp32():
     s32 = cartpole(dtype="float32")
     g = load_golden("user_cartpole_derivs_rk4")
     assert rel_err(s32.f_x_fcn(g["xs"], g["us"]), g["f_x"], floor=1e-2) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("integ", INTEGRATORS)
+def test_user_while_loop_point_functions_vs_reference(integ):
+    """the implicit-spring pendulum (Newton iteration in a lax.while_loop + a lax.cond in _f_cont_fcn) against the
+    UNMODIFIED reference running the same class body: its jacfwd differentiates through the loop (system_base.py:204-205),
+    the generated device loop carries the same tangents"""
+    g = load_golden(f"user_spring_derivs_{integ}")
+    s = spring(integ)
+    xs, us = g["xs"], g["us"]
+    got = dict(f=s.f_fcn(xs, us), f_x=s.f_x_fcn(xs, us), f_u=s.f_u_fcn(xs, us), l=s.l_fcn(xs, us),
+               l_x=s.l_x_fcn(xs, us), l_xx=s.l_xx_fcn(xs, us), l_f_x=s.l_f_x_fcn(xs))
+    for k, v in got.items():
+        ref = g[k].reshape(np.shape(v))
+        assert rel_err(v, ref, floor=1e-3) < 1e-11, (k, rel_err(v, ref, floor=1e-3))
+    # and the implicit function theorem: d y / d r = 1 / (1 + 3 a y^2) at the converged deflection
+    if integ == "euler":
+        a, ks, dt = SPRING["a"], SPRING["ks"], SPRING["dt"]
+        r = np.sin(xs[:, 0]) + 0.5 * xs[:, 1]
+        y = r / (1 + a * r * r)
+        for _ in range(60):
+            y = y - (y + a * y ** 3 - r) / (1 + 3 * a * y * y)
+        damp = np.where(xs[:, 1] > 0, 0.05, 0.15)
+        A10 = dt * (-9.81 * np.cos(xs[:, 0]) - ks * np.cos(xs[:, 0]) / (1 + 3 * a * y * y))
+        A11 = 1 + dt * (-damp - ks * 0.5 / (1 + 3 * a * y * y))
+        assert np.allclose(got["f_x"][:, 1, 0], A10, rtol=1e-10, atol=1e-12)
+        assert np.allclose(got["f_x"][:, 1, 1], A11, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_user_while_loop_passes_vs_reference():
+    from class_files.iLQR_class import iLQR
+    g = load_golden("user_spring_passes_rk4")
+    s = spring("rk4")
+    N = int(g["N"])
+    sol = iLQR(s, float(g["T"]), g["x0"], np.zeros((1, N)), verbose=False)
+    X_nom, U_nom, c0 = sol.forward_pass(g["x0"], 0.0, sol.X, g["U_nom"], sol.U_ff, sol.K)
+    assert rel_err(X_nom, g["X_nom"]) < 1e-12 and rel_err(c0, g["cost0"]) < 1e-12
+    U_ff, K = sol.backward_pass(g["X_nom"], g["U_nom"])
+    assert rel_err(K, g["K"]) < TOL and rel_err(U_ff, g["U_ff"], floor=1e-6) < TOL
+    for a in (1.0, 0.5, 0.125):
+        tag = str(a).replace(".", "p")
+        Xn, Un, c = sol.forward_pass(g["x0_b"], a, g["X_nom"], g["U_nom"], g["U_ff"], g["K"])
+        assert rel_err(Xn, g[f"X_a{tag}"]) < TOL and rel_err(c, g[f"cost_a{tag}"]) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,integ", [("user_spring_solve_rk4_T1", "rk4"), ("user_spring_solve_midpoint_T1", "midpoint")])
+def test_user_while_loop_solve_vs_reference(name, integ):
+    """every iteration the reference executed, on identical inputs (1e-9), then the full solve's flow and result; and a
+    batch whose members need different trip counts per step"""
+    from class_files.iLQR_class import iLQR
+    g = load_golden(name)
+    s = spring(integ)
+    N = int(g["N"])
+    sol = iLQR(s, float(g["T"]), g["x0"], np.zeros((1, N)), tol=float(g["tol"]), maxiter=int(g["maxiter"]), verbose=False)
+    sol.enable_trace()
+    ref_idx, ref_costs = golden_flow(g)
+    for i in range(len(ref_idx)):
+        U_ff, K = sol.backward_pass(g["it_X"][i], g["it_U"][i])
+        assert rel_err(K, g["it_K"][i]) < 1e-8, (i, rel_err(K, g["it_K"][i]))
+        assert rel_err(U_ff, g["it_U_ff"][i], floor=1e-6) < 1e-8, i
+        if ref_idx[i] < 0:
+            continue
+        Xn, Un, c = sol.forward_pass(g["x0"], 0.5 ** ref_idx[i], g["it_X"][i], g["it_U"][i], g["it_U_ff"][i], g["it_K"][i])
+        X_ref = g["it_X"][i + 1] if i + 1 < len(ref_idx) else g["X"]
+        assert rel_err(Xn, X_ref) < TOL and rel_err(c, ref_costs[i + 1]) < TOL, i
+    X, U, cost = sol.optimize_trajectory()
+    idx, alphas, costs = sol.trace(0)
+    k = min(6, len(ref_idx), len(idx))
+    assert np.array_equal(idx[:k], ref_idx[:k]), (idx, ref_idx)
+    assert np.all(np.abs(costs[:k + 1] - ref_costs[:k + 1]) <= 1e-8 * np.abs(ref_costs[:k + 1]))
+    if np.array_equal(idx, ref_idx):
+        assert rel_err(cost, g["cost"]) < 1e-6 and rel_err(X, g["X"]) < 1e-4
+    # batched: member 0 is the golden's initial state, the others start elsewhere (other trip counts in the same warp)
+    B = 96
+    rng = np.random.default_rng(12)
+    x0 = np.concatenate([np.asarray(g["x0"]).reshape(1, 2), rng.uniform(-2.0, 2.0, (B - 1, 2))])
+    solb = iLQR(s, float(g["T"]), x0, np.zeros((1, N)), tol=float(g["tol"]), maxiter=int(g["maxiter"]), verbose=False)
+    Xb, Ub, cb = solb.optimize_trajectory()
+    assert np.all(np.isfinite(cb))
+    assert rel_err(cb[0], cost) < 1e-12 and rel_err(Xb[0], X) < 1e-12       # a member does not depend on its neighbours

@@ -9,6 +9,7 @@ import math
 
 CARTPOLE = dict(dt=0.01, x_target=[0.0, math.pi, 0.0, 0.0], Q=[1.0, 5.0, 0.1, 0.1], R=[0.1],
                 Q_f=[50.0, 200.0, 10.0, 10.0], mc=1.0, mp=0.2, l=0.5, g=9.81, b=0.1, p_max=1.5, w_bar=0.5)
+SPRING = dict(dt=0.01, x_target=[math.pi, 0.0], Q=[1.0, 0.1], R=[0.5], Q_f=[50.0, 5.0], a=0.8, ks=3.0)
 
 
 def make_cartpole_class(System, jnp):
@@ -106,3 +107,44 @@ def make_saturated_pendulum_class(System, jnp):
             return 0.5 * dx.T @ self.Q_f @ dx
 
     return SaturatedPendulum
+
+
+def make_implicit_spring_class(System, jnp, lax):
+    class ImplicitSpringPendulum(System):
+        """A pendulum whose joint spring is given IMPLICITLY: the deflection y solves y + a y^3 = r(x) and is found by a
+        Newton iteration inside _f_cont_fcn -- a lax.while_loop whose trip count depends on the state (what the
+        reference's own integrator does at system_base.py:139).  lax.cond switches the damping law with the sign of the
+        velocity."""
+
+        def __init__(self, dt, x_target, Q, R, Q_f, a=0.8, ks=3.0, use_jit=True, integrator="rk4", **kw):
+            self.x_target, self.Q, self.R, self.Q_f, self.a, self.ks = x_target, Q, R, Q_f, a, ks
+            super().__init__(n_x=2, n_u=1, dt=dt, use_jit=use_jit, integrator=integrator, **kw)
+
+        def _deflection(self, r):
+            a = self.a
+
+            def cond(c):
+                y, k = c
+                return (jnp.abs(y + a * y * y * y - r) > 1e-13) & (k < 30)
+
+            def body(c):
+                y, k = c
+                return (y - (y + a * y * y * y - r) / (1.0 + 3.0 * a * y * y), k + 1)
+
+            y, _ = lax.while_loop(cond, body, (r / (1.0 + a * r * r), 0))
+            return y
+
+        def _f_cont_fcn(self, x, u):
+            y = self._deflection(jnp.sin(x[0]) + 0.5 * x[1])
+            damp = lax.cond(x[1] > 0.0, lambda w: 0.05 * w, lambda w: 0.15 * w, x[1])
+            return jnp.array([x[1], u[0] - damp - 9.81 * jnp.sin(x[0]) - self.ks * y])
+
+        def _l_fcn(self, x, u):
+            dx = x - self.x_target
+            return (0.5 * dx.T @ self.Q @ dx + 0.5 * u.T @ self.R @ u) * self.dt
+
+        def _l_f_fcn(self, x):
+            dx = x - self.x_target
+            return 0.5 * dx.T @ self.Q_f @ dx
+
+    return ImplicitSpringPendulum
