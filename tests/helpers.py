@@ -137,6 +137,25 @@ def backward_sensitivity(O, p, X, U, n_draws=3, eps=1e-14, seed=11):
     return sK, sU
 
 
+def backward_sensitivity_per_step(O, p, X, U, n_draws=3, eps=1e-14, seed=11):
+    """backward_sensitivity resolved in time: drift of K[t] (relative to max|K[t]|) under the same noise draws.  The
+    recursion runs from t = N-1 down, so an ill-conditioned pass is still well determined over the late steps."""
+    rng = np.random.default_rng(seed)
+    U_ff, K = O.backward_pass(p, X, U)
+    K = np.asarray(K)
+    N = K.shape[0]
+    scale = np.maximum(np.max(np.abs(K.reshape(N, -1)), axis=1), 1e-300)
+    s = np.zeros(N)
+    for d in range(n_draws + 1):
+        if d == n_draws:
+            with O.rounding_variant():
+                _, k2 = O.backward_pass(p, X, U)
+        else:
+            _, k2 = O.backward_pass(p, _perturb(rng, X, eps), _perturb(rng, U, eps))
+        s = np.maximum(s, np.max(np.abs(np.asarray(k2) - K).reshape(N, -1), axis=1) / scale)
+    return s, scale
+
+
 def forward_sensitivity(O, p, x0, alpha, X, U, U_ff, K, n_draws=3, eps=1e-14, seed=13):
     """Drift of (X_new, U_new, cost) of one rollout under 1e-14 noise on x0 and the gains."""
     rng = np.random.default_rng(seed)
