@@ -152,6 +152,7 @@ struct Handle {
                               // ILQR_TRIG_TABLE_MIN [8192] trajectories or more (pipe-bound kernels)
     int env_fused_split;      // ILQR_FUSED_SPLIT: -1 [auto: at most two blocks per SM, n = 4], 0 never, 1 whenever n = 4
     void *mu_user;            // optional caller buffer for the per-trajectory regularisation (ilqr_set_mu_buffer)
+    int env_bulk;             // ILQR_BACKWARD_BULK: bulk-copy ring of the thread-per-trajectory K2 (-1: by batch size)
     int ab_blocked;           // ilqr_solve stores the linearization blocked by groups of 32 trajectories (ab_off)
     int sparse;               // lazy schedule: late iterations index the batch through the active list (SparseArgs)
     int lazy;                 // large batches: lazy multi-wave line search over compacted lists (select_lazy_kernel)
@@ -379,7 +380,7 @@ static int launch_backward_depth(Handle *h, const Cost &qc, const void *X, const
                                  int ab_blocked)
 {
     constexpr int L = n * n + n * m + n + m;
-    const size_t smem = (size_t)DEPTH * L * bs * sizeof(T);
+    const size_t smem = (size_t)DEPTH * L * bs * sizeof(T) + (size_t)DEPTH * (bs / 32) * 8;     // ring + its mbarriers
     if (smem > h->smem_backward) {          // a handle uses ONE instantiation (fixed model, dtype, batch)
         cudaError_t e = cudaFuncSetAttribute(backward_kernel<Cost, T, n, m, DEPTH, bs>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
@@ -400,13 +401,17 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
     SparseArgs sa;
     std::memset(&sa, 0, sizeof sa);
     if (sparse) sa = *sparse;
+    // thread-per-trajectory kernel: with the blocked linearization and whole warps of trajectories a warp's step arrives
+    // by bulk copies (ab_blocked = 2, see backward_kernel); large batches by default (HBM bound), ILQR_BACKWARD_BULK=0/1
+    const int ab_lanes = ab_blocked;
+    if (ab_blocked && h->p.B % 32 == 0 && (h->env_bulk >= 0 ? h->env_bulk != 0 : h->p.B >= 32768)) ab_blocked = 2;
     if (h->umod) {
         // the generic thread-per-trajectory scan, ring depth / block size by state dimension and batch as below
         const int n = h->p.n, m = h->p.m, L = n * n + n * m + n + m;
         const bool large = n <= 4 && h->p.B > 32768;
         const int depth = n > 4 ? 2 : (large ? 4 : 8), bs = large ? 64 : 32;
         const int which = large ? ILQR_UK_BACKWARD_LARGE : ILQR_UK_BACKWARD_SMALL;
-        const size_t smem = (size_t)depth * L * bs * (h->p.dtype == ILQR_F64 ? 8 : 4);
+        const size_t smem = (size_t)depth * L * bs * (h->p.dtype == ILQR_F64 ? 8 : 4) + (size_t)depth * (bs / 32) * 8;
         if (smem > h->smem_backward) {
             cudaError_t e = cudaFuncSetAttribute((const void *)h->umod->k[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) { h->last_cuda = (int)e; return ILQR_E_CUDA; }
@@ -436,7 +441,7 @@ static int launch_backward(Handle *h, const void *X, const void *U, const void *
                 const int items = both ? (int)sa.thresh : h->p.B;
                 backward_n4m1_lanes_kernel<T, DEPTH><<<grid_for(items, SLOTS), 32, smem, st>>>(
                     qc, h->p.N, h->p.B, (const T *)X, (const T *)U, (const T *)A, (const T *)Bd, (T *)K, (T *)k, active,
-                    gate, (const T *)mu, sl, ab_blocked);
+                    gate, (const T *)mu, sl, ab_lanes);
                 ILQR_CHECK_LAUNCH(h);
                 if (!both) return ILQR_OK;
                 sa.only = 1;
@@ -929,6 +934,7 @@ static int create_handle(const ilqr_problem_t *p, UserModule *umod, ilqr_handle_
     h->env_sparse_all = (e = getenv("ILQR_SPARSE_ALL")) ? atol(e) : -1;
     h->sparse = (e = getenv("ILQR_SPARSE")) ? atoi(e) != 0 : 1;
     h->ab_blocked = (e = getenv("ILQR_AB_BLOCKED")) ? atoi(e) != 0 : 1;
+    h->env_bulk = (e = getenv("ILQR_BACKWARD_BULK")) ? atoi(e) : -1;
     h->n_first = first_wave_size(p->B, cnt);
     h->spec_cap = spec_capacity(p->B, h->n_first, cnt);
     default_waves(h);

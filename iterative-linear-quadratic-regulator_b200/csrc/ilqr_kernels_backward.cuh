@@ -24,24 +24,24 @@ ILQR_DEV void cp_async(void *smem_dst, const void *gsrc)
 ILQR_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING> ILQR_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
-// rows of one ring stage: A (n*n), Bd (n*m), x (n), u (m); element [row][tid] (filled by backward_kernel's issue())
+// rows of one ring stage: A (n*n), Bd (n*m), x (n), u (m); `stage` points at this thread's element of row 0, rows are
+// `bd` elements apart (filled by backward_kernel's issue())
 template <int bd, typename T, int n, int m>
 ILQR_DEV void bwd_read(BwdIn<T, n, m> &d, const T *stage)
 {
-    const int tid = threadIdx.x;
     int row = 0;
 #pragma unroll
     for (int i = 0; i < n; ++i)
 #pragma unroll
-        for (int j = 0; j < n; ++j, ++row) d.A[i][j] = stage[row * bd + tid];
+        for (int j = 0; j < n; ++j, ++row) d.A[i][j] = stage[row * bd];
 #pragma unroll
     for (int i = 0; i < n; ++i)
 #pragma unroll
-        for (int j = 0; j < m; ++j, ++row) d.Bd[i][j] = stage[row * bd + tid];
+        for (int j = 0; j < m; ++j, ++row) d.Bd[i][j] = stage[row * bd];
 #pragma unroll
-    for (int i = 0; i < n; ++i, ++row) d.x[i] = stage[row * bd + tid];
+    for (int i = 0; i < n; ++i, ++row) d.x[i] = stage[row * bd];
 #pragma unroll
-    for (int j = 0; j < m; ++j, ++row) d.u[j] = stage[row * bd + tid];
+    for (int j = 0; j < m; ++j, ++row) d.u[j] = stage[row * bd];
 }
 
 // One step of the reverse scan (iLQR_class.py:92-119) on the inputs `cur` = (A_t, B_t, x_t, u_t): updates the value
@@ -187,39 +187,80 @@ __global__ void __launch_bounds__(BS) backward_kernel(const __grid_constant__ Co
         b = sa.cur[b];                                                   // A_t, B_t stay at the list position (K1)
     }
     if (b >= B) return;
-    if (active && !active[b]) return;
-    constexpr int stage_elems = L * BS, R = n * n + n * m;
+    constexpr int stage_elems = L * BS, R = n * n + n * m, W = BS / 32;
+    // A ring stage holds one chunk per warp, [warp][row][lane]: the thread's element of row i is wbase[i * 32].
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wbase = warp * L * 32 + lane;
+    // BULK form (ab_blocked == 2: blocked A_t, B_t, B a multiple of 32, chosen by the host; dense iterations only).  In
+    // the blocked layout the R rows of [A_t | B_t] of a warp's 32 trajectories are ONE contiguous chunk (R * 32 elements)
+    // and each row of x_t, u_t is 32 contiguous elements: an elected lane fetches the warp's step with 1 + n + m bulk
+    // copies (cp.async.bulk -- the TMA unit -- SASS UBLKCP) that complete on a per-(stage, warp) mbarrier, instead of
+    // L eight-byte LDGSTS per thread.  Every lane of the warp stays in the loop (stores masked by `valid`).
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + DEPTH * stage_elems) + warp;   // [stage][W]
+    const bool bulk = ab_blocked == 2 && !sparse_now(sa);
+    bool valid = true;
+    if (bulk) {
+        valid = !active || active[b] != 0;
+        if (!__any_sync(0xffffffffu, valid)) return;
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < DEPTH; ++s) mbar_init(bars + s * W, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    } else if (active && !active[b]) {
+        return;
+    }
     // Sources of the ring: timesteps are requested in strictly decreasing order, so each is a pointer that steps
     // back by a fixed stride.  In the solver's blocked layout (ab_off) the R rows of [A_t | B_t] of one trajectory are
     // 32 elements apart: ONE pointer with compile-time offsets serves all of them (the index arithmetic of 25 copies
     // per step used to be 60 % of the kernel's instructions).
-    const T *pab = ab_blocked ? A + ab_off(R, N - 1, 0, cAB, B) : nullptr;
+    const int c0 = bulk ? (cAB & ~31) : cAB, b0 = bulk ? (b & ~31) : b;            // bulk: the warp's first column
+    const T *pab = ab_blocked ? A + ab_off(R, N - 1, 0, c0, B) : nullptr;
     const size_t ab_dec = (((size_t)B + 31) >> 5) * R * 32;
-    const T *px = X + (size_t)(N - 1) * n * B + b, *pu = U + (size_t)(N - 1) * m * B + b;
+    const T *px = X + (size_t)(N - 1) * n * B + b0, *pu = U + (size_t)(N - 1) * m * B + b0;
     const size_t sB = (size_t)B;
     auto issue = [&](T *stage, int t) {
-        T *dst = stage + threadIdx.x;
+        T *dst = stage + wbase;
         if (ab_blocked) {
 #pragma unroll
-            for (int i = 0; i < R; ++i) cp_async<sizeof(T)>(dst + i * BS, pab + i * 32);
+            for (int i = 0; i < R; ++i) cp_async<sizeof(T)>(dst + i * 32, pab + i * 32);
             pab -= ab_dec;
         } else {
 #pragma unroll
-            for (int i = 0; i < n * n; ++i) cp_async<sizeof(T)>(dst + i * BS, A + ((size_t)t * n * n + i) * B + cAB);
+            for (int i = 0; i < n * n; ++i) cp_async<sizeof(T)>(dst + i * 32, A + ((size_t)t * n * n + i) * B + cAB);
 #pragma unroll
-            for (int i = 0; i < n * m; ++i) cp_async<sizeof(T)>(dst + (n * n + i) * BS, Bd + ((size_t)t * n * m + i) * B + cAB);
+            for (int i = 0; i < n * m; ++i) cp_async<sizeof(T)>(dst + (n * n + i) * 32, Bd + ((size_t)t * n * m + i) * B + cAB);
         }
 #pragma unroll
-        for (int i = 0; i < n; ++i) cp_async<sizeof(T)>(dst + (R + i) * BS, px + i * sB);
+        for (int i = 0; i < n; ++i) cp_async<sizeof(T)>(dst + (R + i) * 32, px + i * sB);
 #pragma unroll
-        for (int i = 0; i < m; ++i) cp_async<sizeof(T)>(dst + (R + n + i) * BS, pu + i * sB);
+        for (int i = 0; i < m; ++i) cp_async<sizeof(T)>(dst + (R + n + i) * 32, pu + i * sB);
         px -= n * sB;
         pu -= m * sB;
     };
+    auto issue_bulk = [&](int s) {                                       // lane 0 of each warp
+        T *dst = ring + s * stage_elems + warp * L * 32;
+        unsigned long long *bar = bars + s * W;
+        mbar_arrive_expect_tx(bar, (unsigned)(L * 32 * sizeof(T)));
+        bulk_load(dst, pab, (unsigned)(R * 32 * sizeof(T)), bar);
 #pragma unroll
-    for (int s = 0; s < DEPTH; ++s) {
-        if (N - 1 - s >= 0) issue(ring + s * stage_elems, N - 1 - s);
-        cp_async_commit();
+        for (int i = 0; i < n; ++i) bulk_load(dst + (R + i) * 32, px + i * sB, (unsigned)(32 * sizeof(T)), bar);
+#pragma unroll
+        for (int i = 0; i < m; ++i) bulk_load(dst + (R + n + i) * 32, pu + i * sB, (unsigned)(32 * sizeof(T)), bar);
+        pab -= ab_dec;
+        px -= n * sB;
+        pu -= m * sB;
+    };
+    if (bulk) {
+        if (lane == 0)
+            for (int s = 0; s < DEPTH && N - 1 - s >= 0; ++s) issue_bulk(s);
+    } else {
+#pragma unroll
+        for (int s = 0; s < DEPTH; ++s) {
+            if (N - 1 - s >= 0) issue(ring + s * stage_elems, N - 1 - s);
+            cp_async_commit();
+        }
     }
     const T mu_b = mu ? mu[b] : T(0);                                    // regularisation (RegArgs), 0 in the reference
     T Vx[n], Vxx[n][n];
@@ -239,20 +280,30 @@ __global__ void __launch_bounds__(BS) backward_kernel(const __grid_constant__ Co
     }
     BwdIn<T, n, m> cur;
     int stage = 0;
+    unsigned phase = 0;
     for (int t = N - 1; t >= 0; --t) {
-        cp_async_wait<DEPTH - 1>();                                       // the group holding step t has landed
-        bwd_read<BS>(cur, ring + stage * stage_elems);
+        if (bulk) mbar_wait(bars + stage * W, phase);                     // the warp's chunk of step t has landed
+        else cp_async_wait<DEPTH - 1>();                                  // the group holding step t has landed
+        bwd_read<32>(cur, ring + stage * stage_elems + wbase);
+        if (bulk) {
+            __syncwarp();                                                 // every lane has its copy: refill the stage at once
+            if (lane == 0 && t - DEPTH >= 0) issue_bulk(stage);
+        }
         T Kt[m][n], kt[m];
         riccati_step<Cost, T, n, m>(qc, cur, mu_b, Vx, Vxx, Kt, kt);
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < m; ++j) {
+            for (int j = 0; j < m; ++j) {
 #pragma unroll
-            for (int i = 0; i < n; ++i) K[(((size_t)t * m + j) * n + i) * B + b] = Kt[j][i];
-            k[((size_t)t * m + j) * B + b] = kt[j];
+                for (int i = 0; i < n; ++i) K[(((size_t)t * m + j) * n + i) * B + b] = Kt[j][i];
+                k[((size_t)t * m + j) * B + b] = kt[j];
+            }
         }
-        if (t - DEPTH >= 0) issue(ring + stage * stage_elems, t - DEPTH);
-        cp_async_commit();
-        stage = (stage + 1 == DEPTH) ? 0 : stage + 1;
+        if (!bulk) {
+            if (t - DEPTH >= 0) issue(ring + stage * stage_elems, t - DEPTH);
+            cp_async_commit();
+        }
+        if (++stage == DEPTH) { stage = 0; phase ^= 1u; }
     }
 }
 

@@ -111,4 +111,45 @@ ILQR_DEV void reg_on_success(const RegArgs &rg, int b)
     mu[b] = next < (T)rg.mu_min ? T(0) : next;
 }
 
+// ---- mbarrier (shared::cta) -------------------------------------------------------------------------------------------
+ILQR_DEV void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+// release: the caller's earlier shared-memory writes are visible to whoever observes the phase complete
+ILQR_DEV void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+// acquire: spin until the phase of the given parity has completed (a fresh barrier passes parity 1 at once)
+ILQR_DEV void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(a),
+                 "r"(parity)
+                 : "memory");
+}
+
+// ---- bulk asynchronous copies (the TMA unit's linear form) ---------------------------------------------------------
+// the arriving thread announces how many bytes the copies it is about to issue will deliver to the barrier's phase
+ILQR_DEV void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+// one contiguous chunk global -> shared (16-byte aligned on both sides, size a multiple of 16); completion is counted in
+// bytes on `bar`
+ILQR_DEV void bulk_load(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+                 "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
 }  // namespace ilqr

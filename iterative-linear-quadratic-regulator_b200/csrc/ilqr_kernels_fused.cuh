@@ -12,28 +12,7 @@
 
 namespace ilqr {
 
-// ---- mbarrier (shared::cta) -------------------------------------------------------------------------------------------
-ILQR_DEV void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-// release: the caller's earlier shared-memory writes are visible to whoever observes the phase complete
-ILQR_DEV void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-// acquire: spin until the phase of the given parity has completed (a fresh barrier passes parity 1 at once)
-ILQR_DEV void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-                 "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
-                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(a),
-                 "r"(parity)
-                 : "memory");
-}
+// (mbarrier helpers: ilqr_kernels_common.cuh)
 
 // Thread-per-trajectory form.  One block = one group of 32 trajectories
 // (lane = trajectory) = 1 consumer warp + NP producer warps.  Producer p owns the scan steps i = N-1-t with

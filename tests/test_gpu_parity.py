@@ -308,6 +308,37 @@ def test_backward_variants_agree(monkeypatch):
     assert rel_err(res["1"][1], g["it_K"][3]) < TOL
 
 
+@pytest.mark.parametrize("kind,dtype", [("ua", "float64"), ("double", "float64"), ("pendulum", "float64"), ("ua", "float32")])
+def test_backward_bulk_copy_ring_is_exact(monkeypatch, kind, dtype):
+    """thread-per-trajectory Riccati kernel of the two-kernel path: a warp's step fetched by bulk copies onto an mbarrier
+    (cp.async.bulk, ILQR_BACKWARD_BULK=1: the default from 32768 trajectories up) against the per-thread cp.async ring --
+    same arithmetic on the same data, so BIT FOR BIT, in a solve with staggered convergence (inactive lanes, whole
+    inactive warps), regularisation retries, a warm-started re-solve and backward_pass(); a batch that is not a
+    multiple of 32 silently keeps the per-thread ring"""
+    from class_files.iLQR_class import iLQR
+    golden = {"ua": "solve_ua_rk4_T1_b0", "double": "solve_double_rk4_T1_b0", "pendulum": "solve_pend_rk4_T1"}[kind]
+    s = system_from_golden(load_golden(golden), dtype=dtype)
+    rng = np.random.default_rng(5)
+    monkeypatch.setenv("ILQR_FUSED", "0")
+    monkeypatch.setenv("ILQR_BACKWARD_LANES", "0")
+    monkeypatch.setenv("ILQR_SPARSE", "0")
+    for B in (1024, 1000):
+        N = 80
+        x0 = cfg2_x0(B, seed=5)[:, :s.n_x] if kind != "pendulum" else rng.uniform(-2, 2, (B, 2))
+        out = {}
+        for bulk in ("0", "1"):
+            monkeypatch.setenv("ILQR_BACKWARD_BULK", bulk)
+            sol = iLQR(s, N * s.dt, x0, np.zeros((s.n_u, N)), tol=1e-2, maxiter=40, verbose=False, reg_factor=10.0)
+            res = _solve_outputs(sol)
+            sol.x_0 = x0 + 0.02
+            res += _solve_outputs(sol)
+            U_ff, K = sol.backward_pass(sol.X, sol.U)
+            out[bulk] = res + [np.array(U_ff), np.array(K)]
+        assert len(np.unique(out["0"][5])) > 1
+        for a, b in zip(out["0"], out["1"]):
+            assert np.array_equal(a, b, equal_nan=True), (B, kind)
+
+
 def test_lazy_wave_line_search_is_exact():
     """The lazy multi-wave schedule used for large batches (compacted lists of trajectories that accepted
     none of the step sizes tried so far) evaluates a subset of the eager schedule's rollouts and must pick

@@ -469,3 +469,26 @@ def test_user_while_loop_solve_vs_reference(name, integ):
     Xb, Ub, cb = solb.optimize_trajectory()
     assert np.all(np.isfinite(cb))
     assert rel_err(cb[0], cost) < 1e-12 and rel_err(Xb[0], X) < 1e-12       # a member does not depend on its neighbours
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["cartpole", "spring"])
+def test_user_system_backward_bulk_copy_ring_is_exact(monkeypatch, which):
+    """the NVRTC-compiled generic Riccati kernel of a user system (state-dependent cost Hessians): its bulk-copy ring
+    (cp.async.bulk + mbarrier, the default from 32768 trajectories up, forced here) against the per-thread cp.async ring,
+    bit for bit, over a solve with trajectories finishing at different iterations"""
+    from class_files.iLQR_class import iLQR
+    s = cartpole() if which == "cartpole" else spring()
+    B, N = 512, 100
+    rng = np.random.default_rng(21)
+    x0 = rng.uniform(-0.5, 0.5, (B, s.n_x))
+    out = {}
+    for bulk in ("0", "1"):
+        monkeypatch.setenv("ILQR_BACKWARD_BULK", bulk)
+        sol = iLQR(s, N * 0.01, x0, np.zeros((1, N)), tol=1e-3, maxiter=25, verbose=False)
+        X, U, cost = sol.optimize_trajectory()
+        U_ff, K = sol.backward_pass(X, U)
+        out[bulk] = [np.array(a) for a in (X, U, cost, sol.K, sol.U_ff, sol.iterations, sol.status, U_ff, K)]
+    assert len(np.unique(out["0"][5])) > 1
+    for a, b in zip(out["0"], out["1"]):
+        assert np.array_equal(a, b, equal_nan=True)
