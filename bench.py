@@ -512,8 +512,10 @@ def main():
             large["roofline_backward"]["two_kernel_scan_hbm"] = {
                 "bound": "hbm", "achieved": u["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": u["hbm_frac"],
                 "algorithmic_bytes": u["algorithmic_bytes"],
-                "note": "backward_kernel alone on K1's materialised A_t, B_t (ILQR_FUSED=0): the >= 60 % of HBM "
-                        "roofline north_star asks of the backward pass"}
+                "note": "backward_kernel alone on K1's materialised A_t, B_t (ILQR_FUSED=0; ring filled by cp.async.bulk onto "
+                        "mbarriers): the >= 60 % of HBM roofline north_star asks of the backward pass.  The peak is the driver's "
+                        "measured COPY rate (reads = writes); this kernel reads five times what it writes, so a frac "
+                        "at or slightly above 1 means 'as fast as a device-to-device copy moves the same bytes'"}
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -1,4 +1,5 @@
-// ilqr_kernels_backward.cuh -- K2, the reverse Riccati scan: thread-per-trajectory kernel with a cp.async ring, four-lane
+// ilqr_kernels_backward.cuh -- K2, the reverse Riccati scan: thread-per-trajectory kernel with a shared-memory ring (filled by
+// bulk copies onto mbarriers at large batches, by per-thread cp.async otherwise), four-lane
 // kernel for small batches of n=4/m=1, sixteen-lane kernel for the n=12/m=4 LTV model
 // Part of libilqr_b200.so; included by ilqr_b200.cu only (see the file map at its top).
 #pragma once

@@ -16,6 +16,9 @@ python scripts/ncu_summary.py $out/prof_$tag.ncu-rep --traffic B4096 $out/traffi
 QG_SOLVE_ONLY=1 QG_NO_REPS=1 QG_ITERS=2 ncu --set full --clock-control none -k regex:"rollout|linearize|backward" -c 14 -o /tmp/prof_${tag}_large -f python scripts/quick_gpu.py 131072 500 rk4 > $out/ncu3_$tag.log 2>&1
 python scripts/ncu_summary.py /tmp/prof_${tag}_large.ncu-rep > $out/${tag}_ncu_full_B131072.txt
 python scripts/ncu_summary.py /tmp/prof_${tag}_large.ncu-rep --traffic B131072 $out/traffic_$tag.json
+# the two-kernel path's Riccati scan at B=131072 (bulk-copy ring; the kernel of north_star's HBM target)
+QG_SOLVE_ONLY=1 QG_NO_REPS=1 QG_ITERS=2 ILQR_FUSED=0 ncu --set full --clock-control none -k regex:"backward_kernel" -c 2 -o /tmp/prof_${tag}_k2 -f python scripts/quick_gpu.py 131072 500 rk4 > $out/ncu5_$tag.log 2>&1
+python scripts/ncu_summary.py /tmp/prof_${tag}_k2.ncu-rep > $out/${tag}_ncu_full_K2_B131072.txt
 # config 4 (LTV, n=12, m=4): the sixteen-lane Riccati kernel and the n=12 rollout, incl. the shared-memory counters
 QG_SOLVE_ONLY=1 QG_NO_REPS=1 QG_ITERS=1 QG_ALPHAS=4 ncu --set full --clock-control none --import-source on -k regex:"backward_ltv|rollout" -c 4 -o /tmp/prof_${tag}_ltv -f python scripts/quick_gpu.py 32768 1000 ltv > $out/ncu4_$tag.log 2>&1
 python scripts/ncu_summary.py /tmp/prof_${tag}_ltv.ncu-rep > $out/${tag}_ncu_full_ltv_B32768.txt

@@ -339,6 +339,27 @@ def test_backward_bulk_copy_ring_is_exact(monkeypatch, kind, dtype):
             assert np.array_equal(a, b, equal_nan=True), (B, kind)
 
 
+@pytest.mark.parametrize("B,N", [(32, 1), (64, 3), (96, 9), (4096, 17)])
+def test_backward_bulk_copy_ring_short_horizons(monkeypatch, oracle, B, N):
+    """the bulk-copy ring with horizons shorter than, equal to and just beyond its depth (8 stages at these batch sizes),
+    against the oracle and the per-thread ring"""
+    from class_files.iLQR_class import iLQR
+    monkeypatch.setenv("ILQR_FUSED", "0")
+    monkeypatch.setenv("ILQR_BACKWARD_LANES", "0")
+    x0 = cfg2_x0(B, seed=13)
+    out = {}
+    for bulk in ("0", "1"):
+        monkeypatch.setenv("ILQR_BACKWARD_BULK", bulk)
+        sol = iLQR(ua_system(), N * 0.01, x0, np.zeros((1, N)), maxiter=4, verbose=False)
+        out[bulk] = _solve_outputs(sol)
+    for a, b in zip(out["0"], out["1"]):
+        assert np.array_equal(a, b, equal_nan=True)
+    if B <= 96:
+        ref = oracle.optimize_batch(ua_oracle_problem(oracle, N, maxiter=4), x0, np.zeros((B, 1, N)))
+        assert np.array_equal(out["1"][5], ref["iters"]) and rel_err(out["1"][2], ref["cost"]) < TOL
+        assert rel_err(out["1"][0], ref["X"]) < TOL
+
+
 def test_lazy_wave_line_search_is_exact():
     """The lazy multi-wave schedule used for large batches (compacted lists of trajectories that accepted
     none of the step sizes tried so far) evaluates a subset of the eager schedule's rollouts and must pick
