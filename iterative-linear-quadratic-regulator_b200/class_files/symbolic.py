@@ -219,7 +219,8 @@ class LoopTangent(sp.Function):
     def fdiff(self, argindex=1):
         raise NotImplementedError(
             "second derivatives through lax.while_loop are not generated: a data-dependent loop may appear in "
-            "_f_cont_fcn (first derivatives) but not inside _l_fcn / _l_f_fcn, whose Hessians the backward pass needs")
+            "_f_cont_fcn (first derivatives) but not inside _l_fcn / _l_f_fcn, whose Hessians the backward pass needs "
+            "(the reference cannot either: its grad / hessian are reverse mode, which JAX does not define for while_loop)")
 
 
 class _Loop:
