@@ -339,6 +339,32 @@ def test_backward_bulk_copy_ring_is_exact(monkeypatch, kind, dtype):
             assert np.array_equal(a, b, equal_nan=True), (B, kind)
 
 
+def test_backward_bulk_copy_ring_with_sparse_iterations(monkeypatch):
+    """lazy schedule with active-list iterations on the two-kernel path: the dense iterations run the bulk-copy ring, the
+    sparse ones (decided on the device, inside the same kernel) the per-thread ring over gathered trajectories -- bit for
+    bit what the per-thread ring alone and the eager schedule give"""
+    from class_files.iLQR_class import iLQR
+    B, N = 1024, 80
+    x0 = cfg2_x0(B, seed=5)
+    monkeypatch.setenv("ILQR_FUSED", "0")
+    monkeypatch.setenv("ILQR_BACKWARD_LANES", "0")          # the thread-per-trajectory kernel in dense AND sparse iterations
+    out = {}
+    for name, waves, bulk in (("eager_ring", (), "0"), ("lazy_sparse_ring", (2, 2, 2, 4), "0"), ("lazy_sparse_bulk", (2, 2, 2, 4), "1"),
+                              ("eager_bulk", (), "1")):
+        monkeypatch.setenv("ILQR_BACKWARD_BULK", bulk)
+        sol = iLQR(ua_system(), 0.8, x0, np.zeros((1, N)), tol=1e-2, maxiter=80, verbose=False, reg_factor=10.0)
+        sol.set_linesearch_waves(waves)
+        res = _solve_outputs(sol)
+        sol.x_0 = x0 + 0.02
+        out[name] = res + _solve_outputs(sol)
+    it = out["eager_ring"][5]
+    tail = np.array([(it > k).sum() for k in range(int(it.max()))])
+    assert ((tail > 0) & (tail <= 192)).sum() >= 3          # several iterations ran below the sparse threshold
+    for name in ("lazy_sparse_ring", "lazy_sparse_bulk", "eager_bulk"):
+        for a, b in zip(out["eager_ring"], out[name]):
+            assert np.array_equal(a, b, equal_nan=True), name         # (a warm-started member may diverge to NaN: in every schedule)
+
+
 @pytest.mark.parametrize("B,N", [(32, 1), (64, 3), (96, 9), (4096, 17)])
 def test_backward_bulk_copy_ring_short_horizons(monkeypatch, oracle, B, N):
     """the bulk-copy ring with horizons shorter than, equal to and just beyond its depth (8 stages at these batch sizes),
