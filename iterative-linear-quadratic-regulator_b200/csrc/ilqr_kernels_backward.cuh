@@ -286,12 +286,14 @@ __global__ void __launch_bounds__(BS) backward_kernel(const __grid_constant__ Co
         if (bulk) mbar_wait(bars + stage * W, phase);                     // the warp's chunk of step t has landed
         else cp_async_wait<DEPTH - 1>();                                  // the group holding step t has landed
         bwd_read<32>(cur, ring + stage * stage_elems + wbase);
-        if (bulk) {
-            __syncwarp();                                                 // every lane has its copy: refill the stage at once
-            if (lane == 0 && t - DEPTH >= 0) issue_bulk(stage);
-        }
         T Kt[m][n], kt[m];
         riccati_step<Cost, T, n, m>(qc, cur, mu_b, Vx, Vxx, Kt, kt);
+        if (bulk) {
+            // refill the stage: every lane's shared-memory reads of it have been CONSUMED by the arithmetic above (so they
+            // have completed, not merely been issued, before the copy engine may overwrite the stage)
+            __syncwarp();
+            if (lane == 0 && t - DEPTH >= 0) issue_bulk(stage);
+        }
         if (valid) {
 #pragma unroll
             for (int j = 0; j < m; ++j) {
