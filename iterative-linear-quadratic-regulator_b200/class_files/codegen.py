@@ -27,7 +27,8 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _ROOT = os.path.dirname(_PKG)
 CACHE = os.environ.get("ILQR_USER_CACHE") or os.path.join(_PKG, "_user_cache")
 _FUNCS = {"sin": "sin_t", "cos": "cos_t", "tan": "tan_t", "exp": "exp_t", "log": "log_t", "sqrt": "sqrt_t",
-          "tanh": "tanh_t", "Abs": "abs_t", "atan2": "atan2_t"}
+          "tanh": "tanh_t", "Abs": "abs_t", "atan2": "atan2_t", "atan": "atan_t", "asin": "asin_t", "acos": "acos_t",
+          "sinh": "sinh_t", "cosh": "cosh_t"}
 
 
 class _Printer(C99CodePrinter):

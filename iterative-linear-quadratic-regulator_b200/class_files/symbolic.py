@@ -37,6 +37,10 @@ sin, cos, tan = _elementwise(sp.sin), _elementwise(sp.cos), _elementwise(sp.tan)
 exp, log, sqrt, tanh = _elementwise(sp.exp), _elementwise(sp.log), _elementwise(sp.sqrt), _elementwise(sp.tanh)
 abs = absolute = _elementwise(sp.Abs)            # noqa: A001  (mirrors jnp.abs)
 square = _elementwise(lambda v: v * v)
+arctan, arcsin, arccos = _elementwise(sp.atan), _elementwise(sp.asin), _elementwise(sp.acos)
+sinh, cosh = _elementwise(sp.sinh), _elementwise(sp.cosh)
+# sign as a select (its derivative is 0 on both sides, as jax has it; sympy's own sign differentiates to a DiracDelta)
+sign = _elementwise(lambda v: sp.Piecewise((sp.Integer(1), v > 0), (sp.Integer(-1), v < 0), (sp.Integer(0), True)))
 
 
 def arctan2(y, x):
@@ -115,6 +119,40 @@ def transpose(a):
     return _obj(a).T
 
 
+def reshape(a, shape):
+    return _obj(a).reshape(shape)
+
+
+def zeros_like(a, dtype=None):
+    return zeros(np.shape(a))
+
+
+def ones_like(a, dtype=None):
+    return ones(np.shape(a))
+
+
+def outer(a, b):
+    return np.outer(_obj(a), _obj(b))
+
+
+def cross(a, b):
+    a, b = _obj(a), _obj(b)
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], dtype=object)
+
+
+def trace(a):
+    a = _obj(a)
+    return np.sum(np.array([a[i, i] for i in range(min(a.shape))], dtype=object))
+
+
+def mean(a, axis=None):
+    return np.mean(_obj(a), axis=axis)
+
+
+def prod(a, axis=None):
+    return np.prod(_obj(a), axis=axis)
+
+
 def where(cond, a, b):
     """jnp.where on traced values: a data-dependent SELECT becomes a Piecewise expression, which differentiates branch by
     branch and is generated as a conditional expression in the device code (the select form of lax.cond)."""
@@ -159,6 +197,10 @@ class linalg:
     @staticmethod
     def inv(A):
         return np.array(sp.Matrix(_obj(A).tolist()).inv().tolist(), dtype=object)
+
+    @staticmethod
+    def det(A):
+        return sp.Matrix(_obj(A).tolist()).det(method="berkowitz")
 
     @staticmethod
     def norm(a):

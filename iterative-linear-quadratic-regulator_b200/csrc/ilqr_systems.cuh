@@ -170,6 +170,16 @@ ILQR_DEV double pow_t(double x, double y) { return pow(x, y); }
 ILQR_DEV float pow_t(float x, float y) { return powf(x, y); }
 ILQR_DEV double atan2_t(double y, double x) { return atan2(y, x); }
 ILQR_DEV float atan2_t(float y, float x) { return atan2f(y, x); }
+ILQR_DEV double atan_t(double x) { return atan(x); }
+ILQR_DEV float atan_t(float x) { return atanf(x); }
+ILQR_DEV double asin_t(double x) { return asin(x); }
+ILQR_DEV float asin_t(float x) { return asinf(x); }
+ILQR_DEV double acos_t(double x) { return acos(x); }
+ILQR_DEV float acos_t(float x) { return acosf(x); }
+ILQR_DEV double sinh_t(double x) { return sinh(x); }
+ILQR_DEV float sinh_t(float x) { return sinhf(x); }
+ILQR_DEV double cosh_t(double x) { return cosh(x); }
+ILQR_DEV float cosh_t(float x) { return coshf(x); }
 
 // ------------------------------------------------------------------------------------------
 // Second-order mechanical systems: x = [q, qd], xdot = [qd, qdd(x,u)].  A system provides

@@ -174,6 +174,35 @@ def test_lax_control_flow_is_traced():
         codegen.generate_header(LoopInCost())
 
 
+def _rich():
+    from class_files import symbolic
+    from class_files.systems.system_base import System
+    from user_systems import make_rich_math_class
+    return make_rich_math_class(System, symbolic)()
+
+
+def _rich_numpy_f(xs, us):
+    """the same method body evaluated with numpy as the array namespace"""
+    from user_systems import make_rich_math_class
+    cls = make_rich_math_class(object, np)
+    obj = cls.__new__(cls)
+    return np.stack([np.asarray(cls._f_cont_fcn(obj, x, u), dtype=float) for x, u in zip(xs, us)])
+
+
+def test_wider_jnp_surface_is_generated(tmp_path, monkeypatch):
+    """cross / linalg.det / trace / mean are traced away; arctan, arcsin, sinh, cosh reach the device as their _t overloads;
+    sign is a select; the module compiles"""
+    from class_files import codegen
+    monkeypatch.setattr(codegen, "CACHE", str(tmp_path))
+    s = _rich()
+    text, n, m = codegen.generate_header(s)
+    assert (n, m) == (3, 1)
+    for frag in ("atan_t(", "asin_t(", "sinh_t(", "cosh_t(", "?"):
+        assert frag in text, frag
+    cubin, names, _, _ = codegen.compile_module(s)
+    assert cubin[:4] == b"\x7fELF"
+
+
 def test_shipped_systems_keep_their_device_models():
     s = ua_system()
     assert not s._is_user_defined() and s._device_model()[0] == "ua_double_pendulum"
@@ -492,3 +521,25 @@ def test_user_system_backward_bulk_copy_ring_is_exact(monkeypatch, which):
     assert len(np.unique(out["0"][5])) > 1
     for a, b in zip(out["0"], out["1"]):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_wider_jnp_surface_on_device():
+    """the generated continuous dynamics (euler: f = x + dt f_c) against the SAME method body run with numpy, and the
+    Jacobians against central finite differences"""
+    from class_files import symbolic
+    from class_files.systems.system_base import System
+    from user_systems import make_rich_math_class
+    s = make_rich_math_class(System, symbolic)(integrator="euler")
+    rng = np.random.default_rng(4)
+    xs, us = rng.uniform(-1.5, 1.5, (48, 3)), rng.uniform(-3, 3, (48, 1))
+    xs = xs[np.abs(xs[:, 2]) > 1e-3]                               # away from the kink of sign()
+    us = us[:len(xs)]
+    fc = (s.f_fcn(xs, us) - xs) / 0.01
+    assert np.allclose(fc, _rich_numpy_f(xs, us), rtol=1e-9, atol=1e-11)
+    A, Bm = s.f_x_fcn(xs, us), s.f_u_fcn(xs, us)
+    h = 1e-6
+    for j in range(3):
+        e = np.zeros(3); e[j] = h
+        assert np.allclose(A[:, :, j], (s.f_fcn(xs + e, us) - s.f_fcn(xs - e, us)) / (2 * h), rtol=1e-6, atol=1e-8)
+    assert np.allclose(Bm[:, :, 0], (s.f_fcn(xs, us + h) - s.f_fcn(xs, us - h)) / (2 * h), rtol=1e-6, atol=1e-8)

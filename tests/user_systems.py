@@ -148,3 +148,29 @@ def make_implicit_spring_class(System, jnp, lax):
             return 0.5 * dx.T @ self.Q_f @ dx
 
     return ImplicitSpringPendulum
+
+
+def make_rich_math_class(System, jnp):
+    class RichMath(System):
+        """n = 3, m = 1; exercises the wider jnp surface: cross, linalg.det, arctan, arcsin, sinh, cosh, sign, trace, mean.
+        Written so that the same body runs with numpy as `jnp` (the tests' expected values)."""
+
+        def __init__(self, dt=0.01, use_jit=True, integrator="rk4", **kw):
+            super().__init__(n_x=3, n_u=1, dt=dt, use_jit=use_jit, integrator=integrator, **kw)
+
+        def _f_cont_fcn(self, x, u):
+            c = jnp.cross(jnp.array([x[0], x[1], x[2]]), jnp.array([0.0, 0.0, 1.0]))          # [x1, -x0, 0]
+            M = jnp.array([[1.5 + jnp.cosh(0.2 * x[0]), 0.3 * x[1]], [0.3 * x[1], 2.0]])
+            sat = jnp.arctan(u[0])                                                            # smooth actuator saturation
+            fric = 0.1 * jnp.sign(x[2]) * jnp.sinh(0.3 * x[2]) / jnp.cosh(0.3 * x[2])
+            return jnp.array([c[0] - 0.2 * x[0] + 0.05 * jnp.trace(M),
+                              c[1] - 0.2 * x[1] + jnp.arcsin(0.5 * jnp.sin(x[2])),
+                              (sat - fric) / jnp.linalg.det(M) - 0.1 * jnp.mean(jnp.array([x[0], x[1], x[2]]))])
+
+        def _l_fcn(self, x, u):
+            return (0.5 * (x[0] * x[0] + x[1] * x[1] + 0.1 * x[2] * x[2]) + 0.05 * u[0] * u[0]) * self.dt
+
+        def _l_f_fcn(self, x):
+            return 5.0 * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2])
+
+    return RichMath
