@@ -311,7 +311,7 @@ def test_backward_variants_agree(monkeypatch):
 @pytest.mark.parametrize("kind,dtype", [("ua", "float64"), ("double", "float64"), ("pendulum", "float64"), ("ua", "float32")])
 def test_backward_bulk_copy_ring_is_exact(monkeypatch, kind, dtype):
     """thread-per-trajectory Riccati kernel of the two-kernel path: a warp's step fetched by bulk copies onto an mbarrier
-    (cp.async.bulk, ILQR_BACKWARD_BULK=1: the default from 32768 trajectories up) against the per-thread cp.async ring --
+    (cp.async.bulk, ILQR_BACKWARD_BULK=1: the default from 16384 trajectories up) against the per-thread cp.async ring --
     same arithmetic on the same data, so BIT FOR BIT, in a solve with staggered convergence (inactive lanes, whole
     inactive warps), regularisation retries, a warm-started re-solve and backward_pass(); a batch that is not a
     multiple of 32 silently keeps the per-thread ring"""

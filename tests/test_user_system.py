@@ -504,7 +504,7 @@ def test_user_while_loop_solve_vs_reference(name, integ):
 @pytest.mark.parametrize("which", ["cartpole", "spring"])
 def test_user_system_backward_bulk_copy_ring_is_exact(monkeypatch, which):
     """the NVRTC-compiled generic Riccati kernel of a user system (state-dependent cost Hessians): its bulk-copy ring
-    (cp.async.bulk + mbarrier, the default from 32768 trajectories up, forced here) against the per-thread cp.async ring,
+    (cp.async.bulk + mbarrier, the default from 16384 trajectories up, forced here) against the per-thread cp.async ring,
     bit for bit, over a solve with trajectories finishing at different iterations"""
     from class_files.iLQR_class import iLQR
     s = cartpole() if which == "cartpole" else spring()
