@@ -137,6 +137,127 @@ def test_while_loop_is_staged_as_a_device_loop(tmp_path, monkeypatch):
     assert cubin[:4] == b"\x7fELF" and len(names) == 6
 
 
+_HOST_SHIM = r"""
+// host stand-ins for what the generated model uses from csrc/ilqr_systems.cuh (the device versions are PTX-backed)
+#include <cmath>
+#include <cstring>
+#define ILQR_DEV inline
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+#define DEF1(name, fn) static inline double name(double x) { return fn(x); }
+DEF1(sin_t, std::sin) DEF1(cos_t, std::cos) DEF1(tan_t, std::tan) DEF1(exp_t, std::exp) DEF1(log_t, std::log)
+DEF1(sqrt_t, std::sqrt) DEF1(tanh_t, std::tanh) DEF1(abs_t, std::fabs) DEF1(atan_t, std::atan) DEF1(asin_t, std::asin)
+DEF1(acos_t, std::acos) DEF1(sinh_t, std::sinh) DEF1(cosh_t, std::cosh)
+static inline double pow_t(double x, double y) { return std::pow(x, y); }
+static inline double atan2_t(double y, double x) { return std::atan2(y, x); }
+#include "model.cuh"
+extern "C" void f_jac(const double *x, const double *u, double *xd, double *Ac, double *Bc)
+{
+    constexpr int N = ilqr::UserSys<double>::N, M = ilqr::UserSys<double>::M;
+    ilqr::UserSys<double> s;
+    double A[N][N], B[N][M];
+    s.f_jac(x, u, xd, A, B);
+    std::memcpy(Ac, A, sizeof A);
+    std::memcpy(Bc, B, sizeof B);
+}
+extern "C" void f_only(const double *x, const double *u, double *xd) { ilqr::UserSys<double> s; s.f(x, u, xd); }
+"""
+
+
+def _host_model(system, tmp_path):
+    """the generated model compiled for the HOST (g++), so that its code -- loops and tangents included -- runs on CPU"""
+    import subprocess
+    from class_files import codegen
+    text, n, m = codegen.generate_header(system)
+    (tmp_path / "model.cuh").write_text(text)
+    (tmp_path / "host.cpp").write_text(_HOST_SHIM)
+    so = tmp_path / "libmodel.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", str(tmp_path), "-o", str(so), str(tmp_path / "host.cpp")])
+    lib = C.CDLL(str(so))
+    dp = C.POINTER(C.c_double)
+
+    def f_jac(x, u):
+        x, u = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(u, dtype=np.float64)
+        xd, A, B = np.zeros(n), np.zeros((n, n)), np.zeros((n, m))
+        lib.f_jac(x.ctypes.data_as(dp), u.ctypes.data_as(dp), xd.ctypes.data_as(dp), A.ctypes.data_as(dp), B.ctypes.data_as(dp))
+        return xd, A, B
+
+    def f(x, u):
+        x, u = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(u, dtype=np.float64)
+        xd = np.zeros(n)
+        lib.f_only(x.ctypes.data_as(dp), u.ctypes.data_as(dp), xd.ctypes.data_as(dp))
+        return xd
+    return f, f_jac
+
+
+def test_generated_while_loop_code_runs_on_the_host(tmp_path):
+    """The generated model of the implicit-spring pendulum compiled with g++ and run on the CPU: the staged loop stops where
+    the data says, f and f_jac agree, the loop's forward-mode tangents equal the implicit-function-theorem derivative and
+    central differences, and the lax.cond select switches with the sign of the velocity"""
+    f, f_jac = _host_model(spring(), tmp_path)
+    a, ks = SPRING["a"], SPRING["ks"]
+    rng = np.random.default_rng(8)
+    for _ in range(40):
+        x, u = rng.uniform(-2.5, 2.5, 2), rng.uniform(-2, 2, 1)
+        if abs(x[1]) < 1e-3:
+            continue
+        xd, A, B = f_jac(x, u)
+        assert np.array_equal(xd, f(x, u))
+        r = np.sin(x[0]) + 0.5 * x[1]
+        y = r / (1 + a * r * r)
+        for _ in range(60):
+            y = y - (y + a * y ** 3 - r) / (1 + 3 * a * y * y)
+        damp = 0.05 if x[1] > 0 else 0.15
+        assert np.allclose(xd, [x[1], u[0] - damp * x[1] - 9.81 * np.sin(x[0]) - ks * y], rtol=1e-12, atol=1e-12)
+        dy = 1.0 / (1 + 3 * a * y * y)                                       # implicit function theorem
+        assert np.allclose(A, [[0.0, 1.0], [-9.81 * np.cos(x[0]) - ks * dy * np.cos(x[0]), -damp - ks * dy * 0.5]], rtol=1e-9, atol=1e-11)
+        assert np.allclose(B[:, 0], [0.0, 1.0])
+        for j in range(2):
+            e = np.zeros(2); e[j] = 1e-6
+            assert np.allclose(A[:, j], (f(x + e, u) - f(x - e, u)) / 2e-6, rtol=1e-6, atol=1e-7)
+
+
+def test_two_sequential_while_loops_on_the_host(tmp_path):
+    """a second loop that starts from, and keeps reading, the result of the first: the generated code numbers them 0 and 1,
+    the second loop's tangents chain through the first one's; values against the closed forms, Jacobians against central
+    differences"""
+    from class_files import codegen, symbolic
+    from class_files.systems.system_base import System
+    from user_systems import make_two_loop_class
+    s = make_two_loop_class(System, symbolic, symbolic.lax)()
+    text = codegen.generate_header(s)[0]
+    assert "wl0_trip" in text and "wl1_trip" in text and "wl2_trip" not in text and "wl0_t0_0" in text and "wl1_t0_0" in text
+    assert codegen.compile_module(s)[0][:4] == b"\x7fELF"              # and the device build of the same text (NVRTC)
+    f, f_jac = _host_model(s, tmp_path)
+    rng = np.random.default_rng(15)
+    for _ in range(30):
+        x, u = rng.uniform(-2, 2, 2), rng.uniform(-1, 1, 1)
+        xd, A, B = f_jac(x, u)
+        sq = np.sqrt(1.5 + np.sin(x[0]) + 0.3 * u[0])
+        z = 0.25 * sq
+        for _ in range(400):
+            z = 0.5 * np.cos(sq * z) + 0.1 * x[1]
+        assert np.allclose(xd, [x[1], u[0] - sq * x[0] - (z * z + 2 * z + 3)], rtol=1e-11, atol=1e-12)
+        for j in range(2):
+            e = np.zeros(2); e[j] = 1e-6
+            assert np.allclose(A[:, j], (f(x + e, u) - f(x - e, u)) / 2e-6, rtol=2e-6, atol=1e-7), (x, u, j)
+        assert np.allclose(B[:, 0], (f(x, u + 1e-6) - f(x, u - 1e-6)) / 2e-6, rtol=2e-6, atol=1e-7)
+
+
+def test_generated_code_of_the_wider_jnp_surface_runs_on_the_host(tmp_path):
+    f, f_jac = _host_model(_rich(), tmp_path)
+    rng = np.random.default_rng(4)
+    xs, us = rng.uniform(-1.5, 1.5, (24, 3)), rng.uniform(-3, 3, (24, 1))
+    xs = xs[np.abs(xs[:, 2]) > 1e-3]
+    ref = _rich_numpy_f(xs, us[:len(xs)])
+    for x, u, r in zip(xs, us, ref):
+        xd, A, B = f_jac(x, u)
+        assert np.allclose(xd, r, rtol=1e-12, atol=1e-13)
+        for j in range(3):
+            e = np.zeros(3); e[j] = 1e-6
+            assert np.allclose(A[:, j], (f(x + e, u) - f(x - e, u)) / 2e-6, rtol=1e-6, atol=1e-7)
+        assert np.allclose(B[:, 0], (f(x, u + 1e-6) - f(x, u - 1e-6)) / 2e-6, rtol=1e-6, atol=1e-7)
+
+
 def test_lax_control_flow_is_traced():
     """cond / select / switch / fori_loop / scan of jax.lax on traced values; a while_loop inside a cost is refused
     with a message (its Hessian would need second derivatives through the loop)"""
@@ -543,3 +664,29 @@ def test_wider_jnp_surface_on_device():
         e = np.zeros(3); e[j] = h
         assert np.allclose(A[:, :, j], (s.f_fcn(xs + e, us) - s.f_fcn(xs - e, us)) / (2 * h), rtol=1e-6, atol=1e-8)
     assert np.allclose(Bm[:, :, 0], (s.f_fcn(xs, us + h) - s.f_fcn(xs, us - h)) / (2 * h), rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.gpu
+def test_two_sequential_while_loops_on_device(tmp_path):
+    """the same model on the GPU (euler step: f = x + dt f_c) against its host build, point by point, and a batched solve"""
+    from class_files import symbolic
+    from class_files.iLQR_class import iLQR
+    from class_files.systems.system_base import System
+    from user_systems import make_two_loop_class
+    cls = make_two_loop_class(System, symbolic, symbolic.lax)
+    s = cls(integrator="euler")
+    f, f_jac = _host_model(s, tmp_path)
+    rng = np.random.default_rng(16)
+    xs, us = rng.uniform(-2, 2, (40, 2)), rng.uniform(-1, 1, (40, 1))
+    fx, A, Bm = s.f_fcn(xs, us), s.f_x_fcn(xs, us), s.f_u_fcn(xs, us)
+    for i in range(len(xs)):
+        xd, Ac, Bc = f_jac(xs[i], us[i])
+        assert np.allclose(fx[i], xs[i] + 0.01 * xd, rtol=1e-12, atol=1e-13)
+        assert np.allclose(A[i], np.eye(2) + 0.01 * Ac, rtol=1e-10, atol=1e-12)
+        assert np.allclose(Bm[i], 0.01 * Bc, rtol=1e-10, atol=1e-13)
+    B, N = 64, 60
+    x0 = rng.uniform(-1, 1, (B, 2))
+    sol = iLQR(cls(integrator="rk4"), N * 0.01, x0, np.zeros((1, N)), maxiter=8, verbose=False)
+    c0 = sol.forward_pass(x0, 0.0, np.zeros((B, 2, N + 1)), np.zeros((B, 1, N)), np.zeros((B, 1, N)), np.zeros((B, N, 1, 2)))[2]
+    X, U, cost = sol.optimize_trajectory()
+    assert np.all(np.isfinite(cost)) and np.all(cost <= c0) and np.mean(cost < c0) > 0.9

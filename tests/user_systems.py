@@ -174,3 +174,32 @@ def make_rich_math_class(System, jnp):
             return 5.0 * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2])
 
     return RichMath
+
+
+def make_two_loop_class(System, jnp, lax):
+    class TwoLoops(System):
+        """n = 2, m = 1: two lax.while_loops in sequence -- the second starts from the first one's result and its body
+        reads it again -- and a fori_loop with trace-time bounds; exercises the chain rule through an earlier loop's
+        tangents."""
+
+        def __init__(self, dt=0.01, use_jit=True, integrator="rk4", **kw):
+            super().__init__(n_x=2, n_u=1, dt=dt, use_jit=use_jit, integrator=integrator, **kw)
+
+        def _f_cont_fcn(self, x, u):
+            r = 1.5 + jnp.sin(x[0]) + 0.3 * u[0]                      # in [0.2, 2.8] for |u| <= 1
+            # square root of r by Heron's iteration
+            s, _ = lax.while_loop(lambda c: (jnp.abs(c[0] * c[0] - r) > 1e-14) & (c[1] < 40),
+                                  lambda c: (0.5 * (c[0] + r / c[0]), c[1] + 1), (0.5 * (1.0 + r), 0))
+            # fixed point z = cos(s * z) * 0.5 + 0.1 * x[1], started at s / 4
+            z, _ = lax.while_loop(lambda c: (jnp.abs(c[0] - (0.5 * jnp.cos(s * c[0]) + 0.1 * x[1])) > 1e-14) & (c[1] < 200),
+                                  lambda c: (0.5 * jnp.cos(s * c[0]) + 0.1 * x[1], c[1] + 1), (0.25 * s, 0))
+            p = lax.fori_loop(0, 3, lambda i, v: v * z + (i + 1.0), 0.0)     # Horner: z^2 + 2 z + 3
+            return jnp.array([x[1], u[0] - s * x[0] - p])
+
+        def _l_fcn(self, x, u):
+            return (0.5 * (x[0] * x[0] + 0.1 * x[1] * x[1]) + 0.05 * u[0] * u[0]) * self.dt
+
+        def _l_f_fcn(self, x):
+            return 5.0 * (x[0] * x[0] + x[1] * x[1])
+
+    return TwoLoops
