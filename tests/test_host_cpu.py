@@ -145,3 +145,26 @@ def test_trig_table_header_is_reproducible_and_accurate(tmp_path):
     es = max(abs(mp.mpf(float(a)) - mp.sin(mp.mpf(float(b)))) for a, b in zip(s, x))
     ec = max(abs(mp.mpf(float(a)) - mp.cos(mp.mpf(float(b)))) for a, b in zip(c, x))
     assert es < 2.5e-16 and ec < 2.5e-16, (float(es), float(ec))
+
+
+def test_sass_of_the_shipped_library_has_what_the_design_claims():
+    """the thread-per-trajectory Riccati kernel fills its ring with the TMA unit's linear copies
+    (UBLKCP) completing on mbarriers (SYNCS ... TRANS64), the fused kernel hands its ring over through mbarriers, the LTV
+    Riccati kernel runs on the FP64 tensor cores (DMMA).  Read from the sm_100a cubin inside libilqr_b200.so."""
+    import shutil
+    import subprocess
+    from class_files import _cabi
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", _cabi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    functions = re.split(r"\n\s*Function : ", sass)
+    by = lambda frag: [f for f in functions if frag in f.split("\n", 1)[0]]
+    k2 = by("_ZN4ilqr15backward_kernel")                              # (mangled: not fused_backward_kernel)
+    assert k2 and all("UBLKCP" in f and "SYNCS.ARRIVE.TRANS64" in f and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in f for f in k2)
+    assert all("LDGSTS" in f for f in k2)                              # the per-thread ring is still there (small batches)
+    fused = by("fused_backward")
+    assert fused and all("SYNCS.PHASECHK.TRANS64.TRYWAIT" in f for f in fused)
+    mma = by("backward_ltv_mma_kernel")
+    assert mma and all("DMMA.8x8x4" in f for f in mma)
