@@ -160,6 +160,22 @@ extern "C" void f_jac(const double *x, const double *u, double *xd, double *Ac, 
     std::memcpy(Bc, B, sizeof B);
 }
 extern "C" void f_only(const double *x, const double *u, double *xd) { ilqr::UserSys<double> s; s.f(x, u, xd); }
+extern "C" double cost_expand(double dt, const double *x, const double *u, double *lx, double *lu, double *lxx, double *luu,
+                              double *lux, double *lf, double *lfx, double *lfxx)
+{
+    constexpr int N = ilqr::UserCost<double>::N, M = ilqr::UserCost<double>::M;
+    ilqr::UserCost<double> c;
+    c.dt = dt;
+    double Lxx[N][N], Luu[M][M], Lux[M][N], H[N][N];
+    c.expand(x, u, lx, lu, Lxx, Luu, Lux);
+    c.terminal_expand(x, lfx, H);
+    std::memcpy(lxx, Lxx, sizeof Lxx);
+    std::memcpy(luu, Luu, sizeof Luu);
+    std::memcpy(lux, Lux, sizeof Lux);
+    std::memcpy(lfxx, H, sizeof H);
+    *lf = c.terminal(x);
+    return c.stage(x, u);
+}
 """
 
 
@@ -186,7 +202,39 @@ def _host_model(system, tmp_path):
         xd = np.zeros(n)
         lib.f_only(x.ctypes.data_as(dp), u.ctypes.data_as(dp), xd.ctypes.data_as(dp))
         return xd
+    def cost(x, u):
+        x, u = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(u, dtype=np.float64)
+        o = dict(lx=np.zeros(n), lu=np.zeros(m), lxx=np.zeros((n, n)), luu=np.zeros((m, m)), lux=np.zeros((m, n)),
+                 lf=np.zeros(1), lfx=np.zeros(n), lfxx=np.zeros((n, n)))
+        lib.cost_expand.restype = C.c_double
+        o["l"] = lib.cost_expand(C.c_double(system.dt), x.ctypes.data_as(dp), u.ctypes.data_as(dp),
+                                 *[o[k].ctypes.data_as(dp) for k in ("lx", "lu", "lxx", "luu", "lux", "lf", "lfx", "lfxx")])
+        return o
+    f.cost = cost
     return f, f_jac
+
+
+def test_generated_cost_expansion_runs_on_the_host(tmp_path):
+    """UserCost::stage / expand / terminal / terminal_expand of the cart-pole's barrier cost as GENERATED, compiled for the
+    host: gradients and Hessians (state dependent: the barrier) against central differences of the generated values"""
+    f, _ = _host_model(cartpole(), tmp_path)
+    rng = np.random.default_rng(2)
+    h = 1e-5
+    for _ in range(10):
+        x, u = rng.uniform(-1.2, 1.2, 4), rng.uniform(-2, 2, 1)
+        o = f.cost(x, u)
+        for j in range(4):
+            e = np.zeros(4); e[j] = h
+            op, om = f.cost(x + e, u), f.cost(x - e, u)
+            assert abs(o["lx"][j] - (op["l"] - om["l"]) / (2 * h)) < 1e-7 * max(1.0, abs(o["lx"][j]))
+            assert np.allclose(o["lxx"][:, j], (op["lx"] - om["lx"]) / (2 * h), rtol=1e-6, atol=1e-8)
+            assert np.allclose(o["lux"][:, j], (op["lu"] - om["lu"]) / (2 * h), rtol=1e-6, atol=1e-8)
+            assert abs(o["lfx"][j] - (op["lf"][0] - om["lf"][0]) / (2 * h)) < 1e-6 * max(1.0, abs(o["lfx"][j]))
+            assert np.allclose(o["lfxx"][:, j], (op["lfx"] - om["lfx"]) / (2 * h), rtol=1e-6, atol=1e-7)
+        up, um = f.cost(x, u + h), f.cost(x, u - h)
+        assert abs(o["lu"][0] - (up["l"] - um["l"]) / (2 * h)) < 1e-8 and np.allclose(o["luu"][:, 0], (up["lu"] - um["lu"]) / (2 * h), atol=1e-8)
+    xa, xb = np.array([0.2, 0.1, 0.0, 0.0]), np.array([1.4, 0.1, 0.0, 0.0])
+    assert f.cost(xb, [0.0])["lxx"][0, 0] > 2 * f.cost(xa, [0.0])["lxx"][0, 0]          # the barrier's curvature near the wall
 
 
 def test_generated_while_loop_code_runs_on_the_host(tmp_path):
