@@ -106,7 +106,7 @@ def _loop_code(pr, lp, tangents, indent):
     loop whose trip count is decided per trajectory by the traced condition."""
     g, base = lp.id, lp.base
     act = [i for i in range(len(lp.carry)) if lp.active[i]] if tangents else []
-    tan = {(i, v): sp.Symbol(f"wl{g}_t{i}_{v}", real=True) for i in act for v in range(len(base))}
+    tan = {(i, v): sp.Symbol(f"wl{g}_t{i}_{v}", real=True) for i in act for v in range(len(base)) if lp.nz[i][v]}
     nxt = [sp.Symbol(f"wl{g}_n{i}", real=True) for i in range(len(lp.carry))]
     ntan = {k: sp.Symbol(f"wl{g}_n{k[0]}_{k[1]}", real=True) for k in tan}
     names = [pr.doprint(c) for c in lp.carry] + [pr.doprint(t) for t in tan.values()]
@@ -116,7 +116,8 @@ def _loop_code(pr, lp, tangents, indent):
     for (i, v) in tan:
         e = sp.diff(lp.body[i], base[v])
         for j in act:
-            e += sp.diff(lp.body[i], lp.carry[j]) * tan[j, v]
+            if (j, v) in tan:
+                e += sp.diff(lp.body[i], lp.carry[j]) * tan[j, v]
         step.append((f"const T {pr.doprint(ntan[i, v])}", e))
     trip = f"wl{pr._loop(g)}_trip"
     inner = indent + "    "

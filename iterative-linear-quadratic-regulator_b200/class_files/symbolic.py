@@ -243,8 +243,8 @@ class LoopLeaf(sp.Function):
         i, v = int(self.args[1]), argindex - 3
         if v < 0:
             raise sp.function.ArgumentIndexError(self, argindex)
-        if not lp.active[i]:
-            return sp.Integer(0)              # a leaf that does not depend on x, u (a trip counter)
+        if not lp.nz[i][v]:
+            return sp.Integer(0)              # structurally zero: a trip counter, or a loop that never sees this symbol
         return LoopTangent(*self.args[:2], sp.Integer(v), *self.args[2:])
 
 
@@ -268,16 +268,21 @@ class LoopTangent(sp.Function):
 class _Loop:
     def __init__(self, ident, base, carry, init, cond, body, rebuild):
         self.id, self.base, self.carry, self.init, self.cond, self.body = ident, base, carry, init, cond, body
-        # leaves that depend on x, u (directly, through earlier loops, or through another such leaf): fixed point
-        dep = lambda e: bool(e.free_symbols & set(base)) or bool(e.atoms(LoopLeaf))
-        act = [dep(e) for e in init]
+        # nz[i][v]: can leaf i depend on base symbol v -- directly, through an earlier loop's leaves (their fdiff knows) or
+        # through another leaf of this loop?  A fixed point over the structural zeros of the partial derivatives; only
+        # these (leaf, symbol) pairs get tangent variables in the generated loop (a trip counter gets none at all).
+        L, V = len(carry), len(base)
+        nz = [[sp.diff(init[i], base[v]) != 0 or sp.diff(body[i], base[v]) != 0 for v in range(V)] for i in range(L)]
+        dep = [[sp.diff(body[i], carry[j]) != 0 for j in range(L)] for i in range(L)]
         changed = True
         while changed:
             changed = False
-            for i, b in enumerate(body):
-                if not act[i] and (dep(b) or any(act[j] and b.has(c) for j, c in enumerate(carry))):
-                    act[i] = changed = True
-        self.active = act
+            for i in range(L):
+                for v in range(V):
+                    if not nz[i][v] and any(dep[i][j] and nz[j][v] for j in range(L)):
+                        nz[i][v] = changed = True
+        self.nz = nz
+        self.active = [any(row) for row in nz]
         self.leaves = [LoopLeaf(sp.Integer(ident), sp.Integer(i), *base) for i in range(len(carry))]
         self.result = rebuild(self.leaves)
 

@@ -131,6 +131,7 @@ def test_while_loop_is_staged_as_a_device_loop(tmp_path, monkeypatch):
     assert f_only.count("for (; wl0_trip < ILQR_WHILE_MAX") == 1 and "wl0_t0_0" not in f_only     # values only
     assert f_jac.count("for (; wl0_trip < ILQR_WHILE_MAX") == 1 and "wl0_t0_0 = wl0_n0_0;" in f_jac
     assert "wl0_t1_" not in text                                   # the trip counter does not depend on x, u: no tangents
+    assert "wl0_t0_2" not in text and "wl0_t0_1" in text           # nor does the deflection depend on u (base symbol 2)
     assert "?" in f_jac                                            # the lax.cond became a select
     assert codegen.generate_header(spring())[0] == text            # a second trace prints the same text
     cubin, names, _, _ = codegen.compile_module(s)
