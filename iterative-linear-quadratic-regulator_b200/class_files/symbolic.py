@@ -385,15 +385,20 @@ class lax:
         return lax.while_loop(lambda c: c[0] < upper, lambda c: (c[0] + 1, body_fun(c[0], c[1])), (lower, init_val))[1]
 
     @staticmethod
-    def scan(f, init, xs=None, length=None):
-        """unrolled over the leading axis (trace-time length); -> (carry, stacked ys)"""
-        n = int(length) if xs is None else len(xs)
-        carry, ys = init, []
-        for i in range(n):
-            carry, y = f(carry, None if xs is None else xs[i])
-            ys.append(y)
-        if not ys or ys[0] is None:
+    def scan(f, init, xs=None, length=None, reverse=False):
+        """unrolled over the leading axis (trace-time length); xs and the per-step outputs may be tuples / lists of arrays;
+        -> (carry, stacked ys)"""
+        multi = isinstance(xs, (tuple, list))
+        n = int(length) if xs is None else (len(xs[0]) if multi else len(xs))
+        order = range(n - 1, -1, -1) if reverse else range(n)
+        carry, ys = init, [None] * n
+        for i in order:
+            x_i = None if xs is None else (type(xs)(a[i] for a in xs) if multi else xs[i])
+            carry, ys[i] = f(carry, x_i)
+        if n == 0 or ys[0] is None:
             return carry, None
+        if isinstance(ys[0], (tuple, list)):
+            return carry, type(ys[0])(np.stack([_obj(y[k]) for y in ys]) for k in range(len(ys[0])))
         return carry, np.stack([_obj(y) for y in ys])
 
     @staticmethod

@@ -318,6 +318,8 @@ def test_lax_control_flow_is_traced():
     assert lax.fori_loop(0, 3, lambda i, v: v * x + i, 1.0) == ((1.0 * x + 0) * x + 1) * x + 2
     carry, ys = lax.scan(lambda c, e: (c + e * x, c), 0, jnp.array([1.0, 2.0, 3.0]))
     assert sp.simplify(carry - 6.0 * x) == 0 and ys.shape == (3,) and sp.simplify(ys[2] - 3.0 * x) == 0
+    c2, (ya, yb) = lax.scan(lambda c, e: (c * e[0] + e[1], (c, 2 * c)), 1, (jnp.array([x, 2.0]), jnp.array([1.0, x])), reverse=True)
+    assert sp.expand(c2 - ((1 * 2.0 + x) * x + 1.0)) == 0 and ya.shape == (2,) and ya[1] == 1 and sp.expand(yb[0] - 2 * (2.0 + x)) == 0
     both = lax.cond(x > 0, lambda v: (v, jnp.array([v, 2 * v])), lambda v: (-v, jnp.array([0.0, v])), x)
     assert both[0] == sp.Piecewise((x, x > 0), (-x, True)) and both[1].shape == (2,)
     assert lax.cond(True, lambda v: v + 1, lambda v: v - 1, x) == x + 1
